@@ -1,0 +1,56 @@
+"""Builds the C-ABI shared library ``lib/libpmc_b200.so`` from ``csrc/*.cu`` with nvcc for sm_100a.
+
+nvcc cross-compiles without a GPU, so this runs in the build container; the resulting ``.so`` is
+git-ignored but travels to the GPU box inside the repo snapshot.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(_HERE)
+CSRC = os.path.join(_HERE, "csrc")
+LIB_DIR = os.path.join(_HERE, "lib")
+LIB_PATH = os.path.join(LIB_DIR, "libpmc_b200.so")
+SOURCES = ["api.cu", "chains.cu", "box.cu"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-shared", "-ccbin", "/usr/bin/g++",
+]
+
+
+def _newest_source_mtime() -> float:
+    paths = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, "include", "pmc_b200.h")]
+    return max(os.path.getmtime(p) for p in paths)
+
+
+def find_nvcc() -> str:
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise RuntimeError("nvcc not found: cannot build libpmc_b200.so")
+    return nvcc
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+    """Compile if the library is missing or older than any source. Returns the library path."""
+    if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= _newest_source_mtime():
+        return LIB_PATH
+    os.makedirs(LIB_DIR, exist_ok=True)
+    cmd = [find_nvcc(), *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", LIB_PATH,
+           *[os.path.join(CSRC, s) for s in SOURCES]]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    import sys
+
+    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))

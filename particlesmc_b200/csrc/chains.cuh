@@ -1,0 +1,70 @@
+// chains.cuh -- argument block shared by the host API and the chain-mode kernels.
+#pragma once
+#include <stdint.h>
+
+#include "pmc_b200.h"
+
+namespace pmc {
+
+// Device state of PMC_MODE_CHAINS: M independent systems of N particles each.
+//   x    [M][dim][Npad] float64, wrapped into [0, L]      (SoA: coalesced loads, conflict-free smem)
+//   img  [M][dim][Npad] int32 image counters              (x_unwrapped = x + img * L)
+//   sp   [M][Npad]      uint8 species, 0-based
+//   spids/heads [M][Npad] uint16: SpeciesList (src/utils.jl:31-49), ids grouped by species
+struct ChainArgs {
+    double *x;
+    int32_t *img;
+    uint8_t *sp;
+    uint16_t *spids;
+    uint16_t *heads;
+    const int32_t *spoff;  // [M][PMC_MAX_SPECIES+1]
+    const double *box;     // [M][3]
+    const double *temp;    // [M]
+    double *energy;        // [M] running energy[1]
+    unsigned long long *calls;     // [M][PMC_MAX_MOVES]
+    unsigned long long *accepted;  // [M][PMC_MAX_MOVES]
+    const double *par;             // [ns][ns][PMC_NPAR]
+    const uint16_t *bonds;         // [Npad][PMC_MAX_BONDS], 0xFFFF = none (shared topology)
+    // move pool
+    int32_t n_moves;
+    int32_t mv_kind[PMC_MAX_MOVES];
+    int32_t mv_a[PMC_MAX_MOVES];  // species, 0-based
+    int32_t mv_b[PMC_MAX_MOVES];
+    double mv_cum[PMC_MAX_MOVES];  // cumulative selection probability (normalised)
+    float mv_sigma[PMC_MAX_MOVES];
+    int32_t any_swap;
+    // rng
+    unsigned long long seed;
+    unsigned long long t0;  // index of the first trial of this launch
+    int32_t chain_offset;
+    // shape
+    int32_t N, Npad, ns;
+    long long n_trials;
+    // replay / trace (test hooks)
+    const pmc_trial *replay;
+    pmc_trial *trace;
+    uint8_t *acc_out;
+    double *dE_out;
+    int32_t exact_exp;  // 1: accept iff min(1, exp(-(e2-e1)/T)) > u (reference form); 0: -dE/T > log u
+};
+
+struct EnergyArgs {
+    const double *x;
+    const uint8_t *sp;
+    const double *box;
+    const double *par;
+    const uint16_t *bonds;
+    double *eloc;  // [M][Npad]
+    double *etot;  // [M]
+    int32_t N, Npad, ns;
+};
+
+size_t chain_sweep_smem_bytes(int dim, int Npad, int ns, int threads, bool mol, bool any_swap);
+size_t chain_energy_smem_bytes(int dim, int Npad, int ns, bool mol);
+cudaError_t launch_chain_sweep(int dim, int model, bool mol, bool traced, int M, int threads, size_t smem,
+                               const ChainArgs &a, cudaStream_t st);
+cudaError_t launch_chain_energy(int dim, int model, bool mol, int M, size_t smem, const EnergyArgs &a,
+                                cudaStream_t st);
+cudaError_t configure_chain_kernels(int dim, int model, bool mol, size_t sweep_smem, size_t energy_smem);
+
+}  // namespace pmc

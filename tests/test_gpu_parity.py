@@ -1,0 +1,318 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle.
+
+Tolerances (BASELINE.json north_star): total and local energies within 1e-12 relative of the fp64
+reference arithmetic; accept/reject decisions bit-exact when the same proposals and uniforms are replayed.
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+import particlesmc_b200 as P
+from particlesmc_b200 import _lib as L
+from particlesmc_b200 import models as M
+from particlesmc_b200.device import TRIAL_DTYPE, DeviceContext
+from particlesmc_b200.synthetic import ka_lattice, lattice
+
+pytestmark = pytest.mark.gpu
+
+RTOL_E = 1e-12
+
+
+def zero_based(bonds):
+    return [[j - 1 for j in b] for b in bonds]
+
+
+def rel(a, b):
+    return abs(a - b) / max(abs(b), 1e-300)
+
+
+def assert_local(e_gpu, e_ref):
+    scale = np.maximum(np.abs(e_ref), 1.0)
+    assert np.max(np.abs(e_gpu - e_ref) / scale) < RTOL_E
+
+
+def ka_config(N=1000, seed=0, jitter=0.05):
+    pos, sp, box = ka_lattice(N, 1.2, seed)
+    rng = np.random.default_rng(seed + 100)
+    pos = pos + rng.normal(0.0, jitter, pos.shape)
+    return pos - np.floor(pos / box) * box, sp, box
+
+
+# ---------------------------------------------------------------------------------------------------
+# energies: the reference's known answers + oracle parity
+# ---------------------------------------------------------------------------------------------------
+def test_config0_energy(config0):
+    """test/runtests.jl:22-38 through the device path."""
+    s = P.System(config0["position"], config0["species"], config0["density"], config0["temperature"], P.JBB(),
+                 list_type=P.LinkedList)
+    assert s.N == 1290 and s.d == 2
+    assert abs(P.energy(s) - config0["ref"]) < 1e-6
+    orc = O.OracleSystem(config0["position"], config0["species"], config0["box"], config0["temperature"],
+                         M.MODEL_SMOOTHLJ, M.flatten_model_matrix(M.JBB()), O.LINKEDLIST)
+    assert rel(s.energy[0], orc.energy) < RTOL_E
+    assert_local(P.compute_energy_particle(s), orc.local_energies())
+    assert abs(P.compute_energy_particle(s, 7) - orc.local_energy(6)) < 1e-12 * max(1, abs(orc.local_energy(6)))
+
+
+def test_molecule_energy(molecule):
+    """test/runtests.jl:136-149 through the device path."""
+    s = P.System(molecule["position"], molecule["species"], molecule["molecule"], molecule["density"],
+                 molecule["temperature"], P.Trimer(), molecule["bonds"], list_type=P.LinkedList)
+    assert s.N == 3000 and s.Nmol == 1000
+    assert abs(P.energy(s) - molecule["ref"]) < 1e-6
+    orc = O.OracleSystem(molecule["position"], molecule["species"], molecule["box"], molecule["temperature"],
+                         M.MODEL_KG, M.flatten_model_matrix(M.Trimer()), O.LINKEDLIST,
+                         bonds=zero_based(molecule["bonds"]))
+    assert rel(s.energy[0], orc.energy) < RTOL_E
+    assert_local(P.compute_energy_particle(s), orc.local_energies())
+
+
+@pytest.mark.parametrize("name,d", [("KobAndersen", 3), ("BHHP", 3), ("BHHP", 2), ("JBB", 2)])
+def test_model_energies_vs_oracle(name, d):
+    mm = M.NAMED_MODELS[name]()
+    ns = len(mm)
+    N = 512 if d == 3 else 400
+    fr = [1.0 / ns] * ns
+    pos, sp, box = lattice(N, d, 1.0 if d == 3 else 0.9, seed=4, fractions=fr)
+    pos = pos + np.random.default_rng(5).normal(0, 0.04, pos.shape)
+    s = P.System(pos, sp, N / np.prod(box), 1.0, mm)
+    orc = O.OracleSystem(pos - np.floor(pos / s.box) * s.box, sp, s.box, 1.0, M.model_kind(mm),
+                         M.flatten_model_matrix(mm), O.EMPTYLIST)
+    assert rel(s.energy[0], orc.energy) < RTOL_E
+    assert_local(P.compute_energy_particle(s), orc.local_energies())
+
+
+def test_unwrapped_positions_roundtrip():
+    """Positions outside the box are legal input (src/moves.jl:46-48 never re-wraps) and come back unwrapped."""
+    pos, sp, box = ka_config(216, 2)
+    shift = np.random.default_rng(0).integers(-3, 4, pos.shape) * box
+    par = M.flatten_model_matrix(M.KobAndersen())
+    with DeviceContext(2, 216, 3, 2, M.MODEL_LJ) as ctx:
+        ctx.set_model(par)
+        ctx.upload(np.stack([pos, pos + shift]), np.stack([sp, sp]), box, 1.0)
+        ctx.init_energy()
+        e = ctx.energy()
+        assert rel(e[1], e[0]) < 1e-12
+        back, spb = ctx.download()
+        assert np.allclose(back[1], pos + shift, rtol=0, atol=1e-12)
+        assert np.array_equal(spb[0], sp)
+
+
+def test_initial_overlap_is_an_error():
+    """atoms.jl:53-55: 'Initial configuration has infinite or NaN energy.'"""
+    pos, sp, box = ka_config(216, 1)
+    pos[5] = pos[9]
+    with pytest.raises(ValueError, match="infinite or NaN energy"):
+        P.System(pos, sp, 1.2, 1.0, P.KobAndersen())
+
+
+def test_invalid_arguments_are_errors():
+    with pytest.raises(P.PMCError):
+        DeviceContext(1, 100, 4, 1, M.MODEL_LJ)  # dim 4
+    with DeviceContext(1, 64, 3, 2, M.MODEL_LJ) as ctx:
+        pos, sp, box = ka_config(64, 1)
+        with pytest.raises(P.PMCError, match="pmc_set_model"):
+            ctx.run(10)
+        ctx.set_model(M.flatten_model_matrix(M.KobAndersen()))
+        bad = sp.copy()
+        bad[0] = 3
+        with pytest.raises(P.PMCError, match="species labels"):
+            ctx.upload(pos, bad, box, 1.0)
+        ctx.upload(pos, sp, box, 1.0)
+        with pytest.raises(P.PMCError, match="pmc_set_moves"):
+            ctx.run(10)
+
+
+# ---------------------------------------------------------------------------------------------------
+# decision parity: the production sweep kernel's own proposals replayed by the oracle
+# ---------------------------------------------------------------------------------------------------
+def check_trace(ctx, orcs, pool_labels, n_trials, atol_x=1e-11):
+    tr, acc, dE = ctx.run_traced(n_trials)
+    e_run = ctx.energy()
+    pos, sp = ctx.download()
+    for c, orc in enumerate(orcs):
+        t = tr[c]
+        spA = np.array([pool_labels[m][0] for m in t["move"]], dtype=np.int32)
+        spB = np.array([pool_labels[m][1] for m in t["move"]], dtype=np.int32)
+        o_acc, o_dE, o_E = orc.replay(t["kind"], t["i"], np.maximum(t["j"], 0), spA, spB, t["delta"], t["u"], 1)
+        assert np.array_equal(o_acc, acc[c]), f"chain {c}: {np.count_nonzero(o_acc != acc[c])} decisions differ"
+        fin = np.isfinite(o_dE)
+        assert np.max(np.abs(o_dE[fin] - dE[c][fin]) / np.maximum(1.0, np.abs(o_dE[fin]))) < 1e-11
+        assert rel(e_run[c], orc.energy) < 1e-11
+        opos, osp = orc.state()
+        assert np.array_equal(osp, sp[c])
+        assert np.max(np.abs(opos - pos[c])) < atol_x
+        assert 0 < acc[c].sum() < n_trials
+    return tr, acc
+
+
+def test_trace_parity_kob_andersen():
+    """BASELINE config 1/2 shape: KA N=1000, rho=1.2, Displacement sigma=0.05."""
+    M_ = 3
+    par = M.flatten_model_matrix(M.KobAndersen())
+    cfgs = [ka_config(1000, s) for s in range(M_)]
+    with DeviceContext(M_, 1000, 3, 2, M.MODEL_LJ) as ctx:
+        ctx.set_model(par)
+        ctx.upload(np.stack([c[0] for c in cfgs]), np.stack([c[1] for c in cfgs]), cfgs[0][2], [1.0, 0.5, 2.0])
+        ctx.init_energy()
+        ctx.set_moves([dict(kind="displacement", prob=1.0, sigma=0.05)])
+        ctx.seed(42)
+        orcs = [O.OracleSystem(c[0] - np.floor(c[0] / c[2]) * c[2], c[1], c[2], T, M.MODEL_LJ, par, O.LINKEDLIST)
+                for c, T in zip(cfgs, [1.0, 0.5, 2.0])]
+        for c, o in enumerate(orcs):
+            assert rel(ctx.energy()[c], o.energy) < RTOL_E
+        tr, acc = check_trace(ctx, orcs, {0: (0, 0)}, 3000)
+        # the proposal stream itself: i uniform over particles, delta ~ N(0, sigma^2)
+        assert tr["i"].min() >= 0 and tr["i"].max() < 1000
+        assert abs(tr["delta"].std() - 0.05) < 0.002 and abs(tr["delta"].mean()) < 0.002
+        assert 0.0 <= tr["u"].min() and tr["u"].max() < 1.0
+        calls, accepted = ctx.counters()
+        assert calls[:, 0].tolist() == [3000] * M_ and accepted[:, 0].tolist() == acc.sum(axis=1).tolist()
+
+
+def test_trace_parity_swaps(config0):
+    """test/runtests.jl:93-129 pool on the reference's own ternary configuration."""
+    par = M.flatten_model_matrix(M.JBB())
+    pool = [dict(kind="displacement", prob=0.2, sigma=0.05), dict(kind="swap", prob=0.4, species=(1, 3)),
+            dict(kind="swap", prob=0.4, species=(2, 3))]
+    with DeviceContext(2, 1290, 2, 3, M.MODEL_SMOOTHLJ) as ctx:
+        ctx.set_model(par)
+        ctx.upload(np.stack([config0["position"]] * 2), np.stack([config0["species"]] * 2), config0["box"],
+                   [config0["temperature"], 1.0])
+        ctx.init_energy()
+        ctx.set_moves(pool)
+        ctx.seed(10)
+        orcs = [O.OracleSystem(config0["position"], config0["species"], config0["box"], T, M.MODEL_SMOOTHLJ, par,
+                               O.LINKEDLIST) for T in (config0["temperature"], 1.0)]
+        tr, acc = check_trace(ctx, orcs, {0: (0, 0), 1: (1, 3), 2: (2, 3)}, 2500)
+        kinds = np.bincount(tr["move"].ravel(), minlength=3) / tr.size
+        assert np.all(np.abs(kinds - [0.2, 0.4, 0.4]) < 0.03)
+        sw = tr["kind"] == 1
+        assert acc[sw].sum() > 0  # some swaps are accepted at these temperatures
+        _, sp = ctx.download()
+        assert np.bincount(sp[0])[1:].tolist() == [600, 330, 360]
+
+
+def test_trace_parity_molecules(molecule):
+    """BASELINE config 5 shape: 1000 trimers, bonded FENE + non-bonded WCA, Displacement."""
+    par = M.flatten_model_matrix(M.Trimer())
+    with DeviceContext(1, 3000, 3, 3, M.MODEL_KG, molecules=True) as ctx:
+        ctx.set_model(par)
+        ctx.set_bonds(zero_based(molecule["bonds"]))
+        ctx.upload(molecule["position"], molecule["species"], molecule["box"], molecule["temperature"])
+        ctx.init_energy()
+        ctx.set_moves([dict(kind="displacement", prob=1.0, sigma=0.05)])
+        ctx.seed(10)
+        orc = O.OracleSystem(molecule["position"], molecule["species"], molecule["box"], molecule["temperature"],
+                             M.MODEL_KG, par, O.LINKEDLIST, bonds=zero_based(molecule["bonds"]))
+        check_trace(ctx, [orc], {0: (0, 0)}, 2000)
+
+
+def test_replay_of_injected_proposals():
+    """Proposals and uniforms recorded elsewhere (here: numpy) replayed through the sweep kernel with the
+    reference's acceptance arithmetic: decisions bit-exact vs the oracle running the reference's revert."""
+    rng = np.random.default_rng(7)
+    pos, sp, box = ka_config(512, 3)
+    par = M.flatten_model_matrix(M.KobAndersen())
+    n = 4000
+    tr = np.zeros((1, n), dtype=TRIAL_DTYPE)
+    tr["kind"] = 0
+    tr["i"] = rng.integers(0, 512, n)
+    tr["j"] = -1
+    tr["delta"] = rng.normal(0, 0.08, (1, n, 3))
+    tr["u"] = rng.random(n)
+    is_swap = rng.random(n) < 0.2
+    A_ids, B_ids = np.nonzero(sp == 1)[0], np.nonzero(sp == 2)[0]
+    orc = O.OracleSystem(pos - np.floor(pos / box) * box, sp, box, 0.8, M.MODEL_LJ, par, O.LINKEDLIST)
+    with DeviceContext(1, 512, 3, 2, M.MODEL_LJ) as ctx:
+        ctx.set_model(par)
+        ctx.upload(pos, sp, box, 0.8)
+        ctx.init_energy()
+        # swaps must name a current (A, B) pair: generate them against the evolving oracle state in chunks
+        done = 0
+        while done < n:
+            m = min(500, n - done)
+            cur = orc.state()[1]
+            A_ids, B_ids = np.nonzero(cur == 1)[0], np.nonzero(cur == 2)[0]
+            blk = tr[0, done:done + m]
+            first_swap = True
+            for q in range(m):
+                if is_swap[done + q] and first_swap:  # one swap per chunk keeps the id lists valid
+                    blk["kind"][q], blk["move"][q] = 1, 1
+                    blk["i"][q], blk["j"][q] = rng.choice(A_ids), rng.choice(B_ids)
+                    blk["delta"][q] = 0.0
+                    first_swap = False
+            spA = np.where(blk["kind"] == 1, 1, 0).astype(np.int32)
+            spB = np.where(blk["kind"] == 1, 2, 0).astype(np.int32)
+            o_acc, o_dE, _ = orc.replay(blk["kind"], blk["i"], np.maximum(blk["j"], 0), spA, spB, blk["delta"],
+                                        blk["u"], 0)
+            g_acc, g_dE = ctx.replay(blk.reshape(1, m))
+            assert np.array_equal(o_acc, g_acc[0])
+            fin = np.isfinite(o_dE)
+            assert np.max(np.abs(o_dE[fin] - g_dE[0][fin]) / np.maximum(1.0, np.abs(o_dE[fin]))) < 1e-11
+            done += m
+        gpos, gsp = ctx.download()
+        opos, osp = orc.state()
+        assert np.array_equal(gsp[0], osp)
+        assert np.max(np.abs(gpos[0] - opos)) < 1e-11
+        assert rel(ctx.energy()[0], orc.energy) < 1e-10
+        assert rel(ctx.total_energy()[0], orc.total_energy()) < RTOL_E
+
+
+# ---------------------------------------------------------------------------------------------------
+# stream properties: launch splitting and sharding do not change the chains
+# ---------------------------------------------------------------------------------------------------
+def _ka_ctx(n_chains, chain_offset=0, first=0, threads=0):
+    par = M.flatten_model_matrix(M.KobAndersen())
+    cfgs = [ka_config(216, s) for s in range(first, first + n_chains)]
+    ctx = DeviceContext(n_chains, 216, 3, 2, M.MODEL_LJ, chain_offset=chain_offset, threads=threads)
+    ctx.set_model(par)
+    ctx.upload(np.stack([c[0] for c in cfgs]), np.stack([c[1] for c in cfgs]), cfgs[0][2], 1.0)
+    ctx.init_energy()
+    ctx.set_moves([dict(kind="displacement", prob=0.8, sigma=0.07), dict(kind="swap", prob=0.2, species=(1, 2))])
+    ctx.seed(99)
+    return ctx
+
+
+def test_split_launches_equal_one_launch():
+    with _ka_ctx(3) as a, _ka_ctx(3) as b:
+        a.run(1500)
+        for n in (700, 1, 799):
+            b.run(n)
+        pa, sa = a.download()
+        pb, sb = b.download()
+        assert np.array_equal(pa, pb) and np.array_equal(sa, sb)
+        assert np.array_equal(a.energy(), b.energy())
+        assert np.array_equal(a.counters()[1], b.counters()[1])
+
+
+def test_sharded_chains_equal_unsharded():
+    """Chains keyed by GLOBAL index: ranks holding [0,2) and [2,4) reproduce a single 4-chain context."""
+    with _ka_ctx(4) as full, _ka_ctx(2, chain_offset=0, first=0) as r0, _ka_ctx(2, chain_offset=2, first=2) as r1:
+        for c in (full, r0, r1):
+            c.run(1200)
+        pf, sf = full.download()
+        p0, s0 = r0.download()
+        p1, s1 = r1.download()
+        assert np.array_equal(pf[:2], p0) and np.array_equal(pf[2:], p1)
+        assert np.array_equal(sf[:2], s0) and np.array_equal(sf[2:], s1)
+
+
+@pytest.mark.parametrize("threads", [32, 64, 256])
+def test_cta_size_does_not_change_decisions(threads):
+    with _ka_ctx(2) as a, _ka_ctx(2, threads=threads) as b:
+        _, acc_a, _ = a.run_traced(800)
+        _, acc_b, _ = b.run_traced(800)
+        assert np.array_equal(acc_a, acc_b)
+        assert np.max(np.abs(a.download()[0] - b.download()[0])) < 1e-12
+
+
+def test_energy_bookkeeping_after_long_run():
+    with _ka_ctx(4) as ctx:
+        ctx.run(50 * 216)
+        e_run, e_tot = ctx.energy(), ctx.total_energy()
+        assert np.max(np.abs(e_run - e_tot) / np.abs(e_tot)) < 1e-11
+        calls, acc = ctx.counters()
+        assert np.all(calls.sum(axis=1) == 50 * 216)
+        rate = acc[:, 0] / calls[:, 0]
+        assert np.all((rate > 0.05) & (rate < 0.95))
