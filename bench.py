@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""bench.py -- attempted Metropolis moves per second on the BASELINE.json workloads.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload chains|box] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...   (N > 1)
+
+One "step" = one pass of the hot path over the whole batch: every chain advanced by --sweeps sweeps
+(1 sweep = N_particles attempted moves) in one pmc_run call.  Prints ONE JSON line (rank 0).
+
+  value      device-resident throughput: state already in HBM, K steps bracketed by CUDA events on the
+             launch stream (max over ranks), L2 flushed between steps.
+  e2e        the same metric through the C ABI with HOST buffers: every step uploads all chain states from
+             pinned host memory (pmc_upload + pmc_init_energy), runs the sweeps and downloads energies and
+             full states (pmc_energy + pmc_download).
+  roofline   pair-evaluation roofline of the sweep kernel (FP64 CUDA-core pipe): achieved =
+             moves/s x P x F with P = reference-equivalent candidate pairs per move and F flops per pair,
+             against the DFMA burst peak measured in this run (MEASURED_PEAKS.json has no FP64 figure).
+  cpu_baseline  the oracle (C restatement of the reference CPU algorithm, one chain per host thread) timed
+             on this box's cores on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "attempted MC moves/sec"
+UNIT = "moves/s"
+
+# algorithmic work per attempted Displacement, reference-equivalent
+WORK = {
+    "chains": dict(P=2000.0, F=21.0 + 9.0 * 0.079),   # KA N=1000: 3x3x3 cells = whole box, old + new position
+    "box": dict(P=1032.0, F=21.0 + 9.0 * 0.152),      # KA N=2^20: 27-cell stencil ~516 candidates, x2
+}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="chains", choices=["chains", "box"])
+    ap.add_argument("--chains", type=int, default=4096, help="chains PER GPU (weak scaling)")
+    ap.add_argument("--particles", type=int, default=0, help="particles per system (default 1000 / 2^20)")
+    ap.add_argument("--sweeps", type=int, default=0, help="sweeps per step (default 10 chains / 2 box)")
+    ap.add_argument("--equil", type=int, default=100, help="untimed equilibration sweeps from the lattice")
+    ap.add_argument("--threads", type=int, default=0, help="CTA size of the sweep kernel (0 = library default)")
+    ap.add_argument("--temperature", type=float, default=1.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-sweeps", type=int, default=40)
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        pw = [float(r[2]) for r in self.rows if len(r) >= 7 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
+
+
+def workload_config(args):
+    from particlesmc_b200.synthetic import ka_lattice
+    if args.workload == "chains":
+        N = args.particles or 1000
+        sweeps = args.sweeps or 10
+        M = args.chains
+        name = f"KA LJ 80:20 N={N} rho=1.2 T={args.temperature} x {M} independent chains per GPU, Displacement sigma=0.05"
+    else:
+        N = args.particles or (1 << 20)
+        sweeps = args.sweeps or 2
+        M = 1
+        name = f"single KA LJ 80:20 box N={N} rho=1.2 T={args.temperature}, checkerboard cell sweeps, Displacement sigma=0.05"
+    pos, sp, box = ka_lattice(N, 1.2, seed=0)
+    return N, M, sweeps, name, pos, sp, box
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_arm(args, N, sweeps, pos, sp, box, cores=None):
+    """The oracle on the host cores: one independent chain per thread (the reference's `parallel=true`)."""
+    from oracle import oracle as O
+    from particlesmc_b200 import models as M
+    cores = cores or os.cpu_count() or 1
+    par = M.flatten_model_matrix(M.KobAndersen())
+    pool = O.make_pool([dict(kind="displacement", prob=1.0, sigma=0.05)])
+    if args.workload == "chains":
+        systems = [O.OracleSystem(pos, sp, box, args.temperature, M.MODEL_LJ, par, O.LINKEDLIST) for _ in range(cores)]
+        sample = f"{cores} chains (one per host thread) x {sweeps} sweeps of N={N}"
+    else:
+        systems = [O.OracleSystem(pos, sp, box, args.temperature, M.MODEL_LJ, par, O.LINKEDLIST)]
+        sample = f"1 chain (the box is one sequential chain on the CPU) x {sweeps} sweeps of N={N}"
+    return O, systems, pool, sample
+
+
+def time_cpu(O, systems, pool, n_trials, t0):
+    t = time.perf_counter()
+    used = O.run_chains(systems, 42, t0, n_trials, pool, revert_mode=0, n_threads=0)
+    dt = time.perf_counter() - t
+    return len(systems) * n_trials / dt, dt, min(used, len(systems))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    N, M, sweeps, name, pos, sp, box = workload_config(args)
+    ref_sweeps = max(1, min(sweeps, 4)) if args.workload == "chains" else 1
+    if args.workload == "box":
+        # bounded sample: a 65536-particle box has the same 27-cell stencil occupancy as the 2^20 one
+        from particlesmc_b200.synthetic import ka_lattice
+        if N > 65536:
+            N = 65536
+            pos, sp, box = ka_lattice(N, 1.2, seed=0)
+    O, systems, pool, sample = cpu_reference_arm(args, N, ref_sweeps, pos, sp, box)
+    t0 = 0
+    for _ in range(args.warmup):
+        time_cpu(O, systems, pool, max(1, N // 10), t0)
+        t0 += max(1, N // 10)
+    tot_t, tot_moves, cores = 0.0, 0, 1
+    for _ in range(args.steps):
+        v, dt, cores = time_cpu(O, systems, pool, ref_sweeps * N, t0)
+        t0 += ref_sweeps * N
+        tot_t += dt
+        tot_moves += len(systems) * ref_sweeps * N
+    value = tot_moves / tot_t
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": name, "note": "C restatement of the reference CPU algorithm (oracle/), not Julia: "
+                       "Julia and Arianna.jl are not available on this box"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from particlesmc_b200 import _lib as L
+    from particlesmc_b200 import models as M
+    from particlesmc_b200.device import DeviceContext, measure_fma_peak
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    N, Mc, sweeps, name, pos, sp, box = workload_config(args)
+    par = M.flatten_model_matrix(M.KobAndersen())
+    mode = L.MODE_CHAINS if args.workload == "chains" else L.MODE_BOX
+    # chains are keyed by their GLOBAL index: rank r holds chains [r*Mc, (r+1)*Mc)
+    ctx = DeviceContext(Mc, N, 3, 2, M.MODEL_LJ, mode=mode, device=local, chain_offset=rank * Mc, threads=args.threads)
+    stream = torch.cuda.Stream(device=dev)  # a non-default stream shared by torch events and the library
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
+    ctx.set_model(par)
+
+    # pinned host buffers in the caller's (reference) layout
+    h_pos = torch.empty((Mc, N, 3), dtype=torch.float64).pin_memory()
+    h_sp = torch.empty((Mc, N), dtype=torch.int64).pin_memory()
+    h_box = torch.empty((Mc, 3), dtype=torch.float64).pin_memory()
+    h_T = torch.full((Mc,), args.temperature, dtype=torch.float64).pin_memory()
+    h_E = torch.empty((Mc,), dtype=torch.float64).pin_memory()
+    h_pos.numpy()[:] = pos[None]
+    h_sp.numpy()[:] = sp[None]
+    h_box.numpy()[:] = box[None]
+
+    def upload():
+        ctx.upload_raw(h_pos.data_ptr(), h_sp.data_ptr(), h_box.data_ptr(), h_T.data_ptr(), 0, Mc)
+        ctx.init_energy()
+
+    def download():
+        ctx.energy_into(h_E.data_ptr())
+        ctx.download_raw(h_pos.data_ptr(), h_sp.data_ptr(), 0, Mc)
+
+    upload()
+    ctx.set_moves([dict(kind="displacement", prob=1.0, sigma=0.05)])
+    ctx.seed(42)
+    trials_per_step = sweeps * N
+    if args.equil > 0:
+        ctx.run(args.equil * N)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput -----------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        flush.zero_()
+        ctx.run(trials_per_step, sync=False)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    kernel_ms = []
+    barrier()
+    ev[0].record()
+    for _ in range(args.steps):
+        flush.zero_()
+        ctx.run(trials_per_step, sync=False)
+    ev[1].record()
+    barrier()
+    ms_total = ev[0].elapsed_time(ev[1])
+    launches = ctx.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    # per-launch duration of the sweep kernel(s), CUDA events recorded inside the library on the same stream
+    for _ in range(args.steps):
+        ctx.run(trials_per_step, sync=True)
+        kernel_ms.append(ctx.last_run_ms())
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    moves_per_step = world * Mc * trials_per_step
+    value = moves_per_step * args.steps / (ms_total * 1e-3)
+
+    # ---- end to end through the C ABI with host buffers -------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        for _ in range(2):
+            upload(); ctx.run(trials_per_step, sync=False); download()
+        barrier()
+        t0 = time.perf_counter()
+        ev[0].record()
+        for _ in range(args.steps):
+            upload()
+            ctx.run(trials_per_step, sync=False)
+            download()
+        ev[1].record()
+        barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        e_ms = max(ev[0].elapsed_time(ev[1]), wall_ms)
+        t = torch.tensor([e_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        h2d = h_pos.numel() * 8 + h_sp.numel() * 8 + h_box.numel() * 8 + h_T.numel() * 8
+        d2h = h_pos.numel() * 8 + h_sp.numel() * 8 + h_E.numel() * 8
+        e2e = {"value": moves_per_step * args.steps / (float(t.item()) * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "energy_per_particle_mean": float(h_E.numpy().mean() / N)}
+
+    # ---- energy sanity in the same run: bookkeeping vs recomputed --------------------------------------
+    e_run, e_tot = ctx.energy(), ctx.total_energy()
+    drift = float(np.max(np.abs(e_run - e_tot) / np.abs(e_tot)))
+    calls, acc = ctx.counters()
+
+    if rank == 0:
+        work = WORK[args.workload]
+        kms = float(np.mean(kernel_ms))
+        peak64 = measure_fma_peak(True, local)
+        peak32 = measure_fma_peak(False, local)
+        achieved = Mc * trials_per_step * work["P"] * work["F"] / (kms * 1e-3) / 1e12
+        roofline = {"bound": "fp64_pipe", "achieved": achieved, "peak": peak64, "unit": "TFLOP/s",
+                    "frac": achieved / peak64, "traffic": None,
+                    "kernel": "k_chain_sweep" if args.workload == "chains" else "k_box_sweep (8 colours + cell rebuild)",
+                    "kernel_ms_per_launch": kms, "launches_per_step": launches / args.steps,
+                    "work_model": f"reference-equivalent: P={work['P']:.0f} candidate pairs/move x F={work['F']:.2f} flop/pair (SURVEY.md 8d)",
+                    "peak_source": "DFMA burst micro-benchmark run in this process (pmc_measure_fma_peak); "
+                                   "MEASURED_PEAKS.json holds no FP64/FP32 CUDA-core figure",
+                    "fp32_fma_peak_tflops": peak32,
+                    "hbm_algorithmic_gbs": 2.0 * Mc * N * 28 / (kms * 1e-3) / 1e9,
+                    "hbm_peak_gbs": json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+                    if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0}
+        cpu = None
+        if not args.no_cpu_baseline:
+            N_c, pos_c, sp_c, box_c = N, pos, sp, box
+            if args.workload == "box" and N > 65536:
+                from particlesmc_b200.synthetic import ka_lattice
+                N_c = 65536
+                pos_c, sp_c, box_c = ka_lattice(N_c, 1.2, seed=0)
+            cs = args.cpu_sweeps if args.workload == "chains" else 2
+            O, systems, pool, sample = cpu_reference_arm(args, N_c, cs, pos_c, sp_c, box_c)
+            time_cpu(O, systems, pool, N_c // 4, 0)
+            v, dt, cores = time_cpu(O, systems, pool, cs * N_c, N_c)
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "seconds": dt}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": name, "sweeps_per_step": sweeps, "trials_per_step_per_gpu": Mc * trials_per_step,
+                           "equilibration_sweeps": args.equil, "cta_threads": args.threads or "default",
+                           "l2": "256 MiB buffer zeroed between steps (L2 flush)", "seed": 42},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+                "checks": {"energy_bookkeeping_rel_drift": drift, "acceptance": float(acc.sum() / max(calls.sum(), 1)),
+                           "energy_per_particle": float(e_tot.mean() / N)}}
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -86,7 +86,10 @@ typedef struct pmc_config {
     int32_t chain_offset; /* global index of local chain 0: the RNG stream of a chain is keyed by its GLOBAL
                              index, so results do not depend on how chains are sharded over GPUs */
     int32_t threads;      /* CTA size of the sweep kernels; 0 = library default */
-    int32_t reserved[5];
+    int32_t prefilter;    /* chain kernels: 0 = integer fixed-point distance prefilter when all boxes are cubic
+                             (same fp64 pair terms, far fewer fp64 distance evaluations); -1 = always visit every
+                             candidate in fp64 (the reference-equivalent amount of work) */
+    int32_t reserved[4];
 } pmc_config;
 
 /* One entry of the move pool == Arianna `Move(action, policy, parameters, probability)` as built at

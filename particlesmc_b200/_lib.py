@@ -31,7 +31,7 @@ class Config(C.Structure):
     _fields_ = [("device", C.c_int32), ("mode", C.c_int32), ("precision", C.c_int32), ("n_chains", C.c_int32),
                 ("n_particles", C.c_int32), ("dim", C.c_int32), ("n_species", C.c_int32), ("model_kind", C.c_int32),
                 ("molecules", C.c_int32), ("chain_offset", C.c_int32), ("threads", C.c_int32),
-                ("reserved", C.c_int32 * 5)]
+                ("prefilter", C.c_int32), ("reserved", C.c_int32 * 4)]
 
 
 class MoveSpec(C.Structure):

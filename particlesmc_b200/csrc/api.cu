@@ -158,8 +158,9 @@ struct pmc_ctx {
     unsigned long long seed = 0, t0 = 0;
     bool model_set = false, uploaded = false, energy_set = false, bonds_set = false;
     int64_t launches = 0;
-    size_t sweep_smem = 0, energy_smem = 0;
+    size_t sweep_smem = 0, sweep_smem_filter = 0, energy_smem = 0;
     bool sweep_swap_cfg = false;
+    bool cubic = true;  // every uploaded chain has a cubic box (enables the fixed-point prefilter)
     pmc::BoxState *boxst = nullptr;
 };
 
@@ -186,7 +187,8 @@ bool pool_has_swap(const pmc_ctx *c) {
 
 int configure_sweep(pmc_ctx *c, bool any_swap) {
     const bool mol = c->cfg.molecules != 0;
-    size_t s = pmc::chain_sweep_smem_bytes(c->cfg.dim, c->Npad, c->cfg.n_species, c->threads, mol, any_swap);
+    size_t s = pmc::chain_sweep_smem_bytes(c->cfg.dim, c->Npad, c->cfg.n_species, c->threads, mol, any_swap, false);
+    size_t sf = pmc::chain_sweep_smem_bytes(c->cfg.dim, c->Npad, c->cfg.n_species, c->threads, mol, any_swap, true);
     size_t e = pmc::chain_energy_smem_bytes(c->cfg.dim, c->Npad, c->cfg.n_species, mol);
     int dev_max = 0;
     CU(cudaDeviceGetAttribute(&dev_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->cfg.device));
@@ -194,9 +196,11 @@ int configure_sweep(pmc_ctx *c, bool any_swap) {
         return fail(PMC_ERR_UNSUPPORTED,
                     "chain state needs %zu B of shared memory per CTA (limit %d): use PMC_MODE_BOX for N=%d", s > e ? s : e,
                     dev_max, c->cfg.n_particles);
-    if (s != c->sweep_smem || e != c->energy_smem) {
-        CU(pmc::configure_chain_kernels(c->cfg.dim, c->cfg.model_kind, mol, s, e));
+    if (sf > (size_t)dev_max) sf = s;  // prefilter does not fit: use_filter() falls back to the direct kernel
+    if (s != c->sweep_smem || sf != c->sweep_smem_filter || e != c->energy_smem) {
+        CU(pmc::configure_chain_kernels(c->cfg.dim, c->cfg.model_kind, mol, s, sf, e));
         c->sweep_smem = s;
+        c->sweep_smem_filter = sf;
         c->energy_smem = e;
     }
     return PMC_OK;
@@ -284,8 +288,9 @@ int sweep(pmc_ctx *c, int64_t n_trials, const pmc_trial *d_replay, pmc_trial *d_
     a.dE_out = d_dE;
     a.exact_exp = exact_exp ? 1 : 0;
     CU(cudaEventRecord(c->ev0, c->stream));
-    CU(pmc::launch_chain_sweep(c->cfg.dim, c->cfg.model_kind, c->cfg.molecules != 0, d_trace != nullptr,
-                               c->cfg.n_chains, c->threads, c->sweep_smem, a, c->stream));
+    const bool filter = c->cubic && c->cfg.prefilter >= 0 && c->sweep_smem_filter > c->sweep_smem;
+    CU(pmc::launch_chain_sweep(c->cfg.dim, c->cfg.model_kind, c->cfg.molecules != 0, filter, c->cfg.n_chains,
+                               c->threads, filter ? c->sweep_smem_filter : c->sweep_smem, a, c->stream));
     CU(cudaEventRecord(c->ev1, c->stream));
     c->have_run_events = true;
     c->launches++;
@@ -324,10 +329,10 @@ int pmc_create(const pmc_config *cfg, pmc_ctx **out) {
     pmc_ctx *c = new pmc_ctx();
     c->cfg = *cfg;
     c->Npad = (cfg->n_particles + 31) / 32 * 32;
-    c->threads = cfg->threads > 0 ? cfg->threads : 128;
-    if (c->threads % 32 != 0 || c->threads > 1024) {
+    c->threads = cfg->threads > 0 ? cfg->threads : 256;
+    if (c->threads % 32 != 0 || c->threads > 256) {
         delete c;
-        return fail(PMC_ERR_INVALID, "threads must be a multiple of 32, at most 1024");
+        return fail(PMC_ERR_INVALID, "threads must be a multiple of 32, at most 256");
     }
     if (cfg->mode == PMC_MODE_CHAINS && c->Npad > 65535) {
         delete c;
@@ -450,6 +455,7 @@ int pmc_upload(pmc_ctx *c, int32_t first, int32_t count, const double *position,
             const double L = box[(size_t)k * d + a];
             if (!(L > 0.0) || !std::isfinite(L)) return fail(PMC_ERR_INVALID, "chain %d: box length must be positive", first + k);
             b3[(size_t)k * 3 + a] = L;
+            if (L != box[(size_t)k * d]) c->cubic = false;
         }
         if (!(temperature[k] > 0.0)) return fail(PMC_ERR_INVALID, "chain %d: temperature must be positive", first + k);
     }

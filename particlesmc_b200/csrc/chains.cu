@@ -26,58 +26,61 @@ namespace pmc {
 
 namespace {
 
-constexpr int kMaxWarps = 32;
+constexpr int kMaxThreads = 256;  // CTA size limit of the sweep kernel
+constexpr int kMinBlocks = 4;     // resident CTAs per SM the register allocation is sized for
+constexpr int kMaxWarps = kMaxThreads / 32;
+constexpr int kBatch = 64;  // proposals generated per batch (parked in shared memory)
 
 struct SweepSmem {
-    double *x;        // [DIM][Npad]
+    double *x;        // [DIM][Npad] wrapped positions (source of truth)
     double *par;      // [ns*ns*PMC_NPAR]
     double *red;      // [2][kMaxWarps]
-    double *delta;    // [NT][3]
-    double *thr;      // [NT]  -T*log(u)  (or u itself in exact_exp mode)
-    int *ti;          // [NT]  particle i, or slot ka for swaps
-    int *tj;          // [NT]  slot kb for swaps
-    int *tm;          // [NT]  pool index
+    double *delta;    // [kBatch][3]
+    double *thr;      // [kBatch]  -T*log(u)  (or u itself in exact_exp mode)
     unsigned long long *cnt;  // [2][PMC_MAX_MOVES] calls, accepted
-    int *spoff;               // [PMC_MAX_SPECIES+1]
-    uint16_t *spids;          // [Npad]
-    uint16_t *heads;          // [Npad]
-    uint16_t *bonds;          // [Npad][PMC_MAX_BONDS] (MOL only)
-    uint8_t *sp;              // [Npad]
+    uint32_t *u;      // [DIM][Npad] FILTER: positions as 32-bit fixed-point fractions of L
+    int *dint;        // [kBatch][3] FILTER: delta in the same fixed-point units
+    uint32_t *thr_u;  // [PMC_MAX_SPECIES+1] FILTER: cutoff^2 in fixed-point units per species of i; last = global
+    int *ti;          // [kBatch]  particle i, or slot ka for swaps
+    int *tj;          // [kBatch]  slot kb for swaps
+    int *tm;          // [kBatch]  pool index
+    int *spoff;       // [PMC_MAX_SPECIES+1]
+    uint16_t *wq;     // [nwarp][qcap] FILTER: per-warp queues of surviving candidates
+    uint16_t *spids;  // [Npad]
+    uint16_t *heads;  // [Npad]
+    uint16_t *bonds;  // [Npad][PMC_MAX_BONDS] (MOL only)
+    uint8_t *sp;      // [Npad]
 };
 
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+__host__ __device__ inline int queue_cap(int Npad, int NT) { return (Npad + NT - 1) / NT * 32; }
 
 __host__ __device__ inline size_t carve_sweep(SweepSmem &s, unsigned char *base, int dim, int Npad, int ns, int NT,
-                                              bool mol, bool any_swap) {
+                                              bool mol, bool any_swap, bool filter) {
     size_t o = 0;
-    s.x = (double *)(base + o);
-    o += sizeof(double) * dim * Npad;
-    s.par = (double *)(base + o);
-    o += sizeof(double) * ns * ns * PMC_NPAR;
-    s.red = (double *)(base + o);
-    o += sizeof(double) * 2 * kMaxWarps;
-    s.delta = (double *)(base + o);
-    o += sizeof(double) * 3 * NT;
-    s.thr = (double *)(base + o);
-    o += sizeof(double) * NT;
-    s.cnt = (unsigned long long *)(base + o);
-    o += sizeof(unsigned long long) * 2 * PMC_MAX_MOVES;
-    s.ti = (int *)(base + o);
-    o += sizeof(int) * NT;
-    s.tj = (int *)(base + o);
-    o += sizeof(int) * NT;
-    s.tm = (int *)(base + o);
-    o += sizeof(int) * NT;
-    s.spoff = (int *)(base + o);
-    o += sizeof(int) * 8;
-    s.spids = (uint16_t *)(base + o);
-    o += any_swap ? sizeof(uint16_t) * Npad : 0;
-    s.heads = (uint16_t *)(base + o);
-    o += any_swap ? sizeof(uint16_t) * Npad : 0;
-    s.bonds = (uint16_t *)(base + o);
-    o += mol ? sizeof(uint16_t) * Npad * PMC_MAX_BONDS : 0;
-    s.sp = (uint8_t *)(base + o);
-    o += Npad;
+    auto take = [&](size_t bytes) {
+        unsigned char *p = base + o;
+        o += align_up(bytes, 8);
+        return p;
+    };
+    s.x = (double *)take(sizeof(double) * dim * Npad);
+    s.par = (double *)take(sizeof(double) * ns * ns * PMC_NPAR);
+    s.red = (double *)take(sizeof(double) * 2 * kMaxWarps);
+    s.delta = (double *)take(sizeof(double) * 3 * kBatch);
+    s.thr = (double *)take(sizeof(double) * kBatch);
+    s.cnt = (unsigned long long *)take(sizeof(unsigned long long) * 2 * PMC_MAX_MOVES);
+    s.u = (uint32_t *)take(filter ? sizeof(uint32_t) * dim * Npad : 0);
+    s.dint = (int *)take(filter ? sizeof(int) * 3 * kBatch : 0);
+    s.thr_u = (uint32_t *)take(sizeof(uint32_t) * 8);
+    s.ti = (int *)take(sizeof(int) * kBatch);
+    s.tj = (int *)take(sizeof(int) * kBatch);
+    s.tm = (int *)take(sizeof(int) * kBatch);
+    s.spoff = (int *)take(sizeof(int) * 8);
+    s.wq = (uint16_t *)take(filter ? sizeof(uint16_t) * (NT / 32) * queue_cap(Npad, NT) : 0);
+    s.spids = (uint16_t *)take(any_swap ? sizeof(uint16_t) * Npad : 0);
+    s.heads = (uint16_t *)take(any_swap ? sizeof(uint16_t) * Npad : 0);
+    s.bonds = (uint16_t *)take(mol ? sizeof(uint16_t) * Npad * PMC_MAX_BONDS : 0);
+    s.sp = (uint8_t *)take(Npad);
     return align_up(o, 16);
 }
 
@@ -88,6 +91,23 @@ __device__ __forceinline__ double dist2(const double *__restrict__ sx, int Npad,
     r2 += mi_sq(xi[1], sx[Npad + j], L[1]);
     if constexpr (DIM == 3) r2 += mi_sq(xi[2], sx[2 * Npad + j], L[2]);
     return r2;
+}
+
+// Squared nearest-image separation in fixed-point units: coordinates are 32-bit fractions of the (cubic)
+// box, so the wrapping subtraction IS the minimum image; hi32(d*d) summed over axes is r^2 * 2^32 / L^2.
+template <int DIM>
+__device__ __forceinline__ uint32_t dist2_fixed(const uint32_t *__restrict__ su, int Npad, int j, const uint32_t (&ui)[3]) {
+    const int dx = (int)(ui[0] - su[j]), dy = (int)(ui[1] - su[Npad + j]);
+    uint32_t r = (uint32_t)__mulhi(dx, dx) + (uint32_t)__mulhi(dy, dy);
+    if constexpr (DIM == 3) {
+        const int dz = (int)(ui[2] - su[2 * Npad + j]);
+        r += (uint32_t)__mulhi(dz, dz);
+    }
+    return r;
+}
+
+__device__ __forceinline__ uint32_t to_fixed(double x, double scale) {  // scale = 2^32 / L
+    return (uint32_t)__double2ull_rd(x * scale);
 }
 
 // Block-wide sum with one barrier; every thread returns the same bits.  `slot` alternates per trial
@@ -110,21 +130,83 @@ __device__ __forceinline__ bool bonded_to(const uint16_t (&bi)[PMC_MAX_BONDS], i
     return b;
 }
 
+// Contribution of candidate j to e2 - e1 of a Displacement of particle i (old position xo, new xn).
+template <int DIM, int MODEL, bool MOL>
+__device__ __forceinline__ double displacement_term(const SweepSmem &S, int Npad, int j, const double (&xo)[3],
+                                                    const double (&xn)[3], const double (&L)[3],
+                                                    const double *__restrict__ prow,
+                                                    const uint16_t (&bi)[PMC_MAX_BONDS]) {
+    const double *p = prow + S.sp[j] * PMC_NPAR;
+    const double r2o = dist2<DIM>(S.x, Npad, j, xo, L);
+    const double r2n = dist2<DIM>(S.x, Npad, j, xn, L);
+    if (bonded_to<MOL>(bi, j)) return bond_potential(p, r2n) - bond_potential(p, r2o);
+    const double rc2 = p[PMC_P_RCUT2];
+    double t = 0.0;
+    if (r2o <= rc2) t -= pair_potential<MODEL>(p, r2o);
+    if (r2n <= rc2) t += pair_potential<MODEL>(p, r2n);
+    return t;
+}
+
+// Contribution of particle k to e2 - e1 of a DiscreteSwap between i (species si) and j (species sj):
+// the k-terms of both local energies before and after the exchange (src/moves.jl:159-167).
+template <int DIM, int MODEL, bool MOL>
+__device__ __forceinline__ double swap_term(const SweepSmem &S, int Npad, int ns, int k, int i, int j, int si, int sj,
+                                            const double (&xi)[3], const double (&xj)[3], const double (&L)[3],
+                                            const uint16_t (&bi)[PMC_MAX_BONDS], const uint16_t (&bj)[PMC_MAX_BONDS]) {
+    const int sk_old = S.sp[k];
+    int sk_new = sk_old;
+    if (k == i) sk_new = sj;
+    if (k == j) sk_new = si;
+    double t = 0.0;
+    if (k != i) {  // term of particle i's local energy
+        const double r2 = dist2<DIM>(S.x, Npad, k, xi, L);
+        const double *po = S.par + (si * ns + sk_old) * PMC_NPAR;
+        const double *pn = S.par + (sj * ns + sk_new) * PMC_NPAR;
+        if (bonded_to<MOL>(bi, k)) {
+            t += bond_potential(pn, r2) - bond_potential(po, r2);
+        } else {
+            if (r2 <= po[PMC_P_RCUT2]) t -= pair_potential<MODEL>(po, r2);
+            if (r2 <= pn[PMC_P_RCUT2]) t += pair_potential<MODEL>(pn, r2);
+        }
+    }
+    if (k != j) {  // term of particle j's local energy
+        const double r2 = dist2<DIM>(S.x, Npad, k, xj, L);
+        const double *po = S.par + (sj * ns + sk_old) * PMC_NPAR;
+        const double *pn = S.par + (si * ns + sk_new) * PMC_NPAR;
+        if (bonded_to<MOL>(bj, k)) {
+            t += bond_potential(pn, r2) - bond_potential(po, r2);
+        } else {
+            if (r2 <= po[PMC_P_RCUT2]) t -= pair_potential<MODEL>(po, r2);
+            if (r2 <= pn[PMC_P_RCUT2]) t += pair_potential<MODEL>(pn, r2);
+        }
+    }
+    return t;
+}
+
 // ------------------------------------------------------------------------------------------------
-// Sweep kernel
+// Sweep kernel.  FILTER = true (cubic boxes): every candidate first goes through an integer
+// fixed-point distance test on the ALU/FMA-int pipes; only survivors (a conservative superset of the
+// pairs inside the cutoff) are compacted per warp and evaluated in fp64.  The result is the same set of
+// fp64 pair terms as FILTER = false, which visits all candidates in fp64.
 // ------------------------------------------------------------------------------------------------
-template <int DIM, int MODEL, bool MOL, bool TRACE>
-__global__ void k_chain_sweep(const __grid_constant__ ChainArgs A) {
+template <int DIM, int MODEL, bool MOL, bool FILTER>
+__global__ void __launch_bounds__(kMaxThreads, kMinBlocks) k_chain_sweep(const __grid_constant__ ChainArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = NT >> 5;
     const int c = blockIdx.x;
     const int N = A.N, Npad = A.Npad, ns = A.ns;
     SweepSmem S;
-    carve_sweep(S, smem_raw, DIM, Npad, ns, NT, MOL, A.any_swap != 0);
+    carve_sweep(S, smem_raw, DIM, Npad, ns, NT, MOL, A.any_swap != 0, FILTER);
 
     // ---- load chain state into shared memory --------------------------------------------------
+    double L[3] = {A.box[c * 3 + 0], A.box[c * 3 + 1], A.box[c * 3 + 2]};
+    const double fscale = 4294967296.0 / L[0];  // FILTER: fixed-point units per unit length
     double *gx = A.x + (size_t)c * DIM * Npad;
-    for (int k = tid; k < DIM * Npad; k += NT) S.x[k] = gx[k];
+    for (int k = tid; k < DIM * Npad; k += NT) {
+        const double v = gx[k];
+        S.x[k] = v;
+        if constexpr (FILTER) S.u[k] = to_fixed(v, fscale);
+    }
     uint8_t *gsp = A.sp + (size_t)c * Npad;
     for (int k = tid; k < Npad; k += NT) S.sp[k] = gsp[k];
     for (int k = tid; k < ns * ns * PMC_NPAR; k += NT) S.par[k] = A.par[k];
@@ -140,32 +222,39 @@ __global__ void k_chain_sweep(const __grid_constant__ ChainArgs A) {
     if constexpr (MOL) {
         for (int k = tid; k < Npad * PMC_MAX_BONDS; k += NT) S.bonds[k] = A.bonds[k];
     }
-    double L[3] = {A.box[c * 3 + 0], A.box[c * 3 + 1], A.box[c * 3 + 2]};
+    if constexpr (FILTER) {
+        if (tid <= PMC_MAX_SPECIES) {  // conservative integer cutoffs: per species of i, and global (swaps)
+            double rc2 = 0.0;
+            for (int a = 0; a < ns; a++)
+                for (int b = 0; b < ns; b++)
+                    if (tid == PMC_MAX_SPECIES || a == tid) rc2 = fmax(rc2, A.par[(a * ns + b) * PMC_NPAR + PMC_P_RCUT2]);
+            const double t = rc2 * (1.0 + 1e-9) * (fscale / L[0]) + 64.0;  // r^2 * 2^32 / L^2, + rounding slack
+            S.thr_u[tid] = t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
+        }
+    }
     const double T = A.temp[c];
     double E = A.energy[c];
     const uint32_t k0 = (uint32_t)A.seed, k1 = (uint32_t)(A.seed >> 32);
     const uint32_t gchain = (uint32_t)(A.chain_offset + c);
     int32_t *gimg = A.img + (size_t)c * DIM * Npad;
+    uint16_t *myq = FILTER ? S.wq + warp * queue_cap(Npad, NT) : nullptr;
+    const unsigned lt_mask = (1u << lane) - 1u;
 
     int last_i = -1;  // most recently committed particle and its position (forwarded, see below)
     double last_x[3] = {0.0, 0.0, 0.0};
+    uint32_t last_u[3] = {0u, 0u, 0u};
     int slot = 0;
 
-    for (long long tb = 0; tb < A.n_trials; tb += NT) {
-        const int nb = (int)min((long long)NT, A.n_trials - tb);
+    for (long long tb = 0; tb < A.n_trials; tb += kBatch) {
+        const int nb = (int)min((long long)kBatch, A.n_trials - tb);
         __syncthreads();  // previous batch fully consumed; first pass: state loaded
         // ---- proposals of trials tb .. tb+nb-1, one per thread --------------------------------
-        if (tid < nb) {
-            const long long q = tb + tid;
+        for (int t_ = tid; t_ < nb; t_ += NT) {
+            const long long q = tb + t_;
+            pmc_trial tr;
             if (A.replay) {
-                const pmc_trial tr = A.replay[(size_t)c * A.n_trials + q];
-                S.tm[tid] = tr.move;
-                S.ti[tid] = tr.i;
-                S.tj[tid] = tr.j;
-                S.delta[3 * tid + 0] = tr.delta[0];
-                S.delta[3 * tid + 1] = tr.delta[1];
-                S.delta[3 * tid + 2] = tr.delta[2];
-                S.thr[tid] = A.exact_exp ? tr.u : -T * log(tr.u);
+                tr = A.replay[(size_t)c * A.n_trials + q];
+                S.thr[t_] = A.exact_exp ? tr.u : -T * log(tr.u);
             } else {
                 const unsigned long long t = A.t0 + (unsigned long long)q;
                 const Philox4 a = philox4x32_10((uint32_t)t, (uint32_t)(t >> 32), gchain, 0u, k0, k1);
@@ -174,14 +263,11 @@ __global__ void k_chain_sweep(const __grid_constant__ ChainArgs A) {
                 int m = A.n_moves - 1;
                 for (int k = A.n_moves - 2; k >= 0; k--)
                     if (um < A.mv_cum[k]) m = k;
-                const double u = uniform53(a.v[2], a.v[3]);
-                S.tm[tid] = m;
-                S.thr[tid] = A.exact_exp ? u : -T * log(u);
-                pmc_trial tr;
+                tr.u = uniform53(a.v[2], a.v[3]);
                 tr.move = m;
                 tr.kind = A.mv_kind[m];
-                tr.u = u;
-                if (A.mv_kind[m] == PMC_MOVE_DISPLACEMENT) {
+                S.thr[t_] = A.exact_exp ? tr.u : -T * log(tr.u);
+                if (tr.kind == PMC_MOVE_DISPLACEMENT) {
                     float z0, z1, z2, z3;
                     box_muller(b.v[0], b.v[1], z0, z1);
                     box_muller(b.v[2], b.v[3], z2, z3);
@@ -191,21 +277,22 @@ __global__ void k_chain_sweep(const __grid_constant__ ChainArgs A) {
                     tr.delta[0] = (double)(sg * z0);
                     tr.delta[1] = (double)(sg * z1);
                     tr.delta[2] = (DIM == 3) ? (double)(sg * z2) : 0.0;
-                    S.ti[tid] = tr.i;
-                    S.tj[tid] = -1;
                 } else {  // slots in the species lists; resolved to particles when the trial executes
                     const int nA = S.spoff[A.mv_a[m] + 1] - S.spoff[A.mv_a[m]];
                     const int nB = S.spoff[A.mv_b[m] + 1] - S.spoff[A.mv_b[m]];
                     tr.i = (nA > 0 && nB > 0) ? (int)bounded(a.v[1], (uint32_t)nA) : -1;
                     tr.j = (nA > 0 && nB > 0) ? (int)bounded(b.v[0], (uint32_t)nB) : -1;
                     tr.delta[0] = tr.delta[1] = tr.delta[2] = 0.0;
-                    S.ti[tid] = tr.i;
-                    S.tj[tid] = tr.j;
                 }
-                S.delta[3 * tid + 0] = tr.delta[0];
-                S.delta[3 * tid + 1] = tr.delta[1];
-                S.delta[3 * tid + 2] = tr.delta[2];
-                if constexpr (TRACE) A.trace[(size_t)c * A.n_trials + q] = tr;
+                if (A.trace) A.trace[(size_t)c * A.n_trials + q] = tr;
+            }
+            S.tm[t_] = tr.move;
+            S.ti[t_] = tr.i;
+            S.tj[t_] = (tr.kind == PMC_MOVE_SWAP) ? tr.j : -2;  // -2 marks a displacement
+#pragma unroll
+            for (int a = 0; a < 3; a++) {
+                S.delta[3 * t_ + a] = tr.delta[a];
+                if constexpr (FILTER) S.dint[3 * t_ + a] = (int)__double2ll_rn(tr.delta[a] * fscale);
             }
         }
         __syncthreads();
@@ -213,10 +300,10 @@ __global__ void k_chain_sweep(const __grid_constant__ ChainArgs A) {
         // ---- the serial chain: one trial at a time ---------------------------------------------
         for (int b = 0; b < nb; b++) {
             const int m = S.tm[b];
-            const int kind = A.replay ? (S.tj[b] >= 0 ? PMC_MOVE_SWAP : PMC_MOVE_DISPLACEMENT) : A.mv_kind[m];
+            const bool is_disp = S.tj[b] == -2;
             double part = 0.0, dE;
             bool acc;
-            if (kind == PMC_MOVE_DISPLACEMENT) {
+            if (is_disp) {
                 const int i = S.ti[b];
                 double xo[3] = {0.0, 0.0, 0.0}, xn[3] = {0.0, 0.0, 0.0};
                 int w[3] = {0, 0, 0};
@@ -236,18 +323,34 @@ __global__ void k_chain_sweep(const __grid_constant__ ChainArgs A) {
                     for (int k = 0; k < PMC_MAX_BONDS; k++) bi[k] = S.bonds[i * PMC_MAX_BONDS + k];
                 }
                 const double *prow = S.par + si * ns * PMC_NPAR;
-                for (int j = tid; j < N; j += NT) {
-                    if (j == i) continue;
-                    const double *p = prow + S.sp[j] * PMC_NPAR;
-                    const double r2o = dist2<DIM>(S.x, Npad, j, xo, L);
-                    const double r2n = dist2<DIM>(S.x, Npad, j, xn, L);
-                    if (bonded_to<MOL>(bi, j)) {
-                        part += bond_potential(p, r2n) - bond_potential(p, r2o);
-                    } else {
-                        const double rc2 = p[PMC_P_RCUT2];
-                        if (r2o <= rc2) part -= pair_potential<MODEL>(p, r2o);
-                        if (r2n <= rc2) part += pair_potential<MODEL>(p, r2n);
+                uint32_t un[3] = {0u, 0u, 0u};
+                if constexpr (FILTER) {
+                    uint32_t uo[3] = {0u, 0u, 0u};
+#pragma unroll
+                    for (int a = 0; a < DIM; a++) {
+                        uo[a] = (i == last_i) ? last_u[a] : S.u[a * Npad + i];
+                        un[a] = uo[a] + (uint32_t)S.dint[3 * b + a];  // wraps like the box does
                     }
+                    const uint32_t thr = S.thr_u[si];
+                    int cnt = 0;
+                    for (int j0 = 0; j0 < Npad; j0 += NT) {
+                        const int j = j0 + tid;
+                        bool pass = false;
+                        if (j < N && j != i) {
+                            pass = dist2_fixed<DIM>(S.u, Npad, j, uo) <= thr || dist2_fixed<DIM>(S.u, Npad, j, un) <= thr ||
+                                   bonded_to<MOL>(bi, j);
+                        }
+                        const unsigned mask = __ballot_sync(0xffffffffu, pass);
+                        if (pass) myq[cnt + __popc(mask & lt_mask)] = (uint16_t)j;
+                        cnt += __popc(mask);
+                    }
+                    __syncwarp();
+                    for (int q = lane; q < cnt; q += 32)
+                        part += displacement_term<DIM, MODEL, MOL>(S, Npad, myq[q], xo, xn, L, prow, bi);
+                    __syncwarp();
+                } else {
+                    for (int j = tid; j < N; j += NT)
+                        if (j != i) part += displacement_term<DIM, MODEL, MOL>(S, Npad, j, xo, xn, L, prow, bi);
                 }
                 dE = block_sum(part, S.red, slot, lane, warp, nwarp);
                 slot ^= 1;
@@ -257,12 +360,16 @@ __global__ void k_chain_sweep(const __grid_constant__ ChainArgs A) {
 #pragma unroll
                         for (int a = 0; a < DIM; a++) {
                             S.x[a * Npad + i] = xn[a];
+                            if constexpr (FILTER) S.u[a * Npad + i] = to_fixed(xn[a], fscale);
                             if (w[a] != 0) atomicAdd(&gimg[a * Npad + i], w[a]);
                         }
                     }
                     last_i = i;
 #pragma unroll
-                    for (int a = 0; a < DIM; a++) last_x[a] = xn[a];
+                    for (int a = 0; a < DIM; a++) {
+                        last_x[a] = xn[a];
+                        last_u[a] = un[a];
+                    }
                     E += dE;
                 }
             } else {
@@ -293,39 +400,39 @@ __global__ void k_chain_sweep(const __grid_constant__ ChainArgs A) {
                             bj[k] = S.bonds[j * PMC_MAX_BONDS + k];
                         }
                     }
-                    for (int k = tid; k < N; k += NT) {
-                        // species of k before / after the exchange
-                        int sk_old = S.sp[k], sk_new = sk_old;
-                        if (k == i) sk_new = sj;
-                        if (k == j) sk_new = si;
-                        if (k != i) {  // term of particle i's local energy
-                            const double r2 = dist2<DIM>(S.x, Npad, k, xi, L);
-                            const double *po = S.par + (si * ns + sk_old) * PMC_NPAR;
-                            const double *pn = S.par + (sj * ns + sk_new) * PMC_NPAR;
-                            if (bonded_to<MOL>(bi, k)) {
-                                part += bond_potential(pn, r2) - bond_potential(po, r2);
-                            } else {
-                                if (r2 <= po[PMC_P_RCUT2]) part -= pair_potential<MODEL>(po, r2);
-                                if (r2 <= pn[PMC_P_RCUT2]) part += pair_potential<MODEL>(pn, r2);
-                            }
+                    if constexpr (FILTER) {
+                        uint32_t ui[3] = {0u, 0u, 0u}, uj[3] = {0u, 0u, 0u};
+#pragma unroll
+                        for (int a = 0; a < DIM; a++) {
+                            ui[a] = (i == last_i) ? last_u[a] : S.u[a * Npad + i];
+                            uj[a] = (j == last_i) ? last_u[a] : S.u[a * Npad + j];
                         }
-                        if (k != j) {  // term of particle j's local energy
-                            const double r2 = dist2<DIM>(S.x, Npad, k, xj, L);
-                            const double *po = S.par + (sj * ns + sk_old) * PMC_NPAR;
-                            const double *pn = S.par + (si * ns + sk_new) * PMC_NPAR;
-                            if (bonded_to<MOL>(bj, k)) {
-                                part += bond_potential(pn, r2) - bond_potential(po, r2);
-                            } else {
-                                if (r2 <= po[PMC_P_RCUT2]) part -= pair_potential<MODEL>(po, r2);
-                                if (r2 <= pn[PMC_P_RCUT2]) part += pair_potential<MODEL>(pn, r2);
+                        const uint32_t thr = S.thr_u[PMC_MAX_SPECIES];
+                        int cnt = 0;
+                        for (int k0_ = 0; k0_ < Npad; k0_ += NT) {
+                            const int k = k0_ + tid;
+                            bool pass = false;
+                            if (k < N) {
+                                pass = (k != i && dist2_fixed<DIM>(S.u, Npad, k, ui) <= thr) ||
+                                       (k != j && dist2_fixed<DIM>(S.u, Npad, k, uj) <= thr) || bonded_to<MOL>(bi, k) ||
+                                       bonded_to<MOL>(bj, k);
                             }
+                            const unsigned mask = __ballot_sync(0xffffffffu, pass);
+                            if (pass) myq[cnt + __popc(mask & lt_mask)] = (uint16_t)k;
+                            cnt += __popc(mask);
                         }
+                        __syncwarp();
+                        for (int q = lane; q < cnt; q += 32)
+                            part += swap_term<DIM, MODEL, MOL>(S, Npad, ns, myq[q], i, j, si, sj, xi, xj, L, bi, bj);
+                        __syncwarp();
+                    } else {
+                        for (int k = tid; k < N; k += NT)
+                            part += swap_term<DIM, MODEL, MOL>(S, Npad, ns, k, i, j, si, sj, xi, xj, L, bi, bj);
                     }
                 }
                 dE = block_sum(part, S.red, slot, lane, warp, nwarp);
                 slot ^= 1;
-                acc = (i >= 0 && j >= 0) &&
-                      (A.exact_exp ? accept_exact(dE, T, S.thr[b]) : (dE < S.thr[b]));
+                acc = (i >= 0 && j >= 0) && (A.exact_exp ? accept_exact(dE, T, S.thr[b]) : (dE < S.thr[b]));
                 if (acc) {
                     if (tid == 0) {
                         const uint8_t si = S.sp[i], sj = S.sp[j];
@@ -342,12 +449,10 @@ __global__ void k_chain_sweep(const __grid_constant__ ChainArgs A) {
                     E += dE;
                     __syncthreads();  // species and species lists are read by every thread
                 }
-                if constexpr (TRACE) {
-                    if (tid == 0 && !A.replay) {
-                        pmc_trial *tr = A.trace + (size_t)c * A.n_trials + tb + b;
-                        tr->i = i;
-                        tr->j = j;
-                    }
+                if (A.trace && tid == 0) {
+                    pmc_trial *tr = A.trace + (size_t)c * A.n_trials + tb + b;
+                    tr->i = i;
+                    tr->j = j;
                 }
             }
             if (tid == 0) {
@@ -456,35 +561,40 @@ cudaError_t dispatch(int dim, int model, bool mol, F &&f) {
 
 }  // namespace
 
-size_t chain_sweep_smem_bytes(int dim, int Npad, int ns, int threads, bool mol, bool any_swap) {
+size_t chain_sweep_smem_bytes(int dim, int Npad, int ns, int threads, bool mol, bool any_swap, bool filter) {
     SweepSmem s;
-    return carve_sweep(s, nullptr, dim, Npad, ns, threads, mol, any_swap);
+    return carve_sweep(s, nullptr, dim, Npad, ns, threads, mol, any_swap, filter);
 }
 
 size_t chain_energy_smem_bytes(int dim, int Npad, int ns, bool) {
     return sizeof(double) * ((size_t)dim * Npad + Npad + (size_t)ns * ns * PMC_NPAR) + Npad + 16;
 }
 
-cudaError_t configure_chain_kernels(int dim, int model, bool mol, size_t sweep_smem, size_t energy_smem) {
+cudaError_t configure_chain_kernels(int dim, int model, bool mol, size_t sweep_smem, size_t sweep_smem_filter,
+                                    size_t energy_smem) {
     return dispatch(dim, model, mol, [&](auto D, auto MDL, auto ML) {
-        cudaError_t e = cudaFuncSetAttribute(k_chain_sweep<decltype(D)::value, decltype(MDL)::value, decltype(ML)::value, false>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem);
+        constexpr int d = decltype(D)::value, mdl = decltype(MDL)::value;
+        constexpr bool ml = decltype(ML)::value;
+        cudaError_t e = cudaFuncSetAttribute(k_chain_sweep<d, mdl, ml, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)sweep_smem);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(k_chain_sweep<decltype(D)::value, decltype(MDL)::value, decltype(ML)::value, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)sweep_smem);
+        e = cudaFuncSetAttribute(k_chain_sweep<d, mdl, ml, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)sweep_smem_filter);
         if (e != cudaSuccess) return e;
-        return cudaFuncSetAttribute(k_chain_energy<decltype(D)::value, decltype(MDL)::value, decltype(ML)::value>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        return cudaFuncSetAttribute(k_chain_energy<d, mdl, ml>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)energy_smem);
     });
 }
 
-cudaError_t launch_chain_sweep(int dim, int model, bool mol, bool traced, int M, int threads, size_t smem,
+cudaError_t launch_chain_sweep(int dim, int model, bool mol, bool filter, int M, int threads, size_t smem,
                                const ChainArgs &a, cudaStream_t st) {
     return dispatch(dim, model, mol, [&](auto D, auto MDL, auto ML) {
-        if (traced)
-            k_chain_sweep<decltype(D)::value, decltype(MDL)::value, decltype(ML)::value, true><<<M, threads, smem, st>>>(a);
+        constexpr int d = decltype(D)::value, mdl = decltype(MDL)::value;
+        constexpr bool ml = decltype(ML)::value;
+        if (filter)
+            k_chain_sweep<d, mdl, ml, true><<<M, threads, smem, st>>>(a);
         else
-            k_chain_sweep<decltype(D)::value, decltype(MDL)::value, decltype(ML)::value, false><<<M, threads, smem, st>>>(a);
+            k_chain_sweep<d, mdl, ml, false><<<M, threads, smem, st>>>(a);
         return cudaGetLastError();
     });
 }

@@ -59,12 +59,13 @@ struct EnergyArgs {
     int32_t N, Npad, ns;
 };
 
-size_t chain_sweep_smem_bytes(int dim, int Npad, int ns, int threads, bool mol, bool any_swap);
+size_t chain_sweep_smem_bytes(int dim, int Npad, int ns, int threads, bool mol, bool any_swap, bool filter);
 size_t chain_energy_smem_bytes(int dim, int Npad, int ns, bool mol);
-cudaError_t launch_chain_sweep(int dim, int model, bool mol, bool traced, int M, int threads, size_t smem,
+cudaError_t launch_chain_sweep(int dim, int model, bool mol, bool filter, int M, int threads, size_t smem,
                                const ChainArgs &a, cudaStream_t st);
 cudaError_t launch_chain_energy(int dim, int model, bool mol, int M, size_t smem, const EnergyArgs &a,
                                 cudaStream_t st);
-cudaError_t configure_chain_kernels(int dim, int model, bool mol, size_t sweep_smem, size_t energy_smem);
+cudaError_t configure_chain_kernels(int dim, int model, bool mol, size_t sweep_smem, size_t sweep_smem_filter,
+                                    size_t energy_smem);
 
 }  // namespace pmc

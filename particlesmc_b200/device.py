@@ -34,14 +34,14 @@ assert TRIAL_DTYPE.itemsize == C.sizeof(L.Trial)
 class DeviceContext:
     def __init__(self, n_chains: int, n_particles: int, dim: int, n_species: int, model_kind: int, *,
                  mode: int = L.MODE_CHAINS, precision: int = L.FP64, molecules: bool = False, device: int = 0,
-                 chain_offset: int = 0, threads: int = 0):
+                 chain_offset: int = 0, threads: int = 0, prefilter: int = 0):
         self.lib = L.load()
         self.n_chains, self.N, self.dim, self.ns = n_chains, n_particles, dim, n_species
         self.mode = mode
         self.n_moves = 0
         cfg = L.Config(device=device, mode=mode, precision=precision, n_chains=n_chains, n_particles=n_particles,
                        dim=dim, n_species=n_species, model_kind=model_kind, molecules=int(molecules),
-                       chain_offset=chain_offset, threads=threads)
+                       chain_offset=chain_offset, threads=threads, prefilter=prefilter)
         h = C.c_void_p()
         L.check(self.lib.pmc_create(C.byref(cfg), C.byref(h)))
         self._h = h
@@ -169,6 +169,11 @@ class DeviceContext:
         sp = np.zeros((count, self.N), dtype=np.int64)
         L.check(self.lib.pmc_download(self._h, first, count, _dp(pos), _lp(sp)))
         return pos, sp
+
+    def download_raw(self, pos_ptr: int, sp_ptr: int, first: int, count: int):
+        """Pointer form of ``download`` (pinned host buffers)."""
+        L.check(self.lib.pmc_download(self._h, first, count, C.cast(pos_ptr, C.POINTER(C.c_double)),
+                                      C.cast(sp_ptr, C.POINTER(C.c_int64))))
 
     def counters(self):
         nm = max(self.n_moves, 1)

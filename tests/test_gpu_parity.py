@@ -262,10 +262,11 @@ def test_replay_of_injected_proposals():
 # ---------------------------------------------------------------------------------------------------
 # stream properties: launch splitting and sharding do not change the chains
 # ---------------------------------------------------------------------------------------------------
-def _ka_ctx(n_chains, chain_offset=0, first=0, threads=0):
+def _ka_ctx(n_chains, chain_offset=0, first=0, threads=0, prefilter=0):
     par = M.flatten_model_matrix(M.KobAndersen())
     cfgs = [ka_config(216, s) for s in range(first, first + n_chains)]
-    ctx = DeviceContext(n_chains, 216, 3, 2, M.MODEL_LJ, chain_offset=chain_offset, threads=threads)
+    ctx = DeviceContext(n_chains, 216, 3, 2, M.MODEL_LJ, chain_offset=chain_offset, threads=threads,
+                        prefilter=prefilter)
     ctx.set_model(par)
     ctx.upload(np.stack([c[0] for c in cfgs]), np.stack([c[1] for c in cfgs]), cfgs[0][2], 1.0)
     ctx.init_energy()
@@ -298,13 +299,36 @@ def test_sharded_chains_equal_unsharded():
         assert np.array_equal(sf[:2], s0) and np.array_equal(sf[2:], s1)
 
 
-@pytest.mark.parametrize("threads", [32, 64, 256])
-def test_cta_size_does_not_change_decisions(threads):
-    with _ka_ctx(2) as a, _ka_ctx(2, threads=threads) as b:
+@pytest.mark.parametrize("threads,prefilter", [(32, 0), (64, 0), (128, 0), (128, -1), (256, -1)])
+def test_cta_size_and_prefilter_do_not_change_decisions(threads, prefilter):
+    """The fixed-point prefilter only selects WHICH candidates get the fp64 evaluation (a superset of the pairs
+    inside the cutoff); decisions must equal the kernel that visits every candidate in fp64."""
+    with _ka_ctx(2) as a, _ka_ctx(2, threads=threads, prefilter=prefilter) as b:
         _, acc_a, _ = a.run_traced(800)
         _, acc_b, _ = b.run_traced(800)
         assert np.array_equal(acc_a, acc_b)
         assert np.max(np.abs(a.download()[0] - b.download()[0])) < 1e-12
+
+
+def test_noncubic_box_uses_direct_kernel_and_matches_oracle():
+    """Per-axis box lengths are legal at the ABI; the prefilter needs a cubic box, so this exercises the
+    direct fp64 kernel against the oracle."""
+    rng = np.random.default_rng(3)
+    N, box = 300, np.array([6.0, 7.5, 5.5])
+    grid = np.stack(np.meshgrid(np.arange(6), np.arange(10), np.arange(5), indexing="ij"), -1).reshape(-1, 3)
+    pos = (grid[:N] + 0.5) * (box / np.array([6, 10, 5])) + rng.normal(0, 0.03, (N, 3))
+    pos = pos - np.floor(pos / box) * box
+    sp = rng.permutation(np.repeat([1, 2], [240, 60])).astype(np.int64)
+    par = M.flatten_model_matrix(M.KobAndersen())
+    orc = O.OracleSystem(pos, sp, box, 1.0, M.MODEL_LJ, par, O.LINKEDLIST)
+    with DeviceContext(1, N, 3, 2, M.MODEL_LJ) as ctx:
+        ctx.set_model(par)
+        ctx.upload(pos, sp, box, 1.0)
+        ctx.init_energy()
+        assert rel(ctx.energy()[0], orc.energy) < RTOL_E
+        ctx.set_moves([dict(kind="displacement", prob=1.0, sigma=0.05)])
+        ctx.seed(1)
+        check_trace(ctx, [orc], {0: (0, 0)}, 1500)
 
 
 def test_energy_bookkeeping_after_long_run():
