@@ -56,6 +56,7 @@ def parse_args():
     ap.add_argument("--equil", type=int, default=100, help="untimed equilibration sweeps from the lattice")
     ap.add_argument("--threads", type=int, default=0, help="CTA size of the sweep kernel (0 = library default)")
     ap.add_argument("--temperature", type=float, default=1.0)
+    ap.add_argument("--prefilter", type=int, default=0, help="0 = fixed-point prefilter (default), -1 = visit all candidates in fp64")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-sweeps", type=int, default=40)
@@ -198,7 +199,8 @@ def run_ours(args):
     par = M.flatten_model_matrix(M.KobAndersen())
     mode = L.MODE_CHAINS if args.workload == "chains" else L.MODE_BOX
     # chains are keyed by their GLOBAL index: rank r holds chains [r*Mc, (r+1)*Mc)
-    ctx = DeviceContext(Mc, N, 3, 2, M.MODEL_LJ, mode=mode, device=local, chain_offset=rank * Mc, threads=args.threads)
+    ctx = DeviceContext(Mc, N, 3, 2, M.MODEL_LJ, mode=mode, device=local, chain_offset=rank * Mc, threads=args.threads,
+                        prefilter=args.prefilter)
     stream = torch.cuda.Stream(device=dev)  # a non-default stream shared by torch events and the library
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)

@@ -158,7 +158,7 @@ struct pmc_ctx {
     unsigned long long seed = 0, t0 = 0;
     bool model_set = false, uploaded = false, energy_set = false, bonds_set = false;
     int64_t launches = 0;
-    size_t sweep_smem = 0, sweep_smem_filter = 0, energy_smem = 0;
+    size_t sweep_smem = 0, sweep_smem_filter = 0, energy_smem = 0, fast_smem = 0;
     bool sweep_swap_cfg = false;
     bool cubic = true;  // every uploaded chain has a cubic box (enables the fixed-point prefilter)
     pmc::BoxState *boxst = nullptr;
@@ -275,8 +275,8 @@ int run_energy(pmc_ctx *c) {
 }
 
 int sweep(pmc_ctx *c, int64_t n_trials, const pmc_trial *d_replay, pmc_trial *d_trace, uint8_t *d_acc, double *d_dE,
-          bool exact_exp) {
-    const bool any_swap = pool_has_swap(c) || d_replay != nullptr;
+          bool exact_exp, bool replay_has_swap = false) {
+    const bool any_swap = pool_has_swap(c) || replay_has_swap;
     c->sweep_swap_cfg = any_swap;
     int rc = configure_sweep(c, any_swap);
     if (rc) return rc;
@@ -289,8 +289,18 @@ int sweep(pmc_ctx *c, int64_t n_trials, const pmc_trial *d_replay, pmc_trial *d_
     a.exact_exp = exact_exp ? 1 : 0;
     CU(cudaEventRecord(c->ev0, c->stream));
     const bool filter = c->cubic && c->cfg.prefilter >= 0 && c->sweep_smem_filter > c->sweep_smem;
-    CU(pmc::launch_chain_sweep(c->cfg.dim, c->cfg.model_kind, c->cfg.molecules != 0, filter, c->cfg.n_chains,
-                               c->threads, filter ? c->sweep_smem_filter : c->sweep_smem, a, c->stream));
+    const bool fastk = filter && !any_swap && !c->cfg.molecules && pmc::chain_fast_supported(c->Npad, c->threads);
+    if (fastk) {
+        const size_t fs = pmc::chain_fast_smem_bytes(c->cfg.dim, c->Npad, c->cfg.n_species);
+        if (fs != c->fast_smem) {
+            CU(pmc::configure_chain_fast(c->cfg.dim, c->cfg.model_kind, c->Npad, fs));
+            c->fast_smem = fs;
+        }
+        CU(pmc::launch_chain_sweep_fast(c->cfg.dim, c->cfg.model_kind, c->cfg.n_chains, fs, a, c->stream));
+    } else {
+        CU(pmc::launch_chain_sweep(c->cfg.dim, c->cfg.model_kind, c->cfg.molecules != 0, filter, c->cfg.n_chains,
+                                   c->threads, filter ? c->sweep_smem_filter : c->sweep_smem, a, c->stream));
+    }
     CU(cudaEventRecord(c->ev1, c->stream));
     c->have_run_events = true;
     c->launches++;
@@ -329,7 +339,7 @@ int pmc_create(const pmc_config *cfg, pmc_ctx **out) {
     pmc_ctx *c = new pmc_ctx();
     c->cfg = *cfg;
     c->Npad = (cfg->n_particles + 31) / 32 * 32;
-    c->threads = cfg->threads > 0 ? cfg->threads : 256;
+    c->threads = cfg->threads > 0 ? cfg->threads : 128;
     if (c->threads % 32 != 0 || c->threads > 256) {
         delete c;
         return fail(PMC_ERR_INVALID, "threads must be a multiple of 32, at most 256");
@@ -579,10 +589,12 @@ static int traced_or_replay(pmc_ctx *c, int64_t n, const pmc_trial *in, pmc_tria
     uint8_t *d_acc = nullptr;
     double *d_dE = nullptr;
     std::vector<pmc_trial> fixed;
+    bool replay_swaps = false;
     if (in) {
         fixed.assign(in, in + tot);
         for (auto &t : fixed) {
             if (t.kind == PMC_MOVE_DISPLACEMENT) t.j = -1;
+            if (t.kind == PMC_MOVE_SWAP) replay_swaps = true;
             const bool ok = t.move >= 0 && t.move < PMC_MAX_MOVES && t.i >= 0 && t.i < c->cfg.n_particles &&
                             (t.kind == PMC_MOVE_DISPLACEMENT ||
                              (t.kind == PMC_MOVE_SWAP && t.j >= 0 && t.j < c->cfg.n_particles && t.j != t.i));
@@ -596,7 +608,7 @@ static int traced_or_replay(pmc_ctx *c, int64_t n, const pmc_trial *in, pmc_tria
     if (e == cudaSuccess) {
         const size_t saved_moves = c->pool.size();
         if (in && c->pool.empty()) c->pool.push_back(pmc_move{PMC_MOVE_DISPLACEMENT, 0, 0, 0, 1.0, 1.0});
-        rc = in ? sweep(c, n, d_tr, nullptr, d_acc, d_dE, true) : sweep(c, n, nullptr, d_tr, d_acc, d_dE, false);
+        rc = in ? sweep(c, n, d_tr, nullptr, d_acc, d_dE, true, replay_swaps) : sweep(c, n, nullptr, d_tr, d_acc, d_dE, false);
         if (in && saved_moves == 0) c->pool.clear();
         if (rc == PMC_OK) {
             if (out) e = cudaMemcpyAsync(out, d_tr, sizeof(pmc_trial) * tot, cudaMemcpyDeviceToHost, c->stream);

@@ -19,6 +19,7 @@
 #include <type_traits>
 
 #include "chains.cuh"
+#include "chains_fast.cuh"
 #include "common.cuh"
 #include "rng.cuh"
 
@@ -27,26 +28,40 @@ namespace pmc {
 namespace {
 
 constexpr int kMaxThreads = 256;  // CTA size limit of the sweep kernel
-constexpr int kMinBlocks = 4;     // resident CTAs per SM the register allocation is sized for
 constexpr int kMaxWarps = kMaxThreads / 32;
-constexpr int kBatch = 64;  // proposals generated per batch (parked in shared memory)
+constexpr int kBatch = 32;    // proposals generated per batch (parked in shared memory)
+constexpr int kRegCand = 8;   // FILTER: candidates per thread whose fixed-point coordinates live in registers
 
-struct SweepSmem {
+// One parked proposal (what sample_action! draws + the acceptance threshold), 80 bytes.
+struct __align__(16) TrialRec {
+    double delta[3];
+    double thr;                       // -T*log(u), or u itself in exact_exp mode
+    int dint[3];                      // FILTER: delta in fixed-point units
+    int i;                            // particle i, or slot ka in the species-A list for swaps
+    int j;                            // slot kb for swaps, -2 for displacements
+    int m;                            // pool index
+    int pad[2];
+    uint32_t thr_t[PMC_MAX_SPECIES];  // FILTER: (rc_s + |delta|/2)^2 in fixed-point units
+};
+
+// Fixed-size part of the CTA state: statically allocated so every access is a constant shared-memory
+// offset (no pointer registers on the serial path).
+struct __align__(16) SweepStatic {
+    TrialRec trial[kBatch];
+    double par[PMC_MAX_SPECIES * PMC_MAX_SPECIES * PMC_NPAR];
+    double red[2][kMaxWarps];
+    double rcs[PMC_MAX_SPECIES];            // FILTER: largest cutoff radius per species of the moved particle
+    unsigned long long cnt[2][PMC_MAX_MOVES];  // calls, accepted
+    uint32_t thr_u[PMC_MAX_SPECIES + 4];    // FILTER: cutoff^2 in fixed-point units per species; [4] = global
+    int spoff[PMC_MAX_SPECIES + 4];
+};
+
+// N-dependent part, carved from dynamic shared memory.
+struct SweepDyn {
     double *x;        // [DIM][Npad] wrapped positions (source of truth)
-    double *par;      // [ns*ns*PMC_NPAR]
-    double *red;      // [2][kMaxWarps]
-    double *delta;    // [kBatch][3]
-    double *thr;      // [kBatch]  -T*log(u)  (or u itself in exact_exp mode)
-    unsigned long long *cnt;  // [2][PMC_MAX_MOVES] calls, accepted
     uint32_t *u;      // [DIM][Npad] FILTER: positions as 32-bit fixed-point fractions of L
-    int *dint;        // [kBatch][3] FILTER: delta in the same fixed-point units
-    uint32_t *thr_u;  // [PMC_MAX_SPECIES+1] FILTER: cutoff^2 in fixed-point units per species of i; last = global
-    int *ti;          // [kBatch]  particle i, or slot ka for swaps
-    int *tj;          // [kBatch]  slot kb for swaps
-    int *tm;          // [kBatch]  pool index
-    int *spoff;       // [PMC_MAX_SPECIES+1]
     uint16_t *wq;     // [nwarp][qcap] FILTER: per-warp queues of surviving candidates
-    uint16_t *spids;  // [Npad]
+    uint16_t *spids;  // [Npad] SpeciesList ids grouped by species (swaps)
     uint16_t *heads;  // [Npad]
     uint16_t *bonds;  // [Npad][PMC_MAX_BONDS] (MOL only)
     uint8_t *sp;      // [Npad]
@@ -55,33 +70,22 @@ struct SweepSmem {
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 __host__ __device__ inline int queue_cap(int Npad, int NT) { return (Npad + NT - 1) / NT * 32; }
 
-__host__ __device__ inline size_t carve_sweep(SweepSmem &s, unsigned char *base, int dim, int Npad, int ns, int NT,
-                                              bool mol, bool any_swap, bool filter) {
+__host__ __device__ inline size_t carve_sweep(SweepDyn &s, unsigned char *base, int dim, int Npad, int NT, bool mol,
+                                              bool any_swap, bool filter) {
     size_t o = 0;
     auto take = [&](size_t bytes) {
         unsigned char *p = base + o;
-        o += align_up(bytes, 8);
+        o += align_up(bytes, 16);
         return p;
     };
     s.x = (double *)take(sizeof(double) * dim * Npad);
-    s.par = (double *)take(sizeof(double) * ns * ns * PMC_NPAR);
-    s.red = (double *)take(sizeof(double) * 2 * kMaxWarps);
-    s.delta = (double *)take(sizeof(double) * 3 * kBatch);
-    s.thr = (double *)take(sizeof(double) * kBatch);
-    s.cnt = (unsigned long long *)take(sizeof(unsigned long long) * 2 * PMC_MAX_MOVES);
     s.u = (uint32_t *)take(filter ? sizeof(uint32_t) * dim * Npad : 0);
-    s.dint = (int *)take(filter ? sizeof(int) * 3 * kBatch : 0);
-    s.thr_u = (uint32_t *)take(sizeof(uint32_t) * 8);
-    s.ti = (int *)take(sizeof(int) * kBatch);
-    s.tj = (int *)take(sizeof(int) * kBatch);
-    s.tm = (int *)take(sizeof(int) * kBatch);
-    s.spoff = (int *)take(sizeof(int) * 8);
     s.wq = (uint16_t *)take(filter ? sizeof(uint16_t) * (NT / 32) * queue_cap(Npad, NT) : 0);
     s.spids = (uint16_t *)take(any_swap ? sizeof(uint16_t) * Npad : 0);
     s.heads = (uint16_t *)take(any_swap ? sizeof(uint16_t) * Npad : 0);
     s.bonds = (uint16_t *)take(mol ? sizeof(uint16_t) * Npad * PMC_MAX_BONDS : 0);
     s.sp = (uint8_t *)take(Npad);
-    return align_up(o, 16);
+    return o;
 }
 
 template <int DIM>
@@ -96,12 +100,14 @@ __device__ __forceinline__ double dist2(const double *__restrict__ sx, int Npad,
 // Squared nearest-image separation in fixed-point units: coordinates are 32-bit fractions of the (cubic)
 // box, so the wrapping subtraction IS the minimum image; hi32(d*d) summed over axes is r^2 * 2^32 / L^2.
 template <int DIM>
-__device__ __forceinline__ uint32_t dist2_fixed(const uint32_t *__restrict__ su, int Npad, int j, const uint32_t (&ui)[3]) {
-    const int dx = (int)(ui[0] - su[j]), dy = (int)(ui[1] - su[Npad + j]);
-    uint32_t r = (uint32_t)__mulhi(dx, dx) + (uint32_t)__mulhi(dy, dy);
+__device__ __forceinline__ uint32_t dist2_fixed(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t a0, uint32_t a1, uint32_t a2) {
+    int d = (int)(c0 - a0);
+    uint32_t r = (uint32_t)__mulhi(d, d);
+    d = (int)(c1 - a1);
+    r += (uint32_t)__mulhi(d, d);
     if constexpr (DIM == 3) {
-        const int dz = (int)(ui[2] - su[2 * Npad + j]);
-        r += (uint32_t)__mulhi(dz, dz);
+        d = (int)(c2 - a2);
+        r += (uint32_t)__mulhi(d, d);
     }
     return r;
 }
@@ -110,15 +116,9 @@ __device__ __forceinline__ uint32_t to_fixed(double x, double scale) {  // scale
     return (uint32_t)__double2ull_rd(x * scale);
 }
 
-// Block-wide sum with one barrier; every thread returns the same bits.  `slot` alternates per trial
-// so that a warp racing ahead into the next trial cannot overwrite partials still being read.
-__device__ __forceinline__ double block_sum(double v, double *red, int slot, int lane, int warp, int nwarp) {
-    v = warp_sum(v);
-    if (lane == 0) red[slot * kMaxWarps + warp] = v;
-    __syncthreads();
-    double s = red[slot * kMaxWarps];
-    for (int w = 1; w < nwarp; w++) s += red[slot * kMaxWarps + w];
-    return s;
+__device__ __forceinline__ uint32_t fixed_threshold(double r2_scaled) {  // r^2 * 2^32 / L^2, + rounding slack
+    const double t = r2_scaled * (1.0 + 1e-9) + 64.0;
+    return t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
 }
 
 template <bool MOL>
@@ -132,7 +132,7 @@ __device__ __forceinline__ bool bonded_to(const uint16_t (&bi)[PMC_MAX_BONDS], i
 
 // Contribution of candidate j to e2 - e1 of a Displacement of particle i (old position xo, new xn).
 template <int DIM, int MODEL, bool MOL>
-__device__ __forceinline__ double displacement_term(const SweepSmem &S, int Npad, int j, const double (&xo)[3],
+__device__ __forceinline__ double displacement_term(const SweepDyn &S, int Npad, int j, const double (&xo)[3],
                                                     const double (&xn)[3], const double (&L)[3],
                                                     const double *__restrict__ prow,
                                                     const uint16_t (&bi)[PMC_MAX_BONDS]) {
@@ -150,9 +150,10 @@ __device__ __forceinline__ double displacement_term(const SweepSmem &S, int Npad
 // Contribution of particle k to e2 - e1 of a DiscreteSwap between i (species si) and j (species sj):
 // the k-terms of both local energies before and after the exchange (src/moves.jl:159-167).
 template <int DIM, int MODEL, bool MOL>
-__device__ __forceinline__ double swap_term(const SweepSmem &S, int Npad, int ns, int k, int i, int j, int si, int sj,
-                                            const double (&xi)[3], const double (&xj)[3], const double (&L)[3],
-                                            const uint16_t (&bi)[PMC_MAX_BONDS], const uint16_t (&bj)[PMC_MAX_BONDS]) {
+__device__ __forceinline__ double swap_term(const SweepDyn &S, const double *__restrict__ par, int Npad, int ns, int k,
+                                            int i, int j, int si, int sj, const double (&xi)[3], const double (&xj)[3],
+                                            const double (&L)[3], const uint16_t (&bi)[PMC_MAX_BONDS],
+                                            const uint16_t (&bj)[PMC_MAX_BONDS]) {
     const int sk_old = S.sp[k];
     int sk_new = sk_old;
     if (k == i) sk_new = sj;
@@ -160,8 +161,8 @@ __device__ __forceinline__ double swap_term(const SweepSmem &S, int Npad, int ns
     double t = 0.0;
     if (k != i) {  // term of particle i's local energy
         const double r2 = dist2<DIM>(S.x, Npad, k, xi, L);
-        const double *po = S.par + (si * ns + sk_old) * PMC_NPAR;
-        const double *pn = S.par + (sj * ns + sk_new) * PMC_NPAR;
+        const double *po = par + (si * ns + sk_old) * PMC_NPAR;
+        const double *pn = par + (sj * ns + sk_new) * PMC_NPAR;
         if (bonded_to<MOL>(bi, k)) {
             t += bond_potential(pn, r2) - bond_potential(po, r2);
         } else {
@@ -171,8 +172,8 @@ __device__ __forceinline__ double swap_term(const SweepSmem &S, int Npad, int ns
     }
     if (k != j) {  // term of particle j's local energy
         const double r2 = dist2<DIM>(S.x, Npad, k, xj, L);
-        const double *po = S.par + (sj * ns + sk_old) * PMC_NPAR;
-        const double *pn = S.par + (si * ns + sk_new) * PMC_NPAR;
+        const double *po = par + (sj * ns + sk_old) * PMC_NPAR;
+        const double *pn = par + (si * ns + sk_new) * PMC_NPAR;
         if (bonded_to<MOL>(bj, k)) {
             t += bond_potential(pn, r2) - bond_potential(po, r2);
         } else {
@@ -185,21 +186,22 @@ __device__ __forceinline__ double swap_term(const SweepSmem &S, int Npad, int ns
 
 // ------------------------------------------------------------------------------------------------
 // Sweep kernel.  FILTER = true (cubic boxes): every candidate first goes through an integer
-// fixed-point distance test on the ALU/FMA-int pipes; only survivors (a conservative superset of the
-// pairs inside the cutoff) are compacted per warp and evaluated in fp64.  The result is the same set of
-// fp64 pair terms as FILTER = false, which visits all candidates in fp64.
+// fixed-point distance test on the ALU / integer-FMA pipes; only survivors (a conservative superset of
+// the pairs inside the cutoff) are compacted per warp and evaluated in fp64.  The result is the same set
+// of fp64 pair terms as FILTER = false, which visits all candidates in fp64.
 // ------------------------------------------------------------------------------------------------
-template <int DIM, int MODEL, bool MOL, bool FILTER>
-__global__ void __launch_bounds__(kMaxThreads, kMinBlocks) k_chain_sweep(const __grid_constant__ ChainArgs A) {
+template <int DIM, int MODEL, bool MOL, bool FILTER, int NTMAX>
+__global__ void __launch_bounds__(NTMAX, NTMAX <= 128 ? 5 : 2) k_chain_sweep(const __grid_constant__ ChainArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ SweepStatic T;
     const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = NT >> 5;
     const int c = blockIdx.x;
     const int N = A.N, Npad = A.Npad, ns = A.ns;
-    SweepSmem S;
-    carve_sweep(S, smem_raw, DIM, Npad, ns, NT, MOL, A.any_swap != 0, FILTER);
+    SweepDyn S;
+    carve_sweep(S, smem_raw, DIM, Npad, NT, MOL, A.any_swap != 0, FILTER);
 
     // ---- load chain state into shared memory --------------------------------------------------
-    double L[3] = {A.box[c * 3 + 0], A.box[c * 3 + 1], A.box[c * 3 + 2]};
+    const double L[3] = {A.box[c * 3 + 0], A.box[c * 3 + 1], A.box[c * 3 + 2]};
     const double fscale = 4294967296.0 / L[0];  // FILTER: fixed-point units per unit length
     double *gx = A.x + (size_t)c * DIM * Npad;
     for (int k = tid; k < DIM * Npad; k += NT) {
@@ -209,7 +211,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) k_chain_sweep(const _
     }
     uint8_t *gsp = A.sp + (size_t)c * Npad;
     for (int k = tid; k < Npad; k += NT) S.sp[k] = gsp[k];
-    for (int k = tid; k < ns * ns * PMC_NPAR; k += NT) S.par[k] = A.par[k];
+    for (int k = tid; k < ns * ns * PMC_NPAR; k += NT) T.par[k] = A.par[k];
     if (A.any_swap) {
         const uint16_t *gi = A.spids + (size_t)c * Npad, *gh = A.heads + (size_t)c * Npad;
         for (int k = tid; k < Npad; k += NT) {
@@ -217,22 +219,32 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) k_chain_sweep(const _
             S.heads[k] = gh[k];
         }
     }
-    if (tid <= PMC_MAX_SPECIES) S.spoff[tid] = A.spoff[c * (PMC_MAX_SPECIES + 1) + tid];
-    if (tid < 2 * PMC_MAX_MOVES) S.cnt[tid] = 0ull;
+    if (tid <= PMC_MAX_SPECIES) T.spoff[tid] = A.spoff[c * (PMC_MAX_SPECIES + 1) + tid];
+    if (tid < 2 * PMC_MAX_MOVES) (&T.cnt[0][0])[tid] = 0ull;
     if constexpr (MOL) {
         for (int k = tid; k < Npad * PMC_MAX_BONDS; k += NT) S.bonds[k] = A.bonds[k];
     }
+    // FILTER: the first kRegCand * NT candidates keep their fixed-point coordinates in REGISTERS of the
+    // thread that owns them (candidate j = k * NT + tid lives in slot k of thread tid), so the scan has no
+    // loads or address arithmetic; candidates beyond that (large N) are scanned from shared memory.
+    uint32_t myu[kRegCand][DIM];
     if constexpr (FILTER) {
-        if (tid <= PMC_MAX_SPECIES) {  // conservative integer cutoffs: per species of i, and global (swaps)
+#pragma unroll
+        for (int k = 0; k < kRegCand; k++) {
+            const int j = k * NT + tid;
+#pragma unroll
+            for (int a = 0; a < DIM; a++) myu[k][a] = j < Npad ? to_fixed(gx[a * Npad + j], fscale) : 0u;
+        }
+        if (tid <= PMC_MAX_SPECIES) {  // conservative cutoffs per species of the moved particle; [4] = global
             double rc2 = 0.0;
             for (int a = 0; a < ns; a++)
                 for (int b = 0; b < ns; b++)
                     if (tid == PMC_MAX_SPECIES || a == tid) rc2 = fmax(rc2, A.par[(a * ns + b) * PMC_NPAR + PMC_P_RCUT2]);
-            const double t = rc2 * (1.0 + 1e-9) * (fscale / L[0]) + 64.0;  // r^2 * 2^32 / L^2, + rounding slack
-            S.thr_u[tid] = t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
+            T.thr_u[tid] = fixed_threshold(rc2 * (fscale / L[0]));
+            if (tid < PMC_MAX_SPECIES) T.rcs[tid] = sqrt(rc2);
         }
     }
-    const double T = A.temp[c];
+    const double Tk = A.temp[c];
     double E = A.energy[c];
     const uint32_t k0 = (uint32_t)A.seed, k1 = (uint32_t)(A.seed >> 32);
     const uint32_t gchain = (uint32_t)(A.chain_offset + c);
@@ -254,7 +266,6 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) k_chain_sweep(const _
             pmc_trial tr;
             if (A.replay) {
                 tr = A.replay[(size_t)c * A.n_trials + q];
-                S.thr[t_] = A.exact_exp ? tr.u : -T * log(tr.u);
             } else {
                 const unsigned long long t = A.t0 + (unsigned long long)q;
                 const Philox4 a = philox4x32_10((uint32_t)t, (uint32_t)(t >> 32), gchain, 0u, k0, k1);
@@ -266,7 +277,6 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) k_chain_sweep(const _
                 tr.u = uniform53(a.v[2], a.v[3]);
                 tr.move = m;
                 tr.kind = A.mv_kind[m];
-                S.thr[t_] = A.exact_exp ? tr.u : -T * log(tr.u);
                 if (tr.kind == PMC_MOVE_DISPLACEMENT) {
                     float z0, z1, z2, z3;
                     box_muller(b.v[0], b.v[1], z0, z1);
@@ -278,43 +288,55 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) k_chain_sweep(const _
                     tr.delta[1] = (double)(sg * z1);
                     tr.delta[2] = (DIM == 3) ? (double)(sg * z2) : 0.0;
                 } else {  // slots in the species lists; resolved to particles when the trial executes
-                    const int nA = S.spoff[A.mv_a[m] + 1] - S.spoff[A.mv_a[m]];
-                    const int nB = S.spoff[A.mv_b[m] + 1] - S.spoff[A.mv_b[m]];
+                    const int nA = T.spoff[A.mv_a[m] + 1] - T.spoff[A.mv_a[m]];
+                    const int nB = T.spoff[A.mv_b[m] + 1] - T.spoff[A.mv_b[m]];
                     tr.i = (nA > 0 && nB > 0) ? (int)bounded(a.v[1], (uint32_t)nA) : -1;
                     tr.j = (nA > 0 && nB > 0) ? (int)bounded(b.v[0], (uint32_t)nB) : -1;
                     tr.delta[0] = tr.delta[1] = tr.delta[2] = 0.0;
                 }
                 if (A.trace) A.trace[(size_t)c * A.n_trials + q] = tr;
             }
-            S.tm[t_] = tr.move;
-            S.ti[t_] = tr.i;
-            S.tj[t_] = (tr.kind == PMC_MOVE_SWAP) ? tr.j : -2;  // -2 marks a displacement
+            TrialRec &R = T.trial[t_];
+            R.thr = A.exact_exp ? tr.u : -Tk * log(tr.u);
+            R.m = tr.move;
+            R.i = tr.i;
+            R.j = (tr.kind == PMC_MOVE_SWAP) ? tr.j : -2;  // -2 marks a displacement
 #pragma unroll
             for (int a = 0; a < 3; a++) {
-                S.delta[3 * t_ + a] = tr.delta[a];
-                if constexpr (FILTER) S.dint[3 * t_ + a] = (int)__double2ll_rn(tr.delta[a] * fscale);
+                R.delta[a] = tr.delta[a];
+                if constexpr (FILTER) R.dint[a] = (int)__double2ll_rn(tr.delta[a] * fscale);
+            }
+            if constexpr (FILTER) {
+                // one sphere around the midpoint of old and new position covers both cutoff spheres
+                const double hd = 0.5 * sqrt(tr.delta[0] * tr.delta[0] + tr.delta[1] * tr.delta[1] + tr.delta[2] * tr.delta[2]);
+                for (int sp_ = 0; sp_ < PMC_MAX_SPECIES; sp_++) {
+                    const double r = T.rcs[sp_ < ns ? sp_ : 0] + hd;
+                    R.thr_t[sp_] = fixed_threshold(r * r * (fscale / L[0]));
+                }
             }
         }
         __syncthreads();
 
         // ---- the serial chain: one trial at a time ---------------------------------------------
         for (int b = 0; b < nb; b++) {
-            const int m = S.tm[b];
-            const bool is_disp = S.tj[b] == -2;
+            const TrialRec &R = T.trial[b];
+            const int m = R.m;
+            const bool is_disp = R.j == -2;
             double part = 0.0, dE;
             bool acc;
             if (is_disp) {
-                const int i = S.ti[b];
+                const int i = R.i;
                 double xo[3] = {0.0, 0.0, 0.0}, xn[3] = {0.0, 0.0, 0.0};
                 int w[3] = {0, 0, 0};
                 // The owner thread (i % NT) commits accepted positions after the barrier of the
                 // previous trial; every other thread only ever reads x[i] here, at the start of a
                 // trial.  A commit becomes visible at the NEXT barrier, so the only unordered read
                 // is "same particle as the most recent commit" -- served from registers instead.
+                const bool fwd = (i == last_i);
 #pragma unroll
                 for (int a = 0; a < DIM; a++) {
-                    xo[a] = (i == last_i) ? last_x[a] : S.x[a * Npad + i];
-                    xn[a] = wrap1(xo[a] + S.delta[3 * b + a], L[a], w[a]);
+                    xo[a] = fwd ? last_x[a] : S.x[a * Npad + i];
+                    xn[a] = wrap1(xo[a] + R.delta[a], L[a], w[a]);
                 }
                 const int si = S.sp[i];
                 uint16_t bi[PMC_MAX_BONDS];
@@ -322,46 +344,72 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) k_chain_sweep(const _
 #pragma unroll
                     for (int k = 0; k < PMC_MAX_BONDS; k++) bi[k] = S.bonds[i * PMC_MAX_BONDS + k];
                 }
-                const double *prow = S.par + si * ns * PMC_NPAR;
+                const double *prow = T.par + si * ns * PMC_NPAR;
                 uint32_t un[3] = {0u, 0u, 0u};
                 if constexpr (FILTER) {
-                    uint32_t uo[3] = {0u, 0u, 0u};
+                    uint32_t um[3] = {0u, 0u, 0u};
 #pragma unroll
                     for (int a = 0; a < DIM; a++) {
-                        uo[a] = (i == last_i) ? last_u[a] : S.u[a * Npad + i];
-                        un[a] = uo[a] + (uint32_t)S.dint[3 * b + a];  // wraps like the box does
+                        const uint32_t uo = fwd ? last_u[a] : S.u[a * Npad + i];
+                        un[a] = uo + (uint32_t)R.dint[a];        // wraps like the box does
+                        um[a] = uo + (uint32_t)(R.dint[a] >> 1);  // midpoint of old and new
                     }
-                    const uint32_t thr = S.thr_u[si];
+                    const uint32_t thr = R.thr_t[si];
+                    // Branch-free scan of all candidates against ONE sphere (midpoint, rc + |delta|/2).  Self
+                    // and padding entries are not excluded here (the fp64 pass drops them).  Per candidate:
+                    // 3 wrapping subtractions (= minimum image), 3 mul-hi accumulate, compare, vote, compact.
                     int cnt = 0;
-                    for (int j0 = 0; j0 < Npad; j0 += NT) {
-                        const int j = j0 + tid;
-                        bool pass = false;
-                        if (j < N && j != i) {
-                            pass = dist2_fixed<DIM>(S.u, Npad, j, uo) <= thr || dist2_fixed<DIM>(S.u, Npad, j, un) <= thr ||
-                                   bonded_to<MOL>(bi, j);
+#pragma unroll
+                    for (int k = 0; k < kRegCand; k++) {
+                        if (k * NT < Npad) {  // uniform
+                            bool pass = dist2_fixed<DIM>(um[0], um[1], um[2], myu[k][0], myu[k][1], DIM == 3 ? myu[k][DIM - 1] : 0u) <= thr;
+                            if constexpr (MOL) pass |= bonded_to<MOL>(bi, k * NT + tid);
+                            const unsigned mask = __ballot_sync(0xffffffffu, pass);
+                            if (pass) myq[cnt + __popc(mask & lt_mask)] = (uint16_t)(k * NT + tid);
+                            cnt += __popc(mask);
                         }
+                    }
+                    for (int j0 = kRegCand * NT + tid; j0 < Npad + tid; j0 += NT) {  // large N: the rest from smem
+                        const int jc = min(j0, Npad - 1);
+                        bool pass = dist2_fixed<DIM>(um[0], um[1], um[2], S.u[jc], S.u[Npad + jc], DIM == 3 ? S.u[(DIM - 1) * Npad + jc] : 0u) <= thr;
+                        if constexpr (MOL) pass |= bonded_to<MOL>(bi, j0);
                         const unsigned mask = __ballot_sync(0xffffffffu, pass);
-                        if (pass) myq[cnt + __popc(mask & lt_mask)] = (uint16_t)j;
+                        if (pass) myq[cnt + __popc(mask & lt_mask)] = (uint16_t)j0;
                         cnt += __popc(mask);
                     }
                     __syncwarp();
-                    for (int q = lane; q < cnt; q += 32)
-                        part += displacement_term<DIM, MODEL, MOL>(S, Npad, myq[q], xo, xn, L, prow, bi);
+                    for (int q = lane; q < cnt; q += 32) {
+                        const int j = myq[q];
+                        if (j < N && j != i) part += displacement_term<DIM, MODEL, MOL>(S, Npad, j, xo, xn, L, prow, bi);
+                    }
                     __syncwarp();
                 } else {
                     for (int j = tid; j < N; j += NT)
                         if (j != i) part += displacement_term<DIM, MODEL, MOL>(S, Npad, j, xo, xn, L, prow, bi);
                 }
-                dE = block_sum(part, S.red, slot, lane, warp, nwarp);
+                // block-wide sum, one barrier; every thread ends with the same bits.  `slot` alternates so a
+                // warp racing ahead into the next trial cannot overwrite partials still being read.
+                part = warp_sum(part);
+                if (lane == 0) T.red[slot][warp] = part;
+                __syncthreads();
+                dE = T.red[slot][0];
+                for (int w_ = 1; w_ < nwarp; w_++) dE += T.red[slot][w_];
                 slot ^= 1;
-                acc = A.exact_exp ? accept_exact(dE, T, S.thr[b]) : (dE < S.thr[b]);
+                acc = A.exact_exp ? accept_exact(dE, Tk, R.thr) : (dE < R.thr);
                 if (acc) {
                     if (tid == i % NT) {
 #pragma unroll
                         for (int a = 0; a < DIM; a++) {
                             S.x[a * Npad + i] = xn[a];
-                            if constexpr (FILTER) S.u[a * Npad + i] = to_fixed(xn[a], fscale);
                             if (w[a] != 0) atomicAdd(&gimg[a * Npad + i], w[a]);
+                            if constexpr (FILTER) {
+                                const uint32_t v = to_fixed(xn[a], fscale);
+                                S.u[a * Npad + i] = v;
+                                const int ki = i / NT;
+#pragma unroll
+                                for (int k = 0; k < kRegCand; k++)
+                                    if (k == ki) myu[k][a] = v;
+                            }
                         }
                     }
                     last_i = i;
@@ -375,14 +423,14 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) k_chain_sweep(const _
             } else {
                 // DiscreteSwap: i from the species-A list, j from the species-B list; positions fixed,
                 // four local energies folded into one pass (src/moves.jl:159-167).
-                const int ka = S.ti[b], kb = S.tj[b];
+                const int ka = R.i, kb = R.j;
                 int i = -1, j = -1;
                 if (A.replay) {
                     i = ka;
                     j = kb;
                 } else if (ka >= 0) {
-                    i = S.spids[S.spoff[A.mv_a[m]] + ka];
-                    j = S.spids[S.spoff[A.mv_b[m]] + kb];
+                    i = S.spids[T.spoff[A.mv_a[m]] + ka];
+                    j = S.spids[T.spoff[A.mv_b[m]] + kb];
                 }
                 if (i >= 0 && j >= 0) {
                     double xi[3] = {0.0, 0.0, 0.0}, xj[3] = {0.0, 0.0, 0.0};
@@ -407,32 +455,36 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) k_chain_sweep(const _
                             ui[a] = (i == last_i) ? last_u[a] : S.u[a * Npad + i];
                             uj[a] = (j == last_i) ? last_u[a] : S.u[a * Npad + j];
                         }
-                        const uint32_t thr = S.thr_u[PMC_MAX_SPECIES];
+                        const uint32_t thr = T.thr_u[PMC_MAX_SPECIES];
                         int cnt = 0;
-                        for (int k0_ = 0; k0_ < Npad; k0_ += NT) {
-                            const int k = k0_ + tid;
-                            bool pass = false;
-                            if (k < N) {
-                                pass = (k != i && dist2_fixed<DIM>(S.u, Npad, k, ui) <= thr) ||
-                                       (k != j && dist2_fixed<DIM>(S.u, Npad, k, uj) <= thr) || bonded_to<MOL>(bi, k) ||
-                                       bonded_to<MOL>(bj, k);
-                            }
+                        for (int k_ = tid; k_ < Npad + tid; k_ += NT) {
+                            const int kc = min(k_, Npad - 1);
+                            const uint32_t a0 = S.u[kc], a1 = S.u[Npad + kc], a2 = DIM == 3 ? S.u[(DIM - 1) * Npad + kc] : 0u;
+                            bool pass = min(dist2_fixed<DIM>(ui[0], ui[1], ui[2], a0, a1, a2),
+                                            dist2_fixed<DIM>(uj[0], uj[1], uj[2], a0, a1, a2)) <= thr;
+                            if constexpr (MOL) pass |= bonded_to<MOL>(bi, k_) || bonded_to<MOL>(bj, k_);
                             const unsigned mask = __ballot_sync(0xffffffffu, pass);
-                            if (pass) myq[cnt + __popc(mask & lt_mask)] = (uint16_t)k;
+                            if (pass) myq[cnt + __popc(mask & lt_mask)] = (uint16_t)k_;
                             cnt += __popc(mask);
                         }
                         __syncwarp();
-                        for (int q = lane; q < cnt; q += 32)
-                            part += swap_term<DIM, MODEL, MOL>(S, Npad, ns, myq[q], i, j, si, sj, xi, xj, L, bi, bj);
+                        for (int q = lane; q < cnt; q += 32) {
+                            const int k = myq[q];
+                            if (k < N) part += swap_term<DIM, MODEL, MOL>(S, T.par, Npad, ns, k, i, j, si, sj, xi, xj, L, bi, bj);
+                        }
                         __syncwarp();
                     } else {
                         for (int k = tid; k < N; k += NT)
-                            part += swap_term<DIM, MODEL, MOL>(S, Npad, ns, k, i, j, si, sj, xi, xj, L, bi, bj);
+                            part += swap_term<DIM, MODEL, MOL>(S, T.par, Npad, ns, k, i, j, si, sj, xi, xj, L, bi, bj);
                     }
                 }
-                dE = block_sum(part, S.red, slot, lane, warp, nwarp);
+                part = warp_sum(part);
+                if (lane == 0) T.red[slot][warp] = part;
+                __syncthreads();
+                dE = T.red[slot][0];
+                for (int w_ = 1; w_ < nwarp; w_++) dE += T.red[slot][w_];
                 slot ^= 1;
-                acc = (i >= 0 && j >= 0) && (A.exact_exp ? accept_exact(dE, T, S.thr[b]) : (dE < S.thr[b]));
+                acc = (i >= 0 && j >= 0) && (A.exact_exp ? accept_exact(dE, Tk, R.thr) : (dE < R.thr));
                 if (acc) {
                     if (tid == 0) {
                         const uint8_t si = S.sp[i], sj = S.sp[j];
@@ -440,8 +492,8 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) k_chain_sweep(const _
                         S.sp[j] = si;
                         if (A.any_swap) {  // update_species_list! (src/moves.jl:175-179)
                             const uint16_t hi = S.heads[i], hj = S.heads[j];
-                            S.spids[S.spoff[si] + hi] = (uint16_t)j;
-                            S.spids[S.spoff[sj] + hj] = (uint16_t)i;
+                            S.spids[T.spoff[si] + hi] = (uint16_t)j;
+                            S.spids[T.spoff[sj] + hj] = (uint16_t)i;
                             S.heads[i] = hj;
                             S.heads[j] = hi;
                         }
@@ -456,8 +508,8 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) k_chain_sweep(const _
                 }
             }
             if (tid == 0) {
-                S.cnt[m] += 1ull;
-                S.cnt[PMC_MAX_MOVES + m] += acc ? 1ull : 0ull;
+                T.cnt[0][m] += 1ull;
+                T.cnt[1][m] += acc ? 1ull : 0ull;
                 if (A.acc_out) A.acc_out[(size_t)c * A.n_trials + tb + b] = acc ? 1 : 0;
                 if (A.dE_out) A.dE_out[(size_t)c * A.n_trials + tb + b] = dE;
             }
@@ -477,8 +529,8 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) k_chain_sweep(const _
     }
     if (tid == 0) A.energy[c] = E;
     if (tid < A.n_moves) {
-        A.calls[(size_t)c * PMC_MAX_MOVES + tid] += S.cnt[tid];
-        A.accepted[(size_t)c * PMC_MAX_MOVES + tid] += S.cnt[PMC_MAX_MOVES + tid];
+        A.calls[(size_t)c * PMC_MAX_MOVES + tid] += T.cnt[0][tid];
+        A.accepted[(size_t)c * PMC_MAX_MOVES + tid] += T.cnt[1][tid];
     }
 }
 
@@ -561,9 +613,9 @@ cudaError_t dispatch(int dim, int model, bool mol, F &&f) {
 
 }  // namespace
 
-size_t chain_sweep_smem_bytes(int dim, int Npad, int ns, int threads, bool mol, bool any_swap, bool filter) {
-    SweepSmem s;
-    return carve_sweep(s, nullptr, dim, Npad, ns, threads, mol, any_swap, filter);
+size_t chain_sweep_smem_bytes(int dim, int Npad, int, int threads, bool mol, bool any_swap, bool filter) {
+    SweepDyn s;
+    return carve_sweep(s, nullptr, dim, Npad, threads, mol, any_swap, filter);
 }
 
 size_t chain_energy_smem_bytes(int dim, int Npad, int ns, bool) {
@@ -575,26 +627,69 @@ cudaError_t configure_chain_kernels(int dim, int model, bool mol, size_t sweep_s
     return dispatch(dim, model, mol, [&](auto D, auto MDL, auto ML) {
         constexpr int d = decltype(D)::value, mdl = decltype(MDL)::value;
         constexpr bool ml = decltype(ML)::value;
-        cudaError_t e = cudaFuncSetAttribute(k_chain_sweep<d, mdl, ml, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)sweep_smem);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(k_chain_sweep<d, mdl, ml, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)sweep_smem_filter);
-        if (e != cudaSuccess) return e;
-        return cudaFuncSetAttribute(k_chain_energy<d, mdl, ml>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)energy_smem);
+        const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
+        cudaError_t e = cudaFuncSetAttribute(k_chain_sweep<d, mdl, ml, false, 128>, attr, (int)sweep_smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_chain_sweep<d, mdl, ml, false, 256>, attr, (int)sweep_smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_chain_sweep<d, mdl, ml, true, 128>, attr, (int)sweep_smem_filter);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_chain_sweep<d, mdl, ml, true, 256>, attr, (int)sweep_smem_filter);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_chain_energy<d, mdl, ml>, attr, (int)energy_smem);
+        return e;
     });
 }
 
+// Two register budgets per kernel: CTAs of <= 128 threads are compiled for 5 resident CTAs per SM (the
+// shared-memory residency at N = 1000), larger CTAs for 2.
 cudaError_t launch_chain_sweep(int dim, int model, bool mol, bool filter, int M, int threads, size_t smem,
                                const ChainArgs &a, cudaStream_t st) {
     return dispatch(dim, model, mol, [&](auto D, auto MDL, auto ML) {
         constexpr int d = decltype(D)::value, mdl = decltype(MDL)::value;
         constexpr bool ml = decltype(ML)::value;
-        if (filter)
-            k_chain_sweep<d, mdl, ml, true><<<M, threads, smem, st>>>(a);
-        else
-            k_chain_sweep<d, mdl, ml, false><<<M, threads, smem, st>>>(a);
+        if (threads <= 128) {
+            if (filter)
+                k_chain_sweep<d, mdl, ml, true, 128><<<M, threads, smem, st>>>(a);
+            else
+                k_chain_sweep<d, mdl, ml, false, 128><<<M, threads, smem, st>>>(a);
+        } else {
+            if (filter)
+                k_chain_sweep<d, mdl, ml, true, 256><<<M, threads, smem, st>>>(a);
+            else
+                k_chain_sweep<d, mdl, ml, false, 256><<<M, threads, smem, st>>>(a);
+        }
+        return cudaGetLastError();
+    });
+}
+
+bool chain_fast_supported(int Npad, int threads) {
+    return Npad <= fast::kFastMaxCand * fast::kFastThreads && threads == fast::kFastThreads;
+}
+
+static int fast_npad(int Npad) { return Npad <= 256 ? 256 : (Npad <= 512 ? 512 : 1024); }
+
+size_t chain_fast_smem_bytes(int dim, int Npad, int) {
+    return fast::fast_layout(dim, fast_npad(Npad), PMC_MAX_SPECIES).total;
+}
+
+template <typename F>
+static cudaError_t fast_dispatch(int dim, int model, int Npad, F &&f) {
+    return dispatch(dim, model, false, [&](auto D, auto MDL, auto) {
+        constexpr int d = decltype(D)::value, mdl = decltype(MDL)::value;
+        switch (fast_npad(Npad)) {
+        case 256: return f(fast::k_chain_sweep_fast<d, mdl, 256>);
+        case 512: return f(fast::k_chain_sweep_fast<d, mdl, 512>);
+        default: return f(fast::k_chain_sweep_fast<d, mdl, 1024>);
+        }
+    });
+}
+
+cudaError_t configure_chain_fast(int dim, int model, int Npad, size_t smem) {
+    return fast_dispatch(dim, model, Npad, [&](auto kernel) {
+        return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    });
+}
+
+cudaError_t launch_chain_sweep_fast(int dim, int model, int M, size_t smem, const ChainArgs &a, cudaStream_t st) {
+    return fast_dispatch(dim, model, a.Npad, [&](auto kernel) {
+        kernel<<<M, fast::kFastThreads, smem, st>>>(a);
         return cudaGetLastError();
     });
 }

@@ -1,0 +1,369 @@
+// chains_fast.cuh -- hand-scheduled sweep kernel for the dominant PMC_MODE_CHAINS case:
+// Atoms (no bonds), Displacement-only pools, cubic box, N <= kFastCand * kFastThreads (= 1024).
+// Same algorithm and the same fp64 pair terms as k_chain_sweep<FILTER = true> in chains.cu (which remains the
+// general kernel: swaps, molecules, larger N, non-cubic boxes); what changes is how the work is issued:
+//
+//   * ALL shared-memory traffic goes through explicit 32-bit shared addresses (ld.shared / st.shared), one
+//     base register + constant offsets, instead of ~20 generic pointers the compiler kept re-deriving;
+//   * each thread keeps the fixed-point coordinates of its 8 candidates in registers, so the candidate scan
+//     is 3 subtract + 3 mul-hi + compare per candidate with no loads;
+//   * survivors are compacted with ONE warp prefix sum per trial (per-thread bit mask -> shuffle scan)
+//     instead of one ballot + popc + store sequence per candidate;
+//   * no forwarding registers: every thread performs the (identical) commit stores, so each thread's own
+//     program order makes committed positions visible to it without a second barrier.
+//
+// The kernel is issue-bound (ncu: profiles/), so instruction count per trial is the figure of merit.
+#pragma once
+#include "chains.cuh"
+#include "common.cuh"
+#include "rng.cuh"
+
+namespace pmc {
+namespace fast {
+
+constexpr int kFastThreads = 128;
+constexpr int kFastWarps = kFastThreads / 32;
+constexpr int kFastMaxCand = 8; // candidates per thread (registers) at the largest padded size
+constexpr int kFastBatch = 32;  // parked proposals
+constexpr int kRecBytes = 80;   // trial record stride
+
+// ---- explicit shared-memory accessors (32-bit shared-window addresses) ---------------------------------
+__device__ __forceinline__ double lds_f64(uint32_t a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void lds_f64x2(uint32_t a, double &v0, double &v1) {
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v0), "=d"(v1) : "r"(a) : "memory");
+}
+__device__ __forceinline__ void lds_s32x4(uint32_t a, int &v0, int &v1, int &v2, int &v3) {
+    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(a) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_f64(uint32_t a, double v) {
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
+}
+__device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) {
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+
+// Dynamic shared-memory layout (byte offsets from the base), all 16-byte aligned.
+struct FastLayout {
+    uint32_t x, sp, q, cp, rec, red, cnt, par, rcs, total;
+};
+__host__ __device__ inline FastLayout fast_layout(int dim, int Npad, int ns) {
+    FastLayout f;
+    uint32_t o = 0;
+    auto take = [&](uint32_t bytes) {
+        uint32_t p = o;
+        o += (bytes + 15u) & ~15u;
+        return p;
+    };
+    f.x = take(8u * dim * Npad);
+    f.sp = take(Npad);
+    f.q = take(2u * (uint32_t)Npad);                       // per-warp survivor queues (worst case: all pass)
+    f.cp = take(32u * ns * ns);                            // compact LJ pair table {rc2, eps4, sig2, shift}
+    f.rec = take((uint32_t)kRecBytes * kFastBatch);        // parked proposals
+    f.red = take(8u * 2 * kFastWarps);
+    f.cnt = take(8u * 2 * PMC_MAX_MOVES);
+    f.par = take(8u * ns * ns * PMC_NPAR);                 // full parameter table (non-LJ models)
+    f.rcs = take(8u * PMC_MAX_SPECIES);                    // largest cutoff radius per species of the moved particle
+    f.total = o;
+    return f;
+}
+
+__device__ __forceinline__ uint32_t to_fixed32(double x, double scale) { return (uint32_t)__double2ull_rd(x * scale); }
+
+__device__ __forceinline__ uint32_t fixed_thr(double r2_scaled) {
+    const double t = r2_scaled * (1.0 + 1e-9) + 64.0;
+    return t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
+}
+
+// wrapped-coordinate nearest image, squared, accumulated
+__device__ __forceinline__ double mi_acc(double xi, double xj, double L, double acc) {
+    const double a = fabs(xi - xj);
+    const double r = fmin(a, L - a);
+    return fma(r, r, acc);
+}
+
+// NPAD (compile time): padded particle count of the shared-memory planes, one of 256 / 512 / 1024; makes every
+// shared-memory offset a constant and fixes the number of register-resident candidates per thread.
+template <int DIM, int MODEL, int NPAD>
+__global__ void __launch_bounds__(kFastThreads, 6) k_chain_sweep_fast(const __grid_constant__ ChainArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int kFastCand = NPAD / kFastThreads;
+    constexpr int Npad = NPAD;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int c = blockIdx.x;
+    const int N = A.N, gNpad = A.Npad, ns = A.ns;  // gNpad: stride of the GLOBAL arrays (multiple of 32)
+    const FastLayout F = fast_layout(DIM, Npad, PMC_MAX_SPECIES);
+    const uint32_t sb = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    const uint32_t nb8 = 8u * (uint32_t)Npad;  // byte stride between coordinate planes
+
+    // ---- load chain state -----------------------------------------------------------------------------
+    const double L = A.box[c * 3];
+    const double fscale = 4294967296.0 / L;
+    double *gx = A.x + (size_t)c * DIM * gNpad;
+    {
+        double *sx = (double *)(smem_raw + F.x);
+        for (int a = 0; a < DIM; a++)
+            for (int k = tid; k < Npad; k += kFastThreads) sx[a * Npad + k] = k < gNpad ? gx[a * gNpad + k] : 0.0;
+        uint8_t *ssp = smem_raw + F.sp;
+        const uint8_t *gsp = A.sp + (size_t)c * gNpad;
+        for (int k = tid; k < Npad; k += kFastThreads) ssp[k] = k < gNpad ? gsp[k] : 0;
+        double *spar = (double *)(smem_raw + F.par), *scp = (double *)(smem_raw + F.cp);
+        for (int k = tid; k < ns * ns * PMC_NPAR; k += kFastThreads) spar[k] = A.par[k];
+        for (int k = tid; k < ns * ns; k += kFastThreads) {
+            scp[4 * k + 0] = A.par[k * PMC_NPAR + PMC_P_RCUT2];
+            scp[4 * k + 1] = A.par[k * PMC_NPAR + PMC_P_EPS];
+            scp[4 * k + 2] = A.par[k * PMC_NPAR + PMC_P_SIG2];
+            scp[4 * k + 3] = A.par[k * PMC_NPAR + PMC_P_SHIFT];
+        }
+        unsigned long long *scnt = (unsigned long long *)(smem_raw + F.cnt);
+        if (tid < 2 * PMC_MAX_MOVES) scnt[tid] = 0ull;
+    }
+    // fixed-point coordinates of this thread's candidates j = k * 128 + tid, k = 0..7 (registers)
+    uint32_t myu[kFastCand][DIM];
+#pragma unroll
+    for (int k = 0; k < kFastCand; k++) {
+        const int j = k * kFastThreads + tid;
+#pragma unroll
+        for (int a = 0; a < DIM; a++) myu[k][a] = j < gNpad ? to_fixed32(gx[a * gNpad + j], fscale) : 0u;
+    }
+    if (tid < PMC_MAX_SPECIES) {  // largest cutoff radius per species of the moved particle (filter sphere)
+        double rc2 = 0.0;
+        for (int b = 0; b < ns; b++) rc2 = fmax(rc2, A.par[((tid < ns ? tid : 0) * ns + b) * PMC_NPAR + PMC_P_RCUT2]);
+        ((double *)(smem_raw + F.rcs))[tid] = sqrt(rc2);
+    }
+    const double Tk = A.temp[c];
+    double E = A.energy[c];
+    const uint32_t k0 = (uint32_t)A.seed, k1 = (uint32_t)(A.seed >> 32);
+    const uint32_t gchain = (uint32_t)(A.chain_offset + c);
+    int32_t *gimg = A.img + (size_t)c * DIM * gNpad;
+    const uint32_t qa = sb + F.q + (uint32_t)warp * (2u * kFastCand * 32);
+    uint32_t slot = 0;
+
+    for (long long tb = 0; tb < A.n_trials; tb += kFastBatch) {
+        const int nb = (int)min((long long)kFastBatch, A.n_trials - tb);
+        __syncthreads();
+        // ---- proposals of trials tb .. tb+nb-1 (one warp generates, records parked in shared memory) -----
+        if (tid < nb) {
+            const long long q = tb + tid;
+            pmc_trial tr;
+            if (A.replay) {
+                tr = A.replay[(size_t)c * A.n_trials + q];
+            } else {
+                const unsigned long long t = A.t0 + (unsigned long long)q;
+                const Philox4 a = philox4x32_10((uint32_t)t, (uint32_t)(t >> 32), gchain, 0u, k0, k1);
+                const Philox4 b = philox4x32_10((uint32_t)t, (uint32_t)(t >> 32), gchain, 1u, k0, k1);
+                const double um = (double)a.v[0] * 0x1p-32;
+                int m = A.n_moves - 1;
+                for (int k = A.n_moves - 2; k >= 0; k--)
+                    if (um < A.mv_cum[k]) m = k;
+                float z0, z1, z2, z3;
+                box_muller(b.v[0], b.v[1], z0, z1);
+                box_muller(b.v[2], b.v[3], z2, z3);
+                const float sg = A.mv_sigma[m];
+                tr.u = uniform53(a.v[2], a.v[3]);
+                tr.move = m;
+                tr.kind = PMC_MOVE_DISPLACEMENT;
+                tr.i = (int)bounded(a.v[1], (uint32_t)N);
+                tr.j = -1;
+                tr.delta[0] = (double)(sg * z0);
+                tr.delta[1] = (double)(sg * z1);
+                tr.delta[2] = (DIM == 3) ? (double)(sg * z2) : 0.0;
+                if (A.trace) A.trace[(size_t)c * A.n_trials + q] = tr;
+            }
+            // record layout: f64 delta[3], f64 thr | s32 dint[3], s32 i | s32 m, pad[3] | u32 thr_t[4]
+            unsigned char *rec = smem_raw + F.rec + (size_t)kRecBytes * tid;
+            double *rd = (double *)rec;
+            int *ri = (int *)(rec + 32);
+            uint32_t *rt = (uint32_t *)(rec + 64);
+            rd[0] = tr.delta[0];
+            rd[1] = tr.delta[1];
+            rd[2] = tr.delta[2];
+            rd[3] = A.exact_exp ? tr.u : -Tk * log(tr.u);
+            ri[0] = (int)__double2ll_rn(tr.delta[0] * fscale);
+            ri[1] = (int)__double2ll_rn(tr.delta[1] * fscale);
+            ri[2] = (int)__double2ll_rn(tr.delta[2] * fscale);
+            ri[3] = tr.i;
+            ri[4] = tr.move;
+            // one sphere around the midpoint of old and new position covers both cutoff spheres
+            const double hd = 0.5 * sqrt(tr.delta[0] * tr.delta[0] + tr.delta[1] * tr.delta[1] + tr.delta[2] * tr.delta[2]);
+            const double *rcs = (const double *)(smem_raw + F.rcs);
+#pragma unroll
+            for (int s = 0; s < PMC_MAX_SPECIES; s++) {
+                const double r = rcs[s] + hd;
+                rt[s] = fixed_thr(r * r * (fscale / L));
+            }
+        }
+        __syncthreads();
+
+        // ---- the serial chain -------------------------------------------------------------------------------
+        for (int b = 0; b < nb; b++) {
+            const uint32_t ra = sb + F.rec + (uint32_t)kRecBytes * (uint32_t)b;
+            double d0, d1, d2, thr;
+            int di0, di1, di2, i;
+            lds_f64x2(ra, d0, d1);
+            lds_f64x2(ra + 16, d2, thr);
+            lds_s32x4(ra + 32, di0, di1, di2, i);
+            const uint32_t xa = sb + F.x + 8u * (uint32_t)i;
+            double xo[3], xn[3];
+            xo[0] = lds_f64(xa);
+            xo[1] = lds_f64(xa + nb8);
+            xo[2] = (DIM == 3) ? lds_f64(xa + 2 * nb8) : 0.0;
+            const uint32_t si = lds_u8(sb + F.sp + (uint32_t)i);
+            xn[0] = xo[0] + d0;
+            xn[1] = xo[1] + d1;
+            xn[2] = xo[2] + d2;
+#pragma unroll
+            for (int a = 0; a < DIM; a++) {
+                xn[a] = xn[a] >= L ? xn[a] - L : xn[a];
+                xn[a] = xn[a] < 0.0 ? xn[a] + L : xn[a];
+            }
+            // filter sphere: midpoint of old and new in fixed point, radius from the parked record
+            const uint32_t um0 = to_fixed32(xo[0], fscale) + (uint32_t)(di0 >> 1);
+            const uint32_t um1 = to_fixed32(xo[1], fscale) + (uint32_t)(di1 >> 1);
+            const uint32_t um2 = (DIM == 3) ? to_fixed32(xo[2], fscale) + (uint32_t)(di2 >> 1) : 0u;
+            const uint32_t fthr = lds_u32(ra + 64 + 4u * si);
+            uint32_t m8 = 0;
+#pragma unroll
+            for (int k = 0; k < kFastCand; k++) {
+                int d = (int)(um0 - myu[k][0]);
+                uint32_t r = (uint32_t)__mulhi(d, d);
+                d = (int)(um1 - myu[k][1]);
+                r += (uint32_t)__mulhi(d, d);
+                if constexpr (DIM == 3) {
+                    d = (int)(um2 - myu[k][DIM - 1]);
+                    r += (uint32_t)__mulhi(d, d);
+                }
+                m8 |= (r <= fthr) ? (1u << k) : 0u;
+            }
+            // compaction: warp prefix sum of the per-thread survivor counts
+            const int mine = __popc(m8);
+            int incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                incl += (lane >= o) ? t : 0;
+            }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            uint32_t wp = qa + 2u * (uint32_t)(incl - mine);
+#pragma unroll
+            for (int k = 0; k < kFastCand; k++) {
+                if (m8 & (1u << k)) {
+                    sts_u16(wp, (uint32_t)(k * kFastThreads + tid));
+                    wp += 2;
+                }
+            }
+            __syncwarp();
+            // fp64 pass over this warp's survivors
+            double part = 0.0;
+            const uint32_t prow = si * (uint32_t)ns;
+            for (int q = lane; q < total; q += 32) {
+                const uint32_t j = lds_u16(qa + 2u * (uint32_t)q);
+                if (j < (uint32_t)N && j != (uint32_t)i) {
+                    const uint32_t ja = sb + F.x + 8u * j;
+                    const double xj0 = lds_f64(ja), xj1 = lds_f64(ja + nb8);
+                    double r2o = mi_acc(xo[0], xj0, L, 0.0), r2n = mi_acc(xn[0], xj0, L, 0.0);
+                    r2o = mi_acc(xo[1], xj1, L, r2o);
+                    r2n = mi_acc(xn[1], xj1, L, r2n);
+                    if constexpr (DIM == 3) {
+                        const double xj2 = lds_f64(ja + 2 * nb8);
+                        r2o = mi_acc(xo[2], xj2, L, r2o);
+                        r2n = mi_acc(xn[2], xj2, L, r2n);
+                    }
+                    const uint32_t sj = lds_u8(sb + F.sp + j);
+                    if constexpr (MODEL == PMC_MODEL_LJ || MODEL == PMC_MODEL_KG) {
+                        double rc2, eps4, sig2, shift;
+                        const uint32_t pa = sb + F.cp + 32u * (prow + sj);
+                        lds_f64x2(pa, rc2, eps4);
+                        lds_f64x2(pa + 16, sig2, shift);
+                        const double uo = lj_core(r2o, eps4, sig2) - shift;
+                        const double un = lj_core(r2n, eps4, sig2) - shift;
+                        part += (r2n <= rc2 ? un : 0.0) - (r2o <= rc2 ? uo : 0.0);
+                    } else {
+                        const double *p = (const double *)(smem_raw + F.par) + (prow + sj) * PMC_NPAR;
+                        const double rc2 = p[PMC_P_RCUT2];
+                        if (r2o <= rc2) part -= pair_potential<MODEL>(p, r2o);
+                        if (r2n <= rc2) part += pair_potential<MODEL>(p, r2n);
+                    }
+                }
+            }
+            __syncwarp();
+            // block-wide sum, one barrier, identical bits in every thread; slots alternate between trials
+            part = warp_sum(part);
+            const uint32_t rda = sb + F.red + 32u * slot;
+            if (lane == 0) sts_f64(rda + 8u * (uint32_t)warp, part);
+            __syncthreads();
+            double s0, s1, s2, s3;
+            lds_f64x2(rda, s0, s1);
+            lds_f64x2(rda + 16, s2, s3);
+            const double dE = ((s0 + s1) + s2) + s3;
+            slot ^= 1u;
+            const bool acc = A.exact_exp ? accept_exact(dE, Tk, thr) : (dE < thr);
+            if (acc) {
+                // every thread stores the (identical) committed position: its own later reads are ordered after
+                // its own store, so no forwarding registers and no second barrier are needed
+                sts_f64(xa, xn[0]);
+                sts_f64(xa + nb8, xn[1]);
+                if constexpr (DIM == 3) sts_f64(xa + 2 * nb8, xn[2]);
+                E += dE;
+                if (tid == (i & (kFastThreads - 1))) {  // owner refreshes its register copy
+                    const int ki = i >> 7;  // kFastThreads == 128
+#pragma unroll
+                    for (int k = 0; k < kFastCand; k++) {
+                        if (k == ki) {
+#pragma unroll
+                            for (int a = 0; a < DIM; a++) myu[k][a] = to_fixed32(xn[a], fscale);
+                        }
+                    }
+                }
+            }
+            if (tid == 0) {
+                if (acc) {  // image counters: which way did the coordinate wrap
+                    const double t0 = xo[0] + d0, t1 = xo[1] + d1, t2 = xo[2] + d2;
+                    const int w0 = (t0 >= L) - (t0 < 0.0), w1 = (t1 >= L) - (t1 < 0.0), w2 = (t2 >= L) - (t2 < 0.0);
+                    if (w0) atomicAdd(&gimg[i], w0);
+                    if (w1) atomicAdd(&gimg[gNpad + i], w1);
+                    if (DIM == 3 && w2) atomicAdd(&gimg[2 * gNpad + i], w2);
+                }
+                unsigned long long *scnt = (unsigned long long *)(smem_raw + F.cnt);
+                const int m = (int)lds_u32(ra + 48);
+                scnt[m] += 1ull;
+                scnt[PMC_MAX_MOVES + m] += acc ? 1ull : 0ull;
+                if (A.acc_out) A.acc_out[(size_t)c * A.n_trials + tb + b] = acc ? 1 : 0;
+                if (A.dE_out) A.dE_out[(size_t)c * A.n_trials + tb + b] = dE;
+            }
+        }
+    }
+    __syncthreads();
+    {
+        const double *sx = (const double *)(smem_raw + F.x);
+        for (int a = 0; a < DIM; a++)
+            for (int k = tid; k < gNpad; k += kFastThreads) gx[a * gNpad + k] = sx[a * Npad + k];
+        const unsigned long long *scnt = (const unsigned long long *)(smem_raw + F.cnt);
+        if (tid == 0) A.energy[c] = E;
+        if (tid < A.n_moves) {
+            A.calls[(size_t)c * PMC_MAX_MOVES + tid] += scnt[tid];
+            A.accepted[(size_t)c * PMC_MAX_MOVES + tid] += scnt[PMC_MAX_MOVES + tid];
+        }
+    }
+}
+
+}  // namespace fast
+}  // namespace pmc
