@@ -371,6 +371,9 @@ int pmc_create(const pmc_config *cfg, pmc_ctx **out) {
     if (a == cudaSuccess) a = dalloc(&c->accepted, M * PMC_MAX_MOVES);
     if (a == cudaSuccess) a = dalloc(&c->par, (size_t)PMC_MAX_SPECIES * PMC_MAX_SPECIES * PMC_NPAR);
     if (a == cudaSuccess) a = dalloc(&c->bad, 1);
+    // the zero-fills above ran on the legacy default stream, which the context's non-blocking stream does not
+    // wait for: drain them before any kernel of this context can touch the buffers
+    if (a == cudaSuccess) a = cudaDeviceSynchronize();
     if (a != cudaSuccess) {
         pmc_destroy(c);
         return fail(PMC_ERR_CUDA, "device allocation failed: %s", cudaGetErrorString(a));

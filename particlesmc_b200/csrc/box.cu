@@ -626,6 +626,7 @@ int setup_geometry(BoxState *b, const double *box3) {
     BCU(balloc(&b->start, b->g.ncell + 1));
     BCU(balloc(&b->cellE, b->g.ncell));
     BCU(balloc(&b->cell_acc, b->g.ncell));
+    BCU(cudaDeviceSynchronize());  // zero-fills ran on the legacy default stream
     b->geom_ready = true;
     return PMC_OK;
 }
@@ -685,6 +686,7 @@ int box_create(BoxState **out, const pmc_config &cfg) {
     if (e == cudaSuccess) e = balloc(&b->flags, 2);
     if (e == cudaSuccess) e = cudaMalloc((void **)&b->raw, sizeof(double) * d * N);
     if (e == cudaSuccess) e = cudaMalloc((void **)&b->rsp, sizeof(long long) * N);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();  // zero-fills ran on the legacy default stream
     if (e != cudaSuccess) {
         box_destroy(b);
         return bfail(PMC_ERR_CUDA, "device allocation failed: %s", cudaGetErrorString(e));
