@@ -139,7 +139,8 @@ def cpu_reference_arm(args, N, sweeps, pos, sp, box, cores=None):
 
 def time_cpu(O, systems, pool, n_trials, t0):
     t = time.perf_counter()
-    used = O.run_chains(systems, 42, t0, n_trials, pool, revert_mode=0, n_threads=0)
+    # explicit thread count: torchrun exports OMP_NUM_THREADS=1, the reference arm must use all host cores
+    used = O.run_chains(systems, 42, t0, n_trials, pool, revert_mode=0, n_threads=min(len(systems), os.cpu_count() or 1))
     dt = time.perf_counter() - t
     return len(systems) * n_trials / dt, dt, min(used, len(systems))
 
@@ -305,8 +306,16 @@ def run_ours(args):
         peak64 = measure_fma_peak(True, local)
         peak32 = measure_fma_peak(False, local)
         achieved = Mc * trials_per_step * work["P"] * work["F"] / (kms * 1e-3) / 1e12
+        # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from the committed ncu --set full captures
+        # (profiles/r01_v3_k_chain_sweep_fast_ncu_full_summary.csv: 4096 chains x N=1000; profiles/
+        # r01_k_box_sweep_fast_ncu_full_summary.csv: one colour of N=2^20); null for any other shape
+        traffic = None
+        if args.workload == "chains" and Mc == 4096 and N == 1000:
+            traffic = 105.618176e6 + 44.477952e6
+        elif args.workload == "box" and N == (1 << 20):
+            traffic = 27.703552e6 + 0.18432e6
         roofline = {"bound": "fp64_pipe", "achieved": achieved, "peak": peak64, "unit": "TFLOP/s",
-                    "frac": achieved / peak64, "traffic": None,
+                    "frac": achieved / peak64, "traffic": traffic,
                     "kernel": "k_chain_sweep" if args.workload == "chains" else "k_box_sweep (8 colours + cell rebuild)",
                     "kernel_ms_per_launch": kms, "launches_per_step": launches / args.steps,
                     "work_model": f"reference-equivalent: P={work['P']:.0f} candidate pairs/move x F={work['F']:.2f} flop/pair (SURVEY.md 8d)",

@@ -454,6 +454,299 @@ __global__ void __launch_bounds__(kBoxThreads) k_box_sweep(const __grid_constant
     }
 }
 
+// ---- K5 (fast): checkerboard sweep with the integer prefilter ---------------------------------------------
+// Same trials and the same fp64 pair terms as k_box_sweep, issued the way chains_fast.cuh does it: 64 threads
+// per active cell, every thread keeps the fixed-point frame coordinates of its KC candidates in registers, one
+// sphere test (midpoint of old/new, radius rc + |delta|/2) per candidate on the integer pipes, survivors
+// compacted with one warp prefix sum, fp64 only for survivors (no minimum image in the cell frame), explicit
+// 32-bit shared addressing.  Needs cubic cells (one fixed-point scale); otherwise k_box_sweep is used.
+constexpr int kBfThreads = 64;
+constexpr int kBfWarps = kBfThreads / 32;
+constexpr int kBfBatch = 32;
+constexpr int kBfRec = 80;
+
+struct BfLayout {
+    uint32_t r, sp, mv, q, cp, rec, red, par, rcs, total;
+};
+__host__ __device__ inline BfLayout bf_layout(int dim, int cap) {
+    BfLayout f;
+    uint32_t o = 0;
+    auto take = [&](uint32_t bytes) {
+        uint32_t p = o;
+        o += (bytes + 15u) & ~15u;
+        return p;
+    };
+    f.r = take(8u * dim * cap);
+    f.sp = take(cap);
+    f.mv = take(cap);
+    f.q = take(2u * cap);
+    f.cp = take(32u * PMC_MAX_SPECIES * PMC_MAX_SPECIES);
+    f.rec = take((uint32_t)kBfRec * kBfBatch);
+    f.red = take(8u * 2 * kBfWarps);
+    f.par = take(8u * PMC_MAX_SPECIES * PMC_MAX_SPECIES * PMC_NPAR);
+    f.rcs = take(8u * PMC_MAX_SPECIES);
+    f.total = o;
+    return f;
+}
+
+__device__ __forceinline__ double bf_lds_f64(uint32_t a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void bf_lds_f64x2(uint32_t a, double &v0, double &v1) {
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v0), "=d"(v1) : "r"(a) : "memory");
+}
+__device__ __forceinline__ void bf_lds_s32x4(uint32_t a, int &v0, int &v1, int &v2, int &v3) {
+    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(a) : "memory");
+}
+__device__ __forceinline__ uint32_t bf_lds_u32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t bf_lds_u16(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t bf_lds_u8(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void bf_sts_f64(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+__device__ __forceinline__ void bf_sts_u16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void bf_sts_u8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
+// frame coordinate r in [-cs, 2cs) -> fixed point in [0, 3 * 2^29): differences never wrap
+__device__ __forceinline__ uint32_t bf_fixed(double r, double cs, double scale) { return (uint32_t)__double2ull_rd((r + cs) * scale); }
+
+template <int DIM, int MODEL, int KC>
+__global__ void __launch_bounds__(kBfThreads, 12) k_box_sweep_fast(const __grid_constant__ BoxArgs A, int colour) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ Stencil<DIM> st;
+    constexpr int CAP = kBfThreads * KC;
+    const BfLayout F = bf_layout(DIM, CAP);
+    const uint32_t sb = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    constexpr uint32_t cap8 = 8u * CAP;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double *sr = (double *)(smem_raw + F.r);
+    uint8_t *ssp = smem_raw + F.sp;
+    {
+        double *spar = (double *)(smem_raw + F.par), *scp = (double *)(smem_raw + F.cp);
+        for (int k = tid; k < A.ns * A.ns * PMC_NPAR; k += kBfThreads) spar[k] = A.par[k];
+        for (int k = tid; k < A.ns * A.ns; k += kBfThreads) {
+            scp[4 * k + 0] = A.par[k * PMC_NPAR + PMC_P_RCUT2];
+            scp[4 * k + 1] = A.par[k * PMC_NPAR + PMC_P_EPS];
+            scp[4 * k + 2] = A.par[k * PMC_NPAR + PMC_P_SIG2];
+            scp[4 * k + 3] = A.par[k * PMC_NPAR + PMC_P_SHIFT];
+        }
+        if (tid < PMC_MAX_SPECIES) {
+            double rc2 = 0.0;
+            for (int b = 0; b < A.ns; b++) rc2 = fmax(rc2, A.par[((tid < A.ns ? tid : 0) * A.ns + b) * PMC_NPAR + PMC_P_RCUT2]);
+            ((double *)(smem_raw + F.rcs))[tid] = sqrt(rc2);
+        }
+    }
+    int cc[3] = {0, 0, 0};
+    {
+        int l = blockIdx.x;
+        if constexpr (DIM == 3) { cc[2] = 2 * (l % (A.g.nc[2] / 2)) + ((colour >> 2) & 1); l /= (A.g.nc[2] / 2); }
+        cc[1] = 2 * (l % (A.g.nc[1] / 2)) + ((colour >> 1) & 1);
+        cc[0] = 2 * (l / (A.g.nc[1] / 2)) + (colour & 1);
+    }
+    const int ncand = load_stencil<DIM>(A, cc, &st, sr, ssp);  // A.cap == CAP on this path
+    if (ncand < 0) return;
+    const int cell = st.cell[0], ncen = st.off[1], bstart = A.start[cell];
+    for (int k = tid; k < ncen; k += kBfThreads) smem_raw[F.mv + k] = 0;
+    const double cs = A.g.cs[0];
+    const double fscale = 536870912.0 / cs;  // 2^29 / cell side
+    uint32_t myu[KC][DIM];
+#pragma unroll
+    for (int k = 0; k < KC; k++) {
+        const int j = k * kBfThreads + tid;
+#pragma unroll
+        for (int a = 0; a < DIM; a++) myu[k][a] = j < ncand ? bf_fixed(sr[a * CAP + j], cs, fscale) : 0u;
+    }
+    const uint32_t k0 = (uint32_t)A.seed, k1 = (uint32_t)(A.seed >> 32);
+    const uint32_t qa = sb + F.q + (uint32_t)warp * (2u * KC * 32);
+    double Esum = 0.0;
+    uint32_t nacc = 0, slot = 0;
+
+    for (int tb = 0; tb < ncen; tb += kBfBatch) {
+        const int nb = min(kBfBatch, ncen - tb);
+        __syncthreads();
+        if (tid < nb) {
+            const uint32_t q = (uint32_t)(tb + tid);
+            const Philox4 a = philox4x32_10(q, (uint32_t)cell, A.sweep, 0u, k0, k1);
+            const Philox4 bb = philox4x32_10(q, (uint32_t)cell, A.sweep, 1u, k0, k1);
+            float z0, z1, z2, z3;
+            box_muller(bb.v[0], bb.v[1], z0, z1);
+            box_muller(bb.v[2], bb.v[3], z2, z3);
+            unsigned char *rec = smem_raw + F.rec + (size_t)kBfRec * tid;
+            double *rd = (double *)rec;
+            int *ri = (int *)(rec + 32);
+            uint32_t *rt = (uint32_t *)(rec + 64);
+            const double dx = (double)(A.sigma * z0), dy = (double)(A.sigma * z1), dz = DIM == 3 ? (double)(A.sigma * z2) : 0.0;
+            rd[0] = dx;
+            rd[1] = dy;
+            rd[2] = dz;
+            rd[3] = -A.T * log(uniform53(a.v[2], a.v[3]));
+            ri[0] = (int)__double2ll_rn(dx * fscale);
+            ri[1] = (int)__double2ll_rn(dy * fscale);
+            ri[2] = (int)__double2ll_rn(dz * fscale);
+            ri[3] = (int)bounded(a.v[1], (uint32_t)ncen);
+            const double hd = 0.5 * sqrt(dx * dx + dy * dy + dz * dz);
+            const double *rcs = (const double *)(smem_raw + F.rcs);
+#pragma unroll
+            for (int s = 0; s < PMC_MAX_SPECIES; s++) {
+                const double r = rcs[s] + hd;
+                const double t = r * r * fscale * fscale * 0x1p-32 * (1.0 + 1e-9) + 64.0;
+                rt[s] = t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
+            }
+        }
+        __syncthreads();
+        for (int t = 0; t < nb; t++) {
+            const uint32_t ra = sb + F.rec + (uint32_t)kBfRec * (uint32_t)t;
+            double d0, d1, d2, thr;
+            int di0, di1, di2, k;
+            bf_lds_f64x2(ra, d0, d1);
+            bf_lds_f64x2(ra + 16, d2, thr);
+            bf_lds_s32x4(ra + 32, di0, di1, di2, k);
+            const uint32_t xa = sb + F.r + 8u * (uint32_t)k;
+            double xo[3], xn[3];
+            xo[0] = bf_lds_f64(xa);
+            xo[1] = bf_lds_f64(xa + cap8);
+            xo[2] = DIM == 3 ? bf_lds_f64(xa + 2 * cap8) : 0.0;
+            xn[0] = xo[0] + d0;
+            xn[1] = xo[1] + d1;
+            xn[2] = xo[2] + d2;
+            bool inside = xn[0] >= 0.0 && xn[0] < cs && xn[1] >= 0.0 && xn[1] < cs;
+            if constexpr (DIM == 3) inside = inside && xn[2] >= 0.0 && xn[2] < cs;
+            if (!inside) continue;  // leaves the cell: rejected (uniform across the CTA)
+            const uint32_t si = bf_lds_u8(sb + F.sp + (uint32_t)k);
+            const uint32_t um0 = bf_fixed(xo[0], cs, fscale) + (uint32_t)(di0 >> 1);
+            const uint32_t um1 = bf_fixed(xo[1], cs, fscale) + (uint32_t)(di1 >> 1);
+            const uint32_t um2 = DIM == 3 ? bf_fixed(xo[2], cs, fscale) + (uint32_t)(di2 >> 1) : 0u;
+            const uint32_t fthr = bf_lds_u32(ra + 64 + 4u * si);
+            uint32_t m = 0;
+#pragma unroll
+            for (int kk = 0; kk < KC; kk++) {
+                int d = (int)(um0 - myu[kk][0]);
+                uint32_t r = (uint32_t)__mulhi(d, d);
+                d = (int)(um1 - myu[kk][1]);
+                r += (uint32_t)__mulhi(d, d);
+                if constexpr (DIM == 3) {
+                    d = (int)(um2 - myu[kk][DIM - 1]);
+                    r += (uint32_t)__mulhi(d, d);
+                }
+                m |= (r <= fthr) ? (1u << kk) : 0u;
+            }
+            const int mine = __popc(m);
+            int incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                incl += (lane >= o) ? v : 0;
+            }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            uint32_t wp = qa + 2u * (uint32_t)(incl - mine);
+#pragma unroll
+            for (int kk = 0; kk < KC; kk++) {
+                if (m & (1u << kk)) {
+                    bf_sts_u16(wp, (uint32_t)(kk * kBfThreads + tid));
+                    wp += 2;
+                }
+            }
+            __syncwarp();
+            double part = 0.0;
+            const uint32_t prow = si * (uint32_t)A.ns;
+            for (int q = lane; q < total; q += 32) {
+                const uint32_t j = bf_lds_u16(qa + 2u * (uint32_t)q);
+                if (j < (uint32_t)ncand && j != (uint32_t)k) {
+                    const uint32_t ja = sb + F.r + 8u * j;
+                    const double x0 = bf_lds_f64(ja), x1 = bf_lds_f64(ja + cap8);
+                    double a_ = xo[0] - x0, b_ = xn[0] - x0;
+                    double r2o = a_ * a_, r2n = b_ * b_;
+                    a_ = xo[1] - x1;
+                    b_ = xn[1] - x1;
+                    r2o = fma(a_, a_, r2o);
+                    r2n = fma(b_, b_, r2n);
+                    if constexpr (DIM == 3) {
+                        const double x2 = bf_lds_f64(ja + 2 * cap8);
+                        a_ = xo[2] - x2;
+                        b_ = xn[2] - x2;
+                        r2o = fma(a_, a_, r2o);
+                        r2n = fma(b_, b_, r2n);
+                    }
+                    const uint32_t sj = bf_lds_u8(sb + F.sp + j);
+                    if constexpr (MODEL == PMC_MODEL_LJ || MODEL == PMC_MODEL_KG) {
+                        double rc2, eps4, sig2, shift;
+                        const uint32_t pa = sb + F.cp + 32u * (prow + sj);
+                        bf_lds_f64x2(pa, rc2, eps4);
+                        bf_lds_f64x2(pa + 16, sig2, shift);
+                        const double uo = lj_core(r2o, eps4, sig2) - shift;
+                        const double un = lj_core(r2n, eps4, sig2) - shift;
+                        part += (r2n <= rc2 ? un : 0.0) - (r2o <= rc2 ? uo : 0.0);
+                    } else {
+                        const double *p = (const double *)(smem_raw + F.par) + (prow + sj) * PMC_NPAR;
+                        const double rc2 = p[PMC_P_RCUT2];
+                        if (r2o <= rc2) part -= pair_potential<MODEL>(p, r2o);
+                        if (r2n <= rc2) part += pair_potential<MODEL>(p, r2n);
+                    }
+                }
+            }
+            __syncwarp();
+            part = warp_sum(part);
+            const uint32_t rda = sb + F.red + 16u * slot;
+            if (lane == 0) bf_sts_f64(rda + 8u * (uint32_t)warp, part);
+            __syncthreads();
+            double s0, s1;
+            bf_lds_f64x2(rda, s0, s1);
+            const double dE = s0 + s1;
+            slot ^= 1u;
+            if (dE < thr) {
+                bf_sts_f64(xa, xn[0]);
+                bf_sts_f64(xa + cap8, xn[1]);
+                if constexpr (DIM == 3) bf_sts_f64(xa + 2 * cap8, xn[2]);
+                bf_sts_u8(sb + F.mv + (uint32_t)k, 1u);
+                Esum += dE;
+                nacc++;
+                if (tid == (k & (kBfThreads - 1))) {  // owner refreshes its register copy
+                    const int ki = k / kBfThreads;
+#pragma unroll
+                    for (int kk = 0; kk < KC; kk++) {
+                        if (kk == ki) {
+#pragma unroll
+                            for (int a = 0; a < DIM; a++) myu[kk][a] = bf_fixed(xn[a], cs, fscale);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // write moved particles back: canonical arrays (+ image counters) and the sorted copy
+    for (int k = tid; k < ncen; k += kBfThreads) {
+        if (!smem_raw[F.mv + k]) continue;
+        const int i = A.ids[bstart + k];
+#pragma unroll
+        for (int a = 0; a < DIM; a++) {
+            const double xold = A.xs[(size_t)a * A.N + bstart + k];
+            const double r0 = in_frame(xold, A.g.shift[a], A.g.L[a], A.g.cs[a], cc[a]);
+            int w;
+            const double xnew = wrap1(xold + (sr[a * CAP + k] - r0), A.g.L[a], w);
+            A.xs[(size_t)a * A.N + bstart + k] = xnew;
+            A.x[(size_t)a * A.N + i] = xnew;
+            if (w) A.img[(size_t)a * A.N + i] += w;
+        }
+    }
+    if (tid == 0) {
+        A.cellE[cell] = Esum;
+        A.cell_acc[cell] = nacc;
+    }
+}
+
 // deterministic reduction of per-cell values: out[0] (+)= scale * sum(cellE), acc[0] += sum(cell_acc)
 __global__ void k_box_reduce(const double *__restrict__ cellE, const uint32_t *__restrict__ cell_acc, int n, double scale,
                              int accumulate, double *outE, unsigned long long *out_acc) {
@@ -509,6 +802,8 @@ struct BoxState {
     int64_t calls = 0;
     int64_t launches = 0;
     size_t smem = 0;
+    int fast_kc = 0;        // > 0: k_box_sweep_fast<.., KC> is used for the sweeps
+    size_t fast_smem = 0;
 };
 
 namespace {
@@ -608,7 +903,32 @@ int setup_geometry(BoxState *b, const double *box3) {
     b->cap = cap;
     b->smem = sizeof(double) * (size_t)b->dim * cap + 2 * (size_t)cap + 16;
     if (b->smem > 200 * 1024) return bfail(PMC_ERR_UNSUPPORTED, "stencil of %d candidates does not fit shared memory", cap);
+    // fast sweep kernel: cubic cells, stencil fits 64 threads x KC register candidates
+    b->fast_kc = 0;
+    bool cubic = true;
+    for (int a = 1; a < b->dim; a++) cubic = cubic && b->g.cs[a] == b->g.cs[0];
+    if (cubic && b->cfg.prefilter >= 0) {
+        // register-candidate budget: 1.45 x the mean stencil occupancy covers a simple-cubic lattice start, where a
+        // 3-cell span holds 8 or 9 lattice planes (overflow is detected and reported, never silent)
+        const int need = (int)(occ * nst * 1.45);
+        if (need <= kBfThreads * 8) b->fast_kc = 8;
+        else if (need <= kBfThreads * 12) b->fast_kc = 12;
+        else if (need <= kBfThreads * 16) b->fast_kc = 16;
+    }
+    if (b->fast_kc) {
+        b->cap = kBfThreads * b->fast_kc;
+        b->fast_smem = bf_layout(b->dim, b->cap).total;
+        b->smem = sizeof(double) * (size_t)b->dim * b->cap + 2 * (size_t)b->cap + 16;
+    }
     int rc = bdispatch(b->dim, b->cfg.model_kind, [&](auto D, auto MDL) {
+        if (b->fast_kc) {
+            BCU(cudaFuncSetAttribute(k_box_sweep_fast<decltype(D)::value, decltype(MDL)::value, 8>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bf_layout(b->dim, kBfThreads * 8).total));
+            BCU(cudaFuncSetAttribute(k_box_sweep_fast<decltype(D)::value, decltype(MDL)::value, 12>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bf_layout(b->dim, kBfThreads * 12).total));
+            BCU(cudaFuncSetAttribute(k_box_sweep_fast<decltype(D)::value, decltype(MDL)::value, 16>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bf_layout(b->dim, kBfThreads * 16).total));
+        }
         BCU(cudaFuncSetAttribute(k_box_sweep<decltype(D)::value, decltype(MDL)::value>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem));
         BCU(cudaFuncSetAttribute(k_box_energy<decltype(D)::value, decltype(MDL)::value>,
@@ -804,8 +1124,17 @@ int box_run(BoxState *b, int64_t n_trials) {
         BoxArgs A;
         fill_args(b, A);
         rc = bdispatch(b->dim, b->cfg.model_kind, [&](auto D, auto MDL) {
-            for (int k = 0; k < ncol; k++)
-                k_box_sweep<decltype(D)::value, decltype(MDL)::value><<<nactive, kBoxThreads, b->smem, b->stream>>>(A, order[k]);
+            constexpr int d = decltype(D)::value, mdl = decltype(MDL)::value;
+            for (int k = 0; k < ncol; k++) {
+                if (b->fast_kc == 8)
+                    k_box_sweep_fast<d, mdl, 8><<<nactive, kBfThreads, b->fast_smem, b->stream>>>(A, order[k]);
+                else if (b->fast_kc == 12)
+                    k_box_sweep_fast<d, mdl, 12><<<nactive, kBfThreads, b->fast_smem, b->stream>>>(A, order[k]);
+                else if (b->fast_kc == 16)
+                    k_box_sweep_fast<d, mdl, 16><<<nactive, kBfThreads, b->fast_smem, b->stream>>>(A, order[k]);
+                else
+                    k_box_sweep<d, mdl><<<nactive, kBoxThreads, b->smem, b->stream>>>(A, order[k]);
+            }
             BCU(cudaGetLastError());
             return (int)PMC_OK;
         });
