@@ -226,6 +226,10 @@ def run_ours(args):
         ctx.download_raw(h_pos.data_ptr(), h_sp.data_ptr(), 0, Mc)
 
     upload()
+    strong = args.workload == "box" and world > 1
+    if strong:  # one box replicated on every GPU: colour phases split over ranks, moves pushed over NVLink peer memory
+        from particlesmc_b200.sharding import attach_box_peers
+        attach_box_peers(ctx)
     ctx.set_moves([dict(kind="displacement", prob=1.0, sigma=0.05)])
     ctx.seed(42)
     trials_per_step = sweeps * N
@@ -267,7 +271,7 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
-    moves_per_step = world * Mc * trials_per_step
+    moves_per_step = (1 if strong else world) * Mc * trials_per_step
     value = moves_per_step * args.steps / (ms_total * 1e-3)
 
     # ---- end to end through the C ABI with host buffers -------------------------------------------------
@@ -339,8 +343,8 @@ def run_ours(args):
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "seconds": dt}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": name, "sweeps_per_step": sweeps, "trials_per_step_per_gpu": Mc * trials_per_step,
+                "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": name, "sweeps_per_step": sweeps, "trials_per_step_per_gpu": Mc * trials_per_step // (world if strong else 1),
                            "equilibration_sweeps": args.equil, "cta_threads": args.threads or "default",
                            "l2": "256 MiB buffer zeroed between steps (L2 flush)", "seed": 42},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,

@@ -168,6 +168,18 @@ int64_t pmc_launch_count(const pmc_ctx *ctx);
 /* Device time of the most recent pmc_run, measured with CUDA events on the launch stream (ms). */
 int pmc_last_run_ms(pmc_ctx *ctx, float *ms);
 
+/* ---- multi-GPU, single large box (PMC_MODE_BOX) ---------------------------------------------------------- */
+/* Every rank (one process per GPU) holds a replica of the box, uploads the SAME state and uses the same seed.
+ * Each colour phase of a sweep is split evenly over the ranks; a rank pushes its accepted moves into all
+ * peers' replicas with peer stores over NVLink from inside the sweep kernel, and a device-side flag barrier
+ * separates the phases -- no host round trip and no collective library on the data path.  The result is
+ * bit-identical to the single-GPU run.  Call order: pmc_upload on every rank, exchange the 64-byte handles
+ * (any host channel, e.g. an all-gather), pmc_box_peer_attach, then pmc_init_energy / pmc_run as usual. */
+#define PMC_IPC_HANDLE_BYTES 64
+#define PMC_MAX_RANKS 8
+int pmc_box_peer_export(pmc_ctx *ctx, uint8_t *handle /*[PMC_IPC_HANDLE_BYTES]*/);
+int pmc_box_peer_attach(pmc_ctx *ctx, int32_t rank, int32_t world, const uint8_t *handles /*[world][64]*/);
+
 /* ---- device micro-benchmarks (roofline denominators) ----------------------------- */
 /* Burst FMA throughput of the CUDA-core pipes in TFLOP/s (fp64 = 1: DFMA, 0: FFMA). */
 int pmc_measure_fma_peak(int32_t device, int32_t fp64, double *tflops);

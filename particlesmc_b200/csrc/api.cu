@@ -577,6 +577,10 @@ int pmc_sync(pmc_ctx *c) {
     if (!c) return fail(PMC_ERR_INVALID, "null context");
     CU(cudaSetDevice(c->cfg.device));
     CU(cudaStreamSynchronize(c->stream));
+    if (c->boxst) {  // surfaces asynchronous device-side conditions (stencil overflow, inter-GPU barrier timeout)
+        int rc = pmc::box_check(c->boxst);
+        if (rc) return fail(rc, "%s", pmc::box_error());
+    }
     return PMC_OK;
 }
 
@@ -729,6 +733,24 @@ int pmc_counters(pmc_ctx *c, int64_t *calls, int64_t *accepted) {
             calls[(size_t)k * nm + m] = (int64_t)hc[(size_t)k * PMC_MAX_MOVES + m];
             accepted[(size_t)k * nm + m] = (int64_t)ha[(size_t)k * PMC_MAX_MOVES + m];
         }
+    return PMC_OK;
+}
+
+int pmc_box_peer_export(pmc_ctx *c, uint8_t *handle) {
+    if (!c || !handle) return fail(PMC_ERR_INVALID, "null argument");
+    if (c->cfg.mode != PMC_MODE_BOX) return fail(PMC_ERR_INVALID, "peer replicas exist only in PMC_MODE_BOX");
+    CU(cudaSetDevice(c->cfg.device));
+    int rc = pmc::box_peer_export(c->boxst, handle);
+    if (rc) return fail(rc, "%s", pmc::box_error());
+    return PMC_OK;
+}
+
+int pmc_box_peer_attach(pmc_ctx *c, int32_t rank, int32_t world, const uint8_t *handles) {
+    if (!c || !handles) return fail(PMC_ERR_INVALID, "null argument");
+    if (c->cfg.mode != PMC_MODE_BOX) return fail(PMC_ERR_INVALID, "peer replicas exist only in PMC_MODE_BOX");
+    CU(cudaSetDevice(c->cfg.device));
+    int rc = pmc::box_peer_attach(c->boxst, rank, world, handles);
+    if (rc) return fail(rc, "%s", pmc::box_error());
     return PMC_OK;
 }
 

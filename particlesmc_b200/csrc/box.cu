@@ -18,6 +18,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstring>
 #include <string>
 #include <type_traits>
 #include <vector>
@@ -46,6 +47,8 @@ int bfail(int code, const char *fmt, ...) {
         cudaError_t e_ = (call);                                                                   \
         if (e_ != cudaSuccess) return bfail(PMC_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
+
+constexpr int PMC_MAX_PEERS = 7;  // other GPUs of one 8-GPU box
 
 struct Geom {
     int nc[3];
@@ -77,6 +80,15 @@ struct BoxArgs {
     uint32_t *cell_acc;       // [ncell]
     double *eloc;             // [N] (energy kernel)
     int *overflow;
+    // multi-GPU (replicated state): this rank sweeps active cells [cta_offset, cta_offset + gridDim.x) of the colour
+    // and pushes every accepted move into the peers' replicas with plain stores over NVLink peer memory
+    int cta_offset;
+    int n_peers;
+    double *peer_x[PMC_MAX_PEERS];
+    double *peer_xs[PMC_MAX_PEERS];
+    int32_t *peer_img[PMC_MAX_PEERS];
+    double *peer_cellE[PMC_MAX_PEERS];
+    uint32_t *peer_cacc[PMC_MAX_PEERS];
 };
 
 // Cell coordinate and in-cell coordinate of a wrapped position under grid origin s.
@@ -356,7 +368,7 @@ __global__ void __launch_bounds__(kBoxThreads) k_box_sweep(const __grid_constant
     // active cell of this CTA: coordinates 2*h + colour bit
     int cc[3] = {0, 0, 0};
     {
-        int l = blockIdx.x;
+        int l = blockIdx.x + A.cta_offset;
         if constexpr (DIM == 3) { cc[2] = 2 * (l % (A.g.nc[2] / 2)) + ((colour >> 2) & 1); l /= (A.g.nc[2] / 2); }
         cc[1] = 2 * (l % (A.g.nc[1] / 2)) + ((colour >> 1) & 1);
         cc[0] = 2 * (l / (A.g.nc[1] / 2)) + (colour & 1);
@@ -443,15 +455,26 @@ __global__ void __launch_bounds__(kBoxThreads) k_box_sweep(const __grid_constant
             const double r0 = in_frame(xold, A.g.shift[a], A.g.L[a], A.g.cs[a], cc[a]);
             int w;
             const double xnew = wrap1(xold + (sr[a * A.cap + k] - r0), A.g.L[a], w);
+            const int im = A.img[(size_t)a * A.N + i] + w;
             A.xs[(size_t)a * A.N + b + k] = xnew;
             A.x[(size_t)a * A.N + i] = xnew;
-            if (w) A.img[(size_t)a * A.N + i] += w;
+            if (w) A.img[(size_t)a * A.N + i] = im;
+            for (int p = 0; p < A.n_peers; p++) {
+                A.peer_xs[p][(size_t)a * A.N + b + k] = xnew;
+                A.peer_x[p][(size_t)a * A.N + i] = xnew;
+                if (w) A.peer_img[p][(size_t)a * A.N + i] = im;
+            }
         }
     }
     if (tid == 0) {
         A.cellE[cell] = Esum;
         A.cell_acc[cell] = nacc;
+        for (int p = 0; p < A.n_peers; p++) {
+            A.peer_cellE[p][cell] = Esum;
+            A.peer_cacc[p][cell] = nacc;
+        }
     }
+    if (A.n_peers) __threadfence_system();
 }
 
 // ---- K5 (fast): checkerboard sweep with the integer prefilter ---------------------------------------------
@@ -550,7 +573,7 @@ __global__ void __launch_bounds__(kBfThreads, 12) k_box_sweep_fast(const __grid_
     }
     int cc[3] = {0, 0, 0};
     {
-        int l = blockIdx.x;
+        int l = blockIdx.x + A.cta_offset;
         if constexpr (DIM == 3) { cc[2] = 2 * (l % (A.g.nc[2] / 2)) + ((colour >> 2) & 1); l /= (A.g.nc[2] / 2); }
         cc[1] = 2 * (l % (A.g.nc[1] / 2)) + ((colour >> 1) & 1);
         cc[0] = 2 * (l / (A.g.nc[1] / 2)) + (colour & 1);
@@ -736,14 +759,47 @@ __global__ void __launch_bounds__(kBfThreads, 12) k_box_sweep_fast(const __grid_
             const double r0 = in_frame(xold, A.g.shift[a], A.g.L[a], A.g.cs[a], cc[a]);
             int w;
             const double xnew = wrap1(xold + (sr[a * CAP + k] - r0), A.g.L[a], w);
+            const int im = A.img[(size_t)a * A.N + i] + w;
             A.xs[(size_t)a * A.N + bstart + k] = xnew;
             A.x[(size_t)a * A.N + i] = xnew;
-            if (w) A.img[(size_t)a * A.N + i] += w;
+            if (w) A.img[(size_t)a * A.N + i] = im;
+            for (int p = 0; p < A.n_peers; p++) {
+                A.peer_xs[p][(size_t)a * A.N + bstart + k] = xnew;
+                A.peer_x[p][(size_t)a * A.N + i] = xnew;
+                if (w) A.peer_img[p][(size_t)a * A.N + i] = im;
+            }
         }
     }
     if (tid == 0) {
         A.cellE[cell] = Esum;
         A.cell_acc[cell] = nacc;
+        for (int p = 0; p < A.n_peers; p++) {
+            A.peer_cellE[p][cell] = Esum;
+            A.peer_cacc[p][cell] = nacc;
+        }
+    }
+    if (A.n_peers) __threadfence_system();
+}
+
+// Inter-GPU barrier between colour phases: every rank stores `epoch` into its slot of every peer's flag array
+// (NVLink peer store, after a system fence so the sweep kernel's pushes are visible first), then spins on its own
+// flag array until all ranks have arrived.  Bounded spin: a peer that never arrives raises an error flag
+// instead of hanging the GPU.
+__global__ void k_peer_barrier(volatile uint32_t *local_flags, uint32_t *const *peer_flags, int rank, int world, uint32_t epoch,
+                               int *error) {
+    const int t = threadIdx.x;
+    if (t < world) {
+        __threadfence_system();
+        volatile uint32_t *dst = peer_flags[t] + rank;
+        *dst = epoch;
+        __threadfence_system();
+        unsigned long long spins = 0;
+        while ((int32_t)(local_flags[t] - epoch) < 0) {
+            if (++spins > 50000000ull) {
+                atomicExch(error, 3);
+                break;
+            }
+        }
     }
 }
 
@@ -803,7 +859,16 @@ struct BoxState {
     int64_t launches = 0;
     size_t smem = 0;
     int fast_kc = 0;        // > 0: k_box_sweep_fast<.., KC> is used for the sweeps
+    // multi-GPU replicas (box_peer_attach)
+    int rank = 0, world = 1;
+    uint32_t *bar_flags = nullptr;      // [8] local barrier flags
+    uint32_t **d_peer_flags = nullptr;  // device array [world] of flag arrays (self included)
+    uint32_t epoch = 0;
+    unsigned char *shared_block = nullptr;  // ONE allocation [x | xs | img | cellE | cell_acc | flags]: one IPC handle
+    size_t shared_bytes = 0;
+    unsigned char *peer_block[PMC_MAX_PEERS + 1] = {};  // opened IPC mapping of every rank's block (self = local)
     size_t fast_smem = 0;
+    int ncell_alloc = 0;
 };
 
 namespace {
@@ -831,6 +896,28 @@ int bdispatch(int dim, int model, F &&f) {
     return bfail(PMC_ERR_INVALID, "unsupported dim/model combination");
 }
 
+// Everything a peer GPU writes into lives in ONE allocation: one IPC handle, fixed offsets on every rank.
+struct BlockLayout {
+    size_t x, xs, img, cellE, cacc, flags, total;
+};
+BlockLayout block_layout(int N, int dim, int ncell) {
+    BlockLayout l;
+    size_t o = 0;
+    auto take = [&](size_t bytes) {
+        size_t p = o;
+        o += (bytes + 255) & ~(size_t)255;
+        return p;
+    };
+    l.x = take(sizeof(double) * dim * (size_t)N);
+    l.xs = take(sizeof(double) * dim * (size_t)N);
+    l.img = take(sizeof(int32_t) * dim * (size_t)N);
+    l.cellE = take(sizeof(double) * (size_t)ncell);
+    l.cacc = take(sizeof(uint32_t) * (size_t)ncell);
+    l.flags = take(256);
+    l.total = o;
+    return l;
+}
+
 void fill_args(BoxState *b, BoxArgs &a) {
     a.g = b->g;
     a.N = b->N;
@@ -852,6 +939,21 @@ void fill_args(BoxState *b, BoxArgs &a) {
     a.cell_acc = b->cell_acc;
     a.eloc = b->eloc;
     a.overflow = b->flags + 1;
+    a.cta_offset = 0;
+    a.n_peers = 0;
+    if (b->world > 1) {
+        const BlockLayout bl = block_layout(b->N, b->dim, b->g.ncell);
+        for (int r = 0; r < b->world; r++) {
+            if (r == b->rank) continue;
+            const int p = a.n_peers++;
+            unsigned char *blk = b->peer_block[r];
+            a.peer_x[p] = (double *)(blk + bl.x);
+            a.peer_xs[p] = (double *)(blk + bl.xs);
+            a.peer_img[p] = (int32_t *)(blk + bl.img);
+            a.peer_cellE[p] = (double *)(blk + bl.cellE);
+            a.peer_cacc[p] = (uint32_t *)(blk + bl.cacc);
+        }
+    }
 }
 
 // K1: (re)build the cell-sorted arrays for grid origin g.shift
@@ -936,17 +1038,28 @@ int setup_geometry(BoxState *b, const double *box3) {
         return (int)PMC_OK;
     });
     if (rc) return rc;
-    for (void *p : {(void *)b->count, (void *)b->cursor, (void *)b->start, (void *)b->cellE, (void *)b->cell_acc})
-        if (p) cudaFree(p);
-    b->count = b->cursor = b->start = nullptr;
-    b->cellE = nullptr;
-    b->cell_acc = nullptr;
-    BCU(balloc(&b->count, b->g.ncell));
-    BCU(balloc(&b->cursor, b->g.ncell));
-    BCU(balloc(&b->start, b->g.ncell + 1));
-    BCU(balloc(&b->cellE, b->g.ncell));
-    BCU(balloc(&b->cell_acc, b->g.ncell));
-    BCU(cudaDeviceSynchronize());  // zero-fills ran on the legacy default stream
+    if (b->ncell_alloc != b->g.ncell) {  // buffers survive re-uploads of the same geometry (peers map them)
+        if (b->world > 1) return bfail(PMC_ERR_STATE, "the cell grid changed after peers were attached");
+        for (void *p : {(void *)b->count, (void *)b->cursor, (void *)b->start, (void *)b->shared_block})
+            if (p) cudaFree(p);
+        b->count = b->cursor = b->start = nullptr;
+        b->shared_block = nullptr;
+        BCU(balloc(&b->count, b->g.ncell));
+        BCU(balloc(&b->cursor, b->g.ncell));
+        BCU(balloc(&b->start, b->g.ncell + 1));
+        // everything a peer GPU writes into lives in ONE allocation, so one IPC handle and fixed offsets suffice
+        const BlockLayout bl = block_layout(b->N, b->dim, b->g.ncell);
+        BCU(balloc(&b->shared_block, bl.total));
+        b->shared_bytes = bl.total;
+        b->x = (double *)(b->shared_block + bl.x);
+        b->xs = (double *)(b->shared_block + bl.xs);
+        b->img = (int32_t *)(b->shared_block + bl.img);
+        b->cellE = (double *)(b->shared_block + bl.cellE);
+        b->cell_acc = (uint32_t *)(b->shared_block + bl.cacc);
+        b->bar_flags = (uint32_t *)(b->shared_block + bl.flags);
+        BCU(cudaDeviceSynchronize());  // zero-fills ran on the legacy default stream
+        b->ncell_alloc = b->g.ncell;
+    }
     b->geom_ready = true;
     return PMC_OK;
 }
@@ -956,6 +1069,7 @@ int check_overflow(BoxState *b) {
     BCU(cudaMemcpyAsync(fl, b->flags, sizeof fl, cudaMemcpyDeviceToHost, b->stream));
     BCU(cudaStreamSynchronize(b->stream));
     if (fl[1]) return bfail(PMC_ERR_UNSUPPORTED, "a 3^d-cell neighbourhood holds more than %d particles (density too inhomogeneous)", b->cap);
+    if (fl[0] == 3) return bfail(PMC_ERR_CUDA, "inter-GPU barrier timed out: a peer rank did not arrive");
     return PMC_OK;
 }
 
@@ -978,9 +1092,56 @@ int compute_energy(BoxState *b) {
     return check_overflow(b);
 }
 
+// one inter-GPU barrier on the context's stream
+int peer_barrier(BoxState *b) {
+    b->epoch++;
+    k_peer_barrier<<<1, 32, 0, b->stream>>>(b->bar_flags, b->d_peer_flags, b->rank, b->world, b->epoch, b->flags);
+    BCU(cudaGetLastError());
+    return PMC_OK;
+}
+
 }  // namespace
 
 const char *box_error() { return g_box_err.c_str(); }
+
+int box_check(BoxState *b) { return check_overflow(b); }
+
+int box_peer_export(BoxState *b, unsigned char *handle64) {
+    if (!b->geom_ready) return bfail(PMC_ERR_STATE, "pmc_upload must precede pmc_box_peer_export");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    BCU(cudaIpcGetMemHandle(&h, b->shared_block));
+    memcpy(handle64, &h, 64);
+    return PMC_OK;
+}
+
+int box_peer_attach(BoxState *b, int rank, int world, const unsigned char *handles) {
+    if (!b->geom_ready) return bfail(PMC_ERR_STATE, "pmc_upload must precede pmc_box_peer_attach");
+    if (world < 1 || world > PMC_MAX_PEERS + 1 || rank < 0 || rank >= world)
+        return bfail(PMC_ERR_INVALID, "rank %d / world %d out of range (max %d ranks)", rank, world, PMC_MAX_PEERS + 1);
+    if (b->world > 1) return bfail(PMC_ERR_STATE, "peers are already attached");
+    const BlockLayout bl = block_layout(b->N, b->dim, b->g.ncell);
+    std::vector<uint32_t *> flags(world);
+    for (int r = 0; r < world; r++) {
+        if (r == rank) {
+            b->peer_block[r] = b->shared_block;
+        } else {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, handles + (size_t)64 * r, 64);
+            void *ptr = nullptr;
+            BCU(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+            b->peer_block[r] = (unsigned char *)ptr;
+        }
+        flags[r] = (uint32_t *)(b->peer_block[r] + bl.flags);
+    }
+    if (b->d_peer_flags) cudaFree(b->d_peer_flags);
+    BCU(cudaMalloc((void **)&b->d_peer_flags, sizeof(uint32_t *) * world));
+    BCU(cudaMemcpy(b->d_peer_flags, flags.data(), sizeof(uint32_t *) * world, cudaMemcpyHostToDevice));
+    b->rank = rank;
+    b->world = world;
+    b->epoch = 0;
+    return PMC_OK;
+}
 
 int box_create(BoxState **out, const pmc_config &cfg) {
     if (cfg.n_chains != 1) return bfail(PMC_ERR_INVALID, "PMC_MODE_BOX holds exactly one system (n_chains = %d)", cfg.n_chains);
@@ -991,10 +1152,7 @@ int box_create(BoxState **out, const pmc_config &cfg) {
     b->dim = cfg.dim;
     b->ns = cfg.n_species;
     const size_t N = b->N, d = b->dim;
-    cudaError_t e = balloc(&b->x, d * N);
-    if (e == cudaSuccess) e = balloc(&b->xs, d * N);
-    if (e == cudaSuccess) e = balloc(&b->img, d * N);
-    if (e == cudaSuccess) e = balloc(&b->ids, N);
+    cudaError_t e = balloc(&b->ids, N);
     if (e == cudaSuccess) e = balloc(&b->cid, N);
     if (e == cudaSuccess) e = balloc(&b->sp, N);
     if (e == cudaSuccess) e = balloc(&b->sps, N);
@@ -1017,8 +1175,10 @@ int box_create(BoxState **out, const pmc_config &cfg) {
 
 void box_destroy(BoxState *b) {
     if (!b) return;
-    void *bufs[] = {b->x, b->xs, b->img, b->ids, b->cid, b->sp, b->sps, b->eloc, b->par, b->energy, b->etmp, b->acc_total,
-                    b->flags, b->raw, b->rsp, b->count, b->cursor, b->start, b->cellE, b->cell_acc};
+    for (int r = 0; r < b->world; r++)
+        if (r != b->rank && b->peer_block[r]) cudaIpcCloseMemHandle(b->peer_block[r]);
+    void *bufs[] = {b->shared_block, b->ids, b->cid, b->sp, b->sps, b->eloc, b->par, b->energy, b->etmp, b->acc_total,
+                    b->flags, b->raw, b->rsp, b->count, b->cursor, b->start, b->d_peer_flags};
     for (void *p : bufs)
         if (p) cudaFree(p);
     delete b;
@@ -1123,25 +1283,39 @@ int box_run(BoxState *b, int64_t n_trials) {
         if (rc) return rc;
         BoxArgs A;
         fill_args(b, A);
+        // multi-GPU: this rank sweeps an even share of the colour's active cells (same-colour cells never interact,
+        // so any split is valid); peers must have finished their rebuild before anyone pushes into their arrays
+        const int lo = (int)((int64_t)nactive * b->rank / b->world), hi = (int)((int64_t)nactive * (b->rank + 1) / b->world);
+        A.cta_offset = lo;
+        if (b->world > 1) {
+            rc = peer_barrier(b);
+            if (rc) return rc;
+        }
         rc = bdispatch(b->dim, b->cfg.model_kind, [&](auto D, auto MDL) {
             constexpr int d = decltype(D)::value, mdl = decltype(MDL)::value;
             for (int k = 0; k < ncol; k++) {
-                if (b->fast_kc == 8)
-                    k_box_sweep_fast<d, mdl, 8><<<nactive, kBfThreads, b->fast_smem, b->stream>>>(A, order[k]);
-                else if (b->fast_kc == 12)
-                    k_box_sweep_fast<d, mdl, 12><<<nactive, kBfThreads, b->fast_smem, b->stream>>>(A, order[k]);
-                else if (b->fast_kc == 16)
-                    k_box_sweep_fast<d, mdl, 16><<<nactive, kBfThreads, b->fast_smem, b->stream>>>(A, order[k]);
-                else
-                    k_box_sweep<d, mdl><<<nactive, kBoxThreads, b->smem, b->stream>>>(A, order[k]);
+                if (hi > lo) {
+                    if (b->fast_kc == 8)
+                        k_box_sweep_fast<d, mdl, 8><<<hi - lo, kBfThreads, b->fast_smem, b->stream>>>(A, order[k]);
+                    else if (b->fast_kc == 12)
+                        k_box_sweep_fast<d, mdl, 12><<<hi - lo, kBfThreads, b->fast_smem, b->stream>>>(A, order[k]);
+                    else if (b->fast_kc == 16)
+                        k_box_sweep_fast<d, mdl, 16><<<hi - lo, kBfThreads, b->fast_smem, b->stream>>>(A, order[k]);
+                    else
+                        k_box_sweep<d, mdl><<<hi - lo, kBoxThreads, b->smem, b->stream>>>(A, order[k]);
+                }
+                BCU(cudaGetLastError());
+                if (b->world > 1) {
+                    const int brc = peer_barrier(b);
+                    if (brc) return brc;
+                }
             }
-            BCU(cudaGetLastError());
             return (int)PMC_OK;
         });
         if (rc) return rc;
         k_box_reduce<<<1, 1024, 0, b->stream>>>(b->cellE, b->cell_acc, b->g.ncell, 1.0, 1, b->energy, b->acc_total);
         BCU(cudaGetLastError());
-        b->launches += ncol + 1;
+        b->launches += ncol + 1 + (b->world > 1 ? ncol + 1 : 0);
         b->sweep++;
         b->calls += b->N;
     }

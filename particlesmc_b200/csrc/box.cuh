@@ -27,5 +27,8 @@ int box_run(BoxState *b, int64_t n_trials);
 int box_download(BoxState *b, double *pos_aos, int64_t *species);
 int box_counters(BoxState *b, int64_t *calls, int64_t *accepted);
 int64_t box_take_launches(BoxState *b);
+int box_peer_export(BoxState *b, unsigned char *handle64);
+int box_peer_attach(BoxState *b, int rank, int world, const unsigned char *handles);
+int box_check(BoxState *b);
 
 }  // namespace pmc

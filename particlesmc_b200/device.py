@@ -182,6 +182,16 @@ class DeviceContext:
         L.check(self.lib.pmc_counters(self._h, _lp(calls), _lp(acc)))
         return calls, acc
 
+    # -- multi-GPU replicas of one large box ---------------------------------------------------------------
+    def box_peer_handle(self) -> np.ndarray:
+        h = np.zeros(64, dtype=np.uint8)
+        L.check(self.lib.pmc_box_peer_export(self._h, h.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return h
+
+    def box_peer_attach(self, rank: int, world: int, handles: np.ndarray):
+        hs = np.ascontiguousarray(handles, dtype=np.uint8).reshape(world, 64)
+        L.check(self.lib.pmc_box_peer_attach(self._h, rank, world, hs.ctypes.data_as(C.POINTER(C.c_uint8))))
+
     def launch_count(self) -> int:
         return int(self.lib.pmc_launch_count(self._h))
 

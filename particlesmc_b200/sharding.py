@@ -39,3 +39,26 @@ def gather_chain_values(local: np.ndarray, n_chains: int):
     out = [torch.zeros_like(buf) for _ in range(world)]
     dist.all_gather(out, buf)
     return np.concatenate([o[:c].cpu().numpy() for o, c in zip(out, counts)], axis=0)
+
+
+def attach_box_peers(ctx) -> None:
+    """Multi-GPU single box: all-gather the 64-byte CUDA IPC handles of every rank's replica (host channel:
+    torch.distributed, any backend) and attach them.  Call on every rank after ``ctx.upload``; collective."""
+    import torch
+    import torch.distributed as dist
+
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
+        return
+    world, rank = dist.get_world_size(), dist.get_rank()
+    mine = torch.from_numpy(ctx.box_peer_handle().copy())
+    if dist.get_backend() == "nccl":
+        dev = torch.device("cuda", torch.cuda.current_device())
+        out = [torch.zeros(64, dtype=torch.uint8, device=dev) for _ in range(world)]
+        dist.all_gather(out, mine.to(dev))
+        handles = torch.stack(out).cpu().numpy()
+    else:
+        out = [torch.zeros(64, dtype=torch.uint8) for _ in range(world)]
+        dist.all_gather(out, mine)
+        handles = torch.stack(out).numpy()
+    ctx.box_peer_attach(rank, world, handles)
+    dist.barrier()
