@@ -154,45 +154,62 @@ __global__ void k_box_count(const double *__restrict__ x, int N, Geom g, int32_t
     atomicAdd(&count[l], 1);
 }
 
-// exclusive prefix sum of count[0..n) into start[0..n], single CTA, chunked with a running carry
-__global__ void k_box_scan(const int32_t *__restrict__ count, int32_t *start, int32_t *cursor, int n) {
+// exclusive prefix sum of count[0..n) into start[0..n] in two small launches:
+//   k_box_scan_local : every CTA scans its 1024 coalesced entries, writes the CTA-local exclusive prefix and its total
+//   k_box_scan_apply : every CTA adds the sum of the totals of the CTAs before it (<= a few dozen values)
+__global__ void k_box_scan_local(const int32_t *__restrict__ count, int32_t *start, int32_t *blocksum, int n) {
     __shared__ int s_warp[32];
-    __shared__ int s_carry;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
-    if (tid == 0) s_carry = 0;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int k = blockIdx.x * blockDim.x + tid;
+    const int v = k < n ? count[k] : 0;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
     __syncthreads();
-    for (int base = 0; base < n; base += blockDim.x) {
-        const int k = base + tid;
-        const int v = k < n ? count[k] : 0;
-        int incl = v;
+    if (warp == 0) {
+        int w = s_warp[lane];
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
+            const int t = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += t;
         }
-        if (lane == 31) s_warp[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            int w = lane < nwarp ? s_warp[lane] : 0;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, w, o);
-                if (lane >= o) w += t;
-            }
-            s_warp[lane] = w;  // inclusive over warps
-        }
-        __syncthreads();
-        const int carry = s_carry;
-        const int excl = carry + (warp ? s_warp[warp - 1] : 0) + incl - v;
-        if (k < n) {
-            start[k] = excl;
-            cursor[k] = 0;
-        }
-        __syncthreads();
-        if (tid == blockDim.x - 1) s_carry = carry + s_warp[nwarp - 1];
-        __syncthreads();
+        s_warp[lane] = w;
     }
-    if (tid == 0) start[n] = s_carry;
+    __syncthreads();
+    if (k < n) start[k] = (warp ? s_warp[warp - 1] : 0) + incl - v;
+    if (tid == 0) blocksum[blockIdx.x] = s_warp[31];
+}
+
+__global__ void k_box_scan_apply(int32_t *start, int32_t *cursor, const int32_t *__restrict__ blocksum, int n) {
+    __shared__ int s_off, s_tot;
+    if (threadIdx.x < 32) {
+        int off = 0, tot = 0;
+        for (int b = threadIdx.x; b < (int)gridDim.x; b += 32) {
+            const int v = blocksum[b];
+            tot += v;
+            if (b < (int)blockIdx.x) off += v;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            off += __shfl_xor_sync(0xffffffffu, off, o);
+            tot += __shfl_xor_sync(0xffffffffu, tot, o);
+        }
+        if (threadIdx.x == 0) {
+            s_off = off;
+            s_tot = tot;
+        }
+    }
+    __syncthreads();
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) {
+        start[k] += s_off;
+        cursor[k] = 0;
+    }
+    if (k == 0) start[n] = s_tot;
 }
 
 __global__ void k_box_scatter(const int32_t *__restrict__ cid, const int32_t *__restrict__ start, int32_t *cursor, int N,
@@ -203,27 +220,50 @@ __global__ void k_box_scatter(const int32_t *__restrict__ cid, const int32_t *__
     ids[start[c] + atomicAdd(&cursor[c], 1)] = i;
 }
 
-// canonical order inside each cell (descending particle id) + gather into the sorted SoA
+// canonical order inside each cell (descending particle id) + gather into the sorted SoA: one warp per cell,
+// rank sort through shuffles (cells hold ~20 particles); cells with more than 32 particles fall back to a serial
+// insertion sort by lane 0
 template <int DIM>
 __global__ void k_box_finalize(const int32_t *__restrict__ start, int32_t *ids, int ncell, int N,
                                const double *__restrict__ x, const uint8_t *__restrict__ sp, double *xs, uint8_t *sps) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c >= ncell) return;
-    const int b = start[c], e = start[c + 1];
-    for (int p = b + 1; p < e; p++) {  // insertion sort, descending
-        const int v = ids[p];
-        int q = p - 1;
-        while (q >= b && ids[q] < v) {
-            ids[q + 1] = ids[q];
-            q--;
+    const int b = start[c], e = start[c + 1], cnt = e - b;
+    if (cnt <= 32) {
+        const int mine = lane < cnt ? ids[b + lane] : -1;
+        int rank = 0;
+        for (int k = 0; k < cnt; k++) {
+            const int v = __shfl_sync(0xffffffffu, mine, k);
+            rank += (v > mine) ? 1 : 0;
         }
-        ids[q + 1] = v;
-    }
-    for (int p = b; p < e; p++) {
-        const int i = ids[p];
+        __syncwarp();
+        if (lane < cnt) {
+            const int p = b + rank;
+            ids[p] = mine;
 #pragma unroll
-        for (int a = 0; a < DIM; a++) xs[(size_t)a * N + p] = x[(size_t)a * N + i];
-        sps[p] = sp[i];
+            for (int a = 0; a < DIM; a++) xs[(size_t)a * N + p] = x[(size_t)a * N + mine];
+            sps[p] = sp[mine];
+        }
+    } else {
+        if (lane == 0) {
+            for (int p = b + 1; p < e; p++) {  // insertion sort, descending
+                const int v = ids[p];
+                int q = p - 1;
+                while (q >= b && ids[q] < v) {
+                    ids[q + 1] = ids[q];
+                    q--;
+                }
+                ids[q + 1] = v;
+            }
+        }
+        __syncwarp();
+        for (int p = b + lane; p < e; p += 32) {
+            const int i = ids[p];
+#pragma unroll
+            for (int a = 0; a < DIM; a++) xs[(size_t)a * N + p] = x[(size_t)a * N + i];
+            sps[p] = sp[i];
+        }
     }
 }
 
@@ -869,6 +909,7 @@ struct BoxState {
     unsigned char *peer_block[PMC_MAX_PEERS + 1] = {};  // opened IPC mapping of every rank's block (self = local)
     size_t fast_smem = 0;
     int ncell_alloc = 0;
+    int32_t *cid_blocksum = nullptr;  // [ceil(ncell/1024)] partial sums of the cell-count scan
 };
 
 namespace {
@@ -964,15 +1005,19 @@ int build_cells(BoxState *b) {
         k_box_count<3><<<nb, 256, 0, b->stream>>>(b->x, N, b->g, b->cid, b->count);
     else
         k_box_count<2><<<nb, 256, 0, b->stream>>>(b->x, N, b->g, b->cid, b->count);
-    k_box_scan<<<1, 1024, 0, b->stream>>>(b->count, b->start, b->cursor, b->g.ncell);
+    {
+        const int nsb = (b->g.ncell + 1023) / 1024;
+        k_box_scan_local<<<nsb, 1024, 0, b->stream>>>(b->count, b->start, b->cid_blocksum, b->g.ncell);
+        k_box_scan_apply<<<nsb, 1024, 0, b->stream>>>(b->start, b->cursor, b->cid_blocksum, b->g.ncell);
+    }
     k_box_scatter<<<nb, 256, 0, b->stream>>>(b->cid, b->start, b->cursor, N, b->ids);
-    const int nbc = (b->g.ncell + 127) / 128;
+    const int nbc = (b->g.ncell + 7) / 8;  // one warp per cell, 8 warps per CTA
     if (b->dim == 3)
-        k_box_finalize<3><<<nbc, 128, 0, b->stream>>>(b->start, b->ids, b->g.ncell, N, b->x, b->sp, b->xs, b->sps);
+        k_box_finalize<3><<<nbc, 256, 0, b->stream>>>(b->start, b->ids, b->g.ncell, N, b->x, b->sp, b->xs, b->sps);
     else
-        k_box_finalize<2><<<nbc, 128, 0, b->stream>>>(b->start, b->ids, b->g.ncell, N, b->x, b->sp, b->xs, b->sps);
+        k_box_finalize<2><<<nbc, 256, 0, b->stream>>>(b->start, b->ids, b->g.ncell, N, b->x, b->sp, b->xs, b->sps);
     BCU(cudaGetLastError());
-    b->launches += 4;
+    b->launches += 5;
     return PMC_OK;
 }
 
@@ -1047,6 +1092,8 @@ int setup_geometry(BoxState *b, const double *box3) {
         BCU(balloc(&b->count, b->g.ncell));
         BCU(balloc(&b->cursor, b->g.ncell));
         BCU(balloc(&b->start, b->g.ncell + 1));
+        if (b->cid_blocksum) cudaFree(b->cid_blocksum);
+        BCU(balloc(&b->cid_blocksum, (b->g.ncell + 1023) / 1024));
         // everything a peer GPU writes into lives in ONE allocation, so one IPC handle and fixed offsets suffice
         const BlockLayout bl = block_layout(b->N, b->dim, b->g.ncell);
         BCU(balloc(&b->shared_block, bl.total));
@@ -1178,7 +1225,7 @@ void box_destroy(BoxState *b) {
     for (int r = 0; r < b->world; r++)
         if (r != b->rank && b->peer_block[r]) cudaIpcCloseMemHandle(b->peer_block[r]);
     void *bufs[] = {b->shared_block, b->ids, b->cid, b->sp, b->sps, b->eloc, b->par, b->energy, b->etmp, b->acc_total,
-                    b->flags, b->raw, b->rsp, b->count, b->cursor, b->start, b->d_peer_flags};
+                    b->flags, b->raw, b->rsp, b->count, b->cursor, b->start, b->d_peer_flags, b->cid_blocksum};
     for (void *p : bufs)
         if (p) cudaFree(p);
     delete b;
