@@ -68,8 +68,9 @@ enum pmc_precision {
     PMC_MIXED = 1  /* float32 pair terms, float64 accumulation (parity tolerance 1e-6 relative) */
 };
 
-/* src/moves.jl: Displacement :34 (+SimpleGaussian :105), DiscreteSwap :137 (+DoubleUniform :226) */
-enum pmc_move_kind { PMC_MOVE_DISPLACEMENT = 0, PMC_MOVE_SWAP = 1 };
+/* src/moves.jl: Displacement :34 (+SimpleGaussian :105), DiscreteSwap :137 (+DoubleUniform :226),
+ * MoleculeFlip :291 (+DoubleUniform :336-352): species exchange between two unlike sites of one molecule */
+enum pmc_move_kind { PMC_MOVE_DISPLACEMENT = 0, PMC_MOVE_SWAP = 1, PMC_MOVE_FLIP = 2 };
 
 typedef struct pmc_ctx pmc_ctx;
 
@@ -107,8 +108,8 @@ typedef struct pmc_move {
 typedef struct pmc_trial {
     int32_t kind;    /* enum pmc_move_kind */
     int32_t move;    /* index into the pool (for the counters) */
-    int32_t i;       /* Displacement.i / DiscreteSwap.i, 0-based */
-    int32_t j;       /* DiscreteSwap.j, 0-based; -1 for displacements */
+    int32_t i;       /* Displacement.i / DiscreteSwap.i / MoleculeFlip.i, 0-based */
+    int32_t j;       /* DiscreteSwap.j / MoleculeFlip.j, 0-based; -1 for displacements */
     double delta[3]; /* Displacement.delta (unused components 0) */
     double u;        /* the uniform compared with the acceptance probability */
 } pmc_trial;
@@ -126,6 +127,8 @@ int pmc_set_stream(pmc_ctx *ctx, void *cuda_stream);
 /* ---- system definition ------------------------------------------------------------------------ */
 /* model_matrix (src/atoms.jl:25) flattened to [n_species][n_species][PMC_NPAR]. */
 int pmc_set_model(pmc_ctx *ctx, const double *params);
+/* Molecules.start_mol / length_mol (src/molecules.jl:28-29; 0-based starts), needed by MoleculeFlip. */
+int pmc_set_molecules(pmc_ctx *ctx, int32_t n_molecules, const int32_t *start, const int32_t *length);
 /* Molecules.bonds (src/molecules.jl:40) as CSR over sites; the topology is shared by all chains. */
 int pmc_set_bonds(pmc_ctx *ctx, const int32_t *bond_offsets /*[N+1]*/, const int32_t *bond_index);
 /* State of chains [first, first+count): position [count][N][dim], species [count][N], box [count][dim]

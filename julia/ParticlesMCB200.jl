@@ -78,6 +78,8 @@ function MetropolisB200(chains; pool, seed = 1, parallel = false, sweepstep = le
         off = Int32[0; cumsum(length.(s.bonds))]
         idx = Int32[j - 1 for b in s.bonds for j in b]
         check(ccall((:pmc_set_bonds, LIB), Cint, (Ptr{Cvoid}, Ptr{Int32}, Ptr{Int32}), ctx[], off, idx))
+        st, ln = Int32.(s.start_mol .- 1), Int32.(s.length_mol)    # molecules.jl:28-29, needed by MoleculeFlip
+        check(ccall((:pmc_set_molecules, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Int32}, Ptr{Int32}), ctx[], length(st), st, ln))
     end
     for (k, c) in enumerate(chains)                        # Vector{SVector{d,Float64}} is contiguous AoS
         box = collect(Float64, c.box)
@@ -94,6 +96,9 @@ function MetropolisB200(chains; pool, seed = 1, parallel = false, sweepstep = le
         elseif a isa ParticlesMC.DiscreteSwap
             mv.policy isa ParticlesMC.DoubleUniform || error("DiscreteSwap needs the DoubleUniform policy")
             PmcMove(1, a.species[1], a.species[2], 0, mv.probability, 0.0)
+        elseif a isa ParticlesMC.MoleculeFlip
+            mv.policy isa ParticlesMC.DoubleUniform || error("MoleculeFlip needs the DoubleUniform policy")
+            PmcMove(2, 0, 0, 0, mv.probability, 0.0)
         else
             error("$(typeof(a)) is not on the device path")
         end

@@ -20,7 +20,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "_build", "libpmc_oracle.so")
 NPAR = 12
 EMPTYLIST, LINKEDLIST = 0, 1
-MOVE_DISPLACEMENT, MOVE_SWAP = 0, 1
+MOVE_DISPLACEMENT, MOVE_SWAP, MOVE_FLIP = 0, 1, 2
 
 
 def build(force: bool = False) -> str:
@@ -75,6 +75,8 @@ def lib():
         L.orc_step_displacement.argtypes = [C.c_void_p, C.c_int, dp, C.c_double, C.c_int, dp, dp]
         L.orc_step_swap.restype = C.c_int
         L.orc_step_swap.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, dp, dp]
+        L.orc_step_flip.restype = C.c_int
+        L.orc_step_flip.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int, dp, dp]
         L.orc_step_swap_draw.restype = C.c_int
         L.orc_step_swap_draw.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int,
                                          ip, ip, dp, dp]
@@ -194,6 +196,11 @@ class OracleSystem:
     def step_swap(self, A, B, i, j, u, revert_mode=0):
         e1, e2 = C.c_double(), C.c_double()
         acc = lib().orc_step_swap(self._h, A, B, int(i), int(j), float(u), revert_mode, C.byref(e1), C.byref(e2))
+        return bool(acc), e1.value, e2.value
+
+    def step_flip(self, i, j, u, revert_mode=0):
+        e1, e2 = C.c_double(), C.c_double()
+        acc = lib().orc_step_flip(self._h, int(i), int(j), float(u), revert_mode, C.byref(e1), C.byref(e2))
         return bool(acc), e1.value, e2.value
 
     def replay(self, kind, i, j, spA, spB, delta, u, revert_mode=0):

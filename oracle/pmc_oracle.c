@@ -38,7 +38,7 @@
 #define ORC_NPAR 12
 enum { ORC_LJ = 1, ORC_SOFT = 2, ORC_SMOOTHLJ = 3, ORC_KG = 4 };
 enum { ORC_EMPTYLIST = 0, ORC_LINKEDLIST = 1 };
-enum { ORC_MOVE_DISPLACEMENT = 0, ORC_MOVE_SWAP = 1 };
+enum { ORC_MOVE_DISPLACEMENT = 0, ORC_MOVE_SWAP = 1, ORC_MOVE_FLIP = 2 };
 
 /* parameter slots of one species pair (same layout as include/pmc_b200.h) */
 enum {
@@ -303,6 +303,11 @@ static void species_list_build(orc_system *s) {
     free(cur);
 }
 
+static void species_list_build_free(orc_system *s) {
+    free(s->sp_off); free(s->sp_ids); free(s->sp_heads);
+    species_list_build(s);
+}
+
 /* moves.jl:175-179 update_species_list!(species_list, (A,B), i, j) */
 static void species_list_update(orc_system *s, int A, int B, int i, int j) {
     s->sp_ids[s->sp_off[A - 1] + s->sp_heads[i]] = j;
@@ -465,6 +470,37 @@ int orc_step_swap(orc_system *s, int A, int B, int i, int j, double u, int rever
     return acc;
 }
 
+/* One MoleculeFlip trial between two unlike sites i, j of one molecule: moves.jl:301-307 (perform, the same
+ * four-energy swap_particle_species!), :312-314 (invert), :319-323 (revert).  Molecules carry no species list. */
+int orc_step_flip(orc_system *s, int i, int j, double u, int revert_mode, double *e1_out, double *e2_out) {
+    double Eold = s->energy, de;
+    int64_t spi = s->species[i], spj = s->species[j];
+    double e1i = local_energy(s, i), e1j = local_energy(s, j);
+    s->species[i] = spj;
+    s->species[j] = spi;
+    double e2i = local_energy(s, i), e2j = local_energy(s, j);
+    double e1 = e1i + e1j, e2 = e2i + e2j;
+    if (isinf(e1) || isinf(e2)) {
+        de = 0.0;
+    } else {
+        de = e2 - e1;
+        s->energy += de;
+    }
+    int acc = metropolis_accept(e1, e2, s->temperature, u);
+    if (!acc) {
+        s->species[i] = spi;
+        s->species[j] = spj;
+        s->energy -= de;
+        if (revert_mode == 1) s->energy = Eold;
+    } else {
+        /* keep the oracle's own species list usable if swaps are mixed in (not part of the reference path) */
+        species_list_build_free(s);
+    }
+    if (e1_out) *e1_out = e1;
+    if (e2_out) *e2_out = e2;
+    return acc;
+}
+
 /* DoubleUniform draw (moves.jl:238-241): i = sp_ids[A][ka], j = sp_ids[B][kb] */
 int orc_step_swap_draw(orc_system *s, int A, int B, int ka, int kb, double u, int revert_mode,
                        int *i_out, int *j_out, double *e1_out, double *e2_out) {
@@ -485,6 +521,9 @@ void orc_replay(orc_system *s, int64_t n, const int32_t *kind, const int32_t *ii
         int acc;
         if (kind[t] == ORC_MOVE_DISPLACEMENT)
             acc = orc_step_displacement(s, ii[t], delta + 3 * t, u[t], revert_mode, &e1, &e2);
+        else if (kind[t] == ORC_MOVE_FLIP)
+            acc = (ii[t] >= 0 && jj[t] >= 0 && ii[t] != jj[t]) ? orc_step_flip(s, ii[t], jj[t], u[t], revert_mode, &e1, &e2)
+                                                               : (e1 = e2 = 0.0, 0);
         else
             acc = orc_step_swap(s, spA[t], spB[t], ii[t], jj[t], u[t], revert_mode, &e1, &e2);
         if (accepted) accepted[t] = (uint8_t)acc;

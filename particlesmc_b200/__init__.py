@@ -6,7 +6,7 @@ nothing here computes energies or moves on the CPU.
 """
 from .models import (BHHP, JBB, GeneralKG, KobAndersen, LennardJones, Model, SmoothLennardJones, SoftSpheres, Trimer,
                      cutoff, cutoff2, flatten_model_matrix, get_model, model_kind)
-from .moves import (Action, DiscreteSwap, Displacement, DoubleUniform, Move, Policy, SimpleGaussian,
+from .moves import (Action, DiscreteSwap, Displacement, DoubleUniform, MoleculeFlip, Move, Policy, SimpleGaussian,
                     delta_log_target_density, log_proposal_density)
 from .systems import (Atoms, CellList, EmptyList, LinkedList, Molecules, NeighbourList, Particles, System, VerletList,
                       bonds_from_pairs, compute_energy_particle, energy, fold_back, make_context)

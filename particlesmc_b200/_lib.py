@@ -17,7 +17,7 @@ PMC_MAX_BONDS = 6
 PMC_OK, PMC_ERR_INVALID, PMC_ERR_CUDA, PMC_ERR_NONFINITE, PMC_ERR_UNSUPPORTED, PMC_ERR_STATE = range(6)
 MODE_CHAINS, MODE_BOX = 0, 1
 FP64, MIXED = 0, 1
-MOVE_DISPLACEMENT, MOVE_SWAP = 0, 1
+MOVE_DISPLACEMENT, MOVE_SWAP, MOVE_FLIP = 0, 1, 2
 
 
 class PMCError(RuntimeError):
@@ -47,7 +47,7 @@ class Trial(C.Structure):
 # every symbol include/pmc_b200.h declares (tests check that the library exports all of them)
 EXPORTS = [
     "pmc_abi_version", "pmc_last_error", "pmc_create", "pmc_destroy", "pmc_set_stream", "pmc_set_model",
-    "pmc_set_bonds", "pmc_upload", "pmc_init_energy", "pmc_set_moves", "pmc_seed", "pmc_run", "pmc_sync",
+    "pmc_set_bonds", "pmc_set_molecules", "pmc_upload", "pmc_init_energy", "pmc_set_moves", "pmc_seed", "pmc_run", "pmc_sync",
     "pmc_run_traced", "pmc_replay", "pmc_energy", "pmc_total_energy", "pmc_local_energy", "pmc_download",
     "pmc_counters", "pmc_launch_count", "pmc_last_run_ms", "pmc_measure_fma_peak", "pmc_box_peer_export",
     "pmc_box_peer_attach",
@@ -75,6 +75,7 @@ def load():
     L.pmc_set_stream.argtypes = [vp, vp]
     L.pmc_set_model.argtypes = [vp, dp]
     L.pmc_set_bonds.argtypes = [vp, ip, ip]
+    L.pmc_set_molecules.argtypes = [vp, C.c_int32, ip, ip]
     L.pmc_upload.argtypes = [vp, C.c_int32, C.c_int32, dp, lp, dp, dp]
     L.pmc_init_energy.argtypes = [vp]
     L.pmc_set_moves.argtypes = [vp, C.POINTER(MoveSpec), C.c_int32]

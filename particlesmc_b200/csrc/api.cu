@@ -148,6 +148,8 @@ struct pmc_ctx {
     double *box = nullptr, *temp = nullptr, *energy = nullptr, *etot = nullptr, *eloc = nullptr, *par = nullptr;
     unsigned long long *calls = nullptr, *accepted = nullptr;
     uint16_t *bonds = nullptr;
+    int32_t *mol_start = nullptr, *mol_len = nullptr;
+    int n_mol = 0;
     int *bad = nullptr;
     // staging
     double *raw_pos = nullptr;
@@ -181,7 +183,7 @@ int ensure_staging(pmc_ctx *c, size_t chains) {
 
 bool pool_has_swap(const pmc_ctx *c) {
     for (auto &m : c->pool)
-        if (m.kind == PMC_MOVE_SWAP) return true;
+        if (m.kind == PMC_MOVE_SWAP || m.kind == PMC_MOVE_FLIP) return true;
     return false;
 }
 
@@ -221,6 +223,9 @@ void fill_chain_args(pmc_ctx *c, pmc::ChainArgs &a, int64_t n_trials, bool any_s
     a.accepted = c->accepted;
     a.par = c->par;
     a.bonds = c->bonds;
+    a.mol_start = c->mol_start;
+    a.mol_len = c->mol_len;
+    a.n_mol = c->n_mol;
     a.n_moves = (int)c->pool.size();
     double tot = 0.0, cum = 0.0;
     for (auto &m : c->pool) tot += m.probability;
@@ -396,7 +401,7 @@ void pmc_destroy(pmc_ctx *c) {
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
     if (c->boxst) pmc::box_destroy(c->boxst);
     void *bufs[] = {c->x, c->img, c->sp, c->spids, c->heads, c->spoff, c->box, c->temp, c->energy, c->etot, c->eloc,
-                    c->par, c->calls, c->accepted, c->bonds, c->bad, c->raw_pos, c->raw_sp};
+                    c->par, c->calls, c->accepted, c->bonds, c->bad, c->raw_pos, c->raw_sp, c->mol_start, c->mol_len};
     for (void *p : bufs)
         if (p) cudaFree(p);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -430,6 +435,25 @@ int pmc_set_model(pmc_ctx *c, const double *params) {
         if (rc) return fail(rc, "%s", pmc::box_error());
     }
     c->model_set = true;
+    return PMC_OK;
+}
+
+int pmc_set_molecules(pmc_ctx *c, int32_t n_mol, const int32_t *start, const int32_t *length) {
+    if (!c || !start || !length) return fail(PMC_ERR_INVALID, "null argument");
+    if (n_mol < 1) return fail(PMC_ERR_INVALID, "n_molecules must be >= 1");
+    CU(cudaSetDevice(c->cfg.device));
+    for (int m = 0; m < n_mol; m++)
+        if (start[m] < 0 || length[m] < 1 || start[m] + length[m] > c->cfg.n_particles)
+            return fail(PMC_ERR_INVALID, "molecule %d: sites [%d, %d) outside 0..%d", m, start[m], start[m] + length[m], c->cfg.n_particles);
+    if (c->mol_start) cudaFree(c->mol_start);
+    if (c->mol_len) cudaFree(c->mol_len);
+    c->mol_start = c->mol_len = nullptr;
+    CU(cudaMalloc((void **)&c->mol_start, sizeof(int32_t) * n_mol));
+    CU(cudaMalloc((void **)&c->mol_len, sizeof(int32_t) * n_mol));
+    CU(cudaMemcpyAsync(c->mol_start, start, sizeof(int32_t) * n_mol, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->mol_len, length, sizeof(int32_t) * n_mol, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->n_mol = n_mol;
     return PMC_OK;
 }
 
@@ -530,7 +554,12 @@ int pmc_set_moves(pmc_ctx *c, const pmc_move *pool, int32_t n) {
     double tot = 0.0;
     for (int k = 0; k < n; k++) {
         const pmc_move &m = pool[k];
-        if (m.kind != PMC_MOVE_DISPLACEMENT && m.kind != PMC_MOVE_SWAP) return fail(PMC_ERR_INVALID, "move %d: unknown kind %d", k, m.kind);
+        if (m.kind != PMC_MOVE_DISPLACEMENT && m.kind != PMC_MOVE_SWAP && m.kind != PMC_MOVE_FLIP)
+            return fail(PMC_ERR_INVALID, "move %d: unknown kind %d", k, m.kind);
+        if (m.kind == PMC_MOVE_FLIP) {
+            if (c->n_mol < 1) return fail(PMC_ERR_STATE, "move %d: MoleculeFlip needs pmc_set_molecules first", k);
+            if (c->cfg.mode == PMC_MODE_BOX) return fail(PMC_ERR_UNSUPPORTED, "MoleculeFlip is not available in PMC_MODE_BOX");
+        }
         if (!(m.probability >= 0.0)) return fail(PMC_ERR_INVALID, "move %d: negative probability", k);
         if (m.kind == PMC_MOVE_DISPLACEMENT && !(m.sigma > 0.0)) return fail(PMC_ERR_INVALID, "move %d: sigma must be positive", k);
         if (m.kind == PMC_MOVE_SWAP) {
@@ -601,10 +630,10 @@ static int traced_or_replay(pmc_ctx *c, int64_t n, const pmc_trial *in, pmc_tria
         fixed.assign(in, in + tot);
         for (auto &t : fixed) {
             if (t.kind == PMC_MOVE_DISPLACEMENT) t.j = -1;
-            if (t.kind == PMC_MOVE_SWAP) replay_swaps = true;
+            if (t.kind == PMC_MOVE_SWAP || t.kind == PMC_MOVE_FLIP) replay_swaps = true;
             const bool ok = t.move >= 0 && t.move < PMC_MAX_MOVES && t.i >= 0 && t.i < c->cfg.n_particles &&
                             (t.kind == PMC_MOVE_DISPLACEMENT ||
-                             (t.kind == PMC_MOVE_SWAP && t.j >= 0 && t.j < c->cfg.n_particles && t.j != t.i));
+                             ((t.kind == PMC_MOVE_SWAP || t.kind == PMC_MOVE_FLIP) && t.j >= 0 && t.j < c->cfg.n_particles && t.j != t.i));
             if (!ok) return fail(PMC_ERR_INVALID, "replay trial out of range (kind %d, move %d, i %d, j %d)", t.kind, t.move, t.i, t.j);
         }
     }

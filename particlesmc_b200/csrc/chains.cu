@@ -40,8 +40,10 @@ struct __align__(16) TrialRec {
     int i;                            // particle i, or slot ka in the species-A list for swaps
     int j;                            // slot kb for swaps, -2 for displacements
     int m;                            // pool index
-    int pad[2];
+    int pad[2];                       // MoleculeFlip: four parked (site a, site b) pairs, 8 bits each
     uint32_t thr_t[PMC_MAX_SPECIES];  // FILTER: (rc_s + |delta|/2)^2 in fixed-point units
+    int flip;                         // 1: MoleculeFlip whose sites are resolved from `pad` when the trial executes
+    int pad2[3];
 };
 
 // Fixed-size part of the CTA state: statically allocated so every access is a constant shared-memory
@@ -264,6 +266,7 @@ __global__ void __launch_bounds__(NTMAX, NTMAX <= 128 ? 5 : 2) k_chain_sweep(con
         for (int t_ = tid; t_ < nb; t_ += NT) {
             const long long q = tb + t_;
             pmc_trial tr;
+            unsigned long long flip_pairs = 0ull;
             if (A.replay) {
                 tr = A.replay[(size_t)c * A.n_trials + q];
             } else {
@@ -287,6 +290,28 @@ __global__ void __launch_bounds__(NTMAX, NTMAX <= 128 ? 5 : 2) k_chain_sweep(con
                     tr.delta[0] = (double)(sg * z0);
                     tr.delta[1] = (double)(sg * z1);
                     tr.delta[2] = (DIM == 3) ? (double)(sg * z2) : 0.0;
+                } else if (tr.kind == PMC_MOVE_FLIP) {
+                    // MoleculeFlip (src/moves.jl:344-352): a molecule uniformly, then ordered pairs of distinct sites
+                    // until their species differ.  Species are only known when the trial executes, so four candidate
+                    // pairs are parked; the first unlike one is taken (none: the trial is a rejected no-op).
+                    const int mol = A.n_mol > 0 ? (int)bounded(a.v[1], (uint32_t)A.n_mol) : 0;
+                    const int len = A.n_mol > 0 ? A.mol_len[mol] : 0;
+                    tr.i = A.n_mol > 0 ? A.mol_start[mol] : -1;
+                    tr.j = -1;
+                    const Philox4 c4 = philox4x32_10((uint32_t)t, (uint32_t)(t >> 32), gchain, 2u, k0, k1);
+                    const uint32_t w[8] = {b.v[0], b.v[1], b.v[2], b.v[3], c4.v[0], c4.v[1], c4.v[2], c4.v[3]};
+                    unsigned long long packed = 0;
+                    for (int q = 0; q < 4; q++) {
+                        uint32_t pa = 0, pb = 0;
+                        if (len >= 2) {
+                            pa = bounded(w[2 * q], (uint32_t)len);
+                            pb = bounded(w[2 * q + 1], (uint32_t)(len - 1));
+                            pb += (pb >= pa) ? 1u : 0u;
+                        }
+                        packed |= (unsigned long long)((pa & 0xFFu) | ((pb & 0xFFu) << 8)) << (16 * q);
+                    }
+                    flip_pairs = len >= 2 && len <= 255 ? packed : 0ull;
+                    tr.delta[0] = tr.delta[1] = tr.delta[2] = 0.0;
                 } else {  // slots in the species lists; resolved to particles when the trial executes
                     const int nA = T.spoff[A.mv_a[m] + 1] - T.spoff[A.mv_a[m]];
                     const int nB = T.spoff[A.mv_b[m] + 1] - T.spoff[A.mv_b[m]];
@@ -300,7 +325,10 @@ __global__ void __launch_bounds__(NTMAX, NTMAX <= 128 ? 5 : 2) k_chain_sweep(con
             R.thr = A.exact_exp ? tr.u : -Tk * log(tr.u);
             R.m = tr.move;
             R.i = tr.i;
-            R.j = (tr.kind == PMC_MOVE_SWAP) ? tr.j : -2;  // -2 marks a displacement
+            R.j = (tr.kind == PMC_MOVE_DISPLACEMENT) ? -2 : tr.j;  // -2 marks a displacement
+            R.pad[0] = (tr.kind == PMC_MOVE_FLIP && !A.replay) ? (int)(uint32_t)flip_pairs : 0;
+            R.pad[1] = (tr.kind == PMC_MOVE_FLIP && !A.replay) ? (int)(uint32_t)(flip_pairs >> 32) : 0;
+            R.flip = (tr.kind == PMC_MOVE_FLIP && !A.replay) ? 1 : 0;
 #pragma unroll
             for (int a = 0; a < 3; a++) {
                 R.delta[a] = tr.delta[a];
@@ -428,6 +456,17 @@ __global__ void __launch_bounds__(NTMAX, NTMAX <= 128 ? 5 : 2) k_chain_sweep(con
                 if (A.replay) {
                     i = ka;
                     j = kb;
+                } else if (R.flip) {
+                    const unsigned long long packed = (unsigned long long)(uint32_t)R.pad[0] | ((unsigned long long)(uint32_t)R.pad[1] << 32);
+                    if (packed != 0ull && ka >= 0) {
+                        for (int q = 3; q >= 0; q--) {  // first unlike pair wins
+                            const int sa = ka + (int)((packed >> (16 * q)) & 0xFFull), sb = ka + (int)((packed >> (16 * q + 8)) & 0xFFull);
+                            if (S.sp[sa] != S.sp[sb]) {
+                                i = sa;
+                                j = sb;
+                            }
+                        }
+                    }
                 } else if (ka >= 0) {
                     i = S.spids[T.spoff[A.mv_a[m]] + ka];
                     j = S.spids[T.spoff[A.mv_b[m]] + kb];

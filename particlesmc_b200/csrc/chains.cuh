@@ -25,6 +25,9 @@ struct ChainArgs {
     unsigned long long *accepted;  // [M][PMC_MAX_MOVES]
     const double *par;             // [ns][ns][PMC_NPAR]
     const uint16_t *bonds;         // [Npad][PMC_MAX_BONDS], 0xFFFF = none (shared topology)
+    const int32_t *mol_start;      // [n_mol] first site of each molecule (MoleculeFlip)
+    const int32_t *mol_len;        // [n_mol]
+    int32_t n_mol;
     // move pool
     int32_t n_moves;
     int32_t mv_kind[PMC_MAX_MOVES];

@@ -81,6 +81,12 @@ class DeviceContext:
         idx = np.asarray([j for b in bonds for j in b] or [0], dtype=np.int32)
         L.check(self.lib.pmc_set_bonds(self._h, _ip(off), _ip(idx)))
 
+    def set_molecules(self, start, length):
+        """Molecules.start_mol / length_mol with 0-based starts (needed by MoleculeFlip)."""
+        st = np.ascontiguousarray(start, dtype=np.int32)
+        ln = np.ascontiguousarray(length, dtype=np.int32)
+        L.check(self.lib.pmc_set_molecules(self._h, len(st), _ip(st), _ip(ln)))
+
     def upload(self, position, species, box, temperature, first: int = 0):
         pos = np.ascontiguousarray(position, dtype=np.float64)
         if pos.ndim == 2:
@@ -108,6 +114,8 @@ class DeviceContext:
         for k, m in enumerate(moves):
             if m["kind"] in ("displacement", L.MOVE_DISPLACEMENT):
                 arr[k] = L.MoveSpec(L.MOVE_DISPLACEMENT, 0, 0, 0, float(m["prob"]), float(m["sigma"]))
+            elif m["kind"] in ("flip", L.MOVE_FLIP):
+                arr[k] = L.MoveSpec(L.MOVE_FLIP, 0, 0, 0, float(m["prob"]), 0.0)
             else:
                 a, b = m["species"]
                 arr[k] = L.MoveSpec(L.MOVE_SWAP, int(a), int(b), 0, float(m["prob"]), 0.0)

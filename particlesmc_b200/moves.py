@@ -45,6 +45,14 @@ class DiscreteSwap(Action):
         return cls(1, 1, (int(species[0]), int(species[1])), (n1, n2), 0.0)
 
 
+@dataclass
+class MoleculeFlip(Action):
+    """mutable struct MoleculeFlip (src/moves.jl:291-295): species exchange between two unlike sites of a molecule."""
+    i: int = 0
+    j: int = 0
+    de: float = 0.0
+
+
 class SimpleGaussian(Policy):
     """struct SimpleGaussian <: Policy (src/moves.jl:105); parameters: sigma."""
 
@@ -83,6 +91,8 @@ def log_proposal_density(action: Action, policy: Policy, parameters, system) -> 
         return float(-np.dot(delta, delta) / (2 * sigma ** 2) - system.d * np.log(2 * np.pi * sigma ** 2) / 2)
     if isinstance(action, DiscreteSwap):
         return float(-np.log(action.particles_per_species[0] * action.particles_per_species[1]))
+    if isinstance(action, MoleculeFlip):
+        return float(-np.log(2))  # src/moves.jl:336-338
     raise TypeError(type(action))
 
 
@@ -103,6 +113,10 @@ def pool_to_specs(pool: Sequence[Move]):
                 raise NotImplementedError("DiscreteSwap is implemented with the DoubleUniform policy "
                                           "(EnergyBias is policy-guided MC, outside the hot path)")
             specs.append({"kind": "swap", "prob": mv.probability, "species": tuple(mv.action.species)})
+        elif isinstance(mv.action, MoleculeFlip):
+            if not isinstance(mv.policy, DoubleUniform):
+                raise NotImplementedError("MoleculeFlip is implemented with the DoubleUniform policy")
+            specs.append({"kind": "flip", "prob": mv.probability})
         else:
             raise NotImplementedError(f"action {type(mv.action).__name__} is not on the device path")
     return specs

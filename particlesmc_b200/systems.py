@@ -155,6 +155,7 @@ def make_context(systems: Sequence[Particles], *, device: int = 0, chain_offset:
         ctx.set_model(params)
         if mol:
             ctx.set_bonds([[j - 1 for j in b] for b in s0.bonds])
+            ctx.set_molecules([f - 1 for f in s0.start_mol], s0.length_mol)
         ctx.upload(np.stack([s.position for s in systems]), np.stack([s.species for s in systems]),
                    np.stack([s.box for s in systems]), np.array([s.temperature for s in systems]))
     except Exception:

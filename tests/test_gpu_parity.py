@@ -208,6 +208,31 @@ def test_trace_parity_molecules(molecule):
         check_trace(ctx, [orc], {0: (0, 0)}, 2000)
 
 
+def test_trace_parity_molecule_flip(molecule):
+    """examples/ortho-terphenyl pool: Displacement 0.8 + MoleculeFlip 0.2 (params-template.toml:59-68)."""
+    par = M.flatten_model_matrix(M.Trimer())
+    with DeviceContext(2, 3000, 3, 3, M.MODEL_KG, molecules=True) as ctx:
+        ctx.set_model(par)
+        ctx.set_bonds(zero_based(molecule["bonds"]))
+        ctx.set_molecules(np.arange(0, 3000, 3), np.full(1000, 3))
+        ctx.upload(np.stack([molecule["position"]] * 2), np.stack([molecule["species"]] * 2), molecule["box"],
+                   [molecule["temperature"], 8.0])
+        ctx.init_energy()
+        ctx.set_moves([dict(kind="displacement", prob=0.8, sigma=0.05), dict(kind="flip", prob=0.2)])
+        ctx.seed(3)
+        orcs = [O.OracleSystem(molecule["position"], molecule["species"], molecule["box"], T, M.MODEL_KG, par,
+                               O.LINKEDLIST, bonds=zero_based(molecule["bonds"])) for T in (molecule["temperature"], 8.0)]
+        tr, acc = check_trace(ctx, orcs, {0: (0, 0), 1: (0, 0)}, 2500)
+        fl = tr["kind"] == 2
+        assert abs(fl.mean() - 0.2) < 0.03
+        # both sites belong to the same trimer and carried different species when the flip was drawn
+        assert np.all(tr["i"][fl] // 3 == tr["j"][fl] // 3) and np.all(tr["i"][fl] != tr["j"][fl])
+        assert acc[fl].sum() > 0
+        _, sp = ctx.download()
+        for c in range(2):  # every trimer still holds one site of each species
+            assert np.array_equal(np.sort(sp[c].reshape(1000, 3), axis=1), np.tile([1, 2, 3], (1000, 1)))
+
+
 def test_replay_of_injected_proposals():
     """Proposals and uniforms recorded elsewhere (here: numpy) replayed through the sweep kernel with the
     reference's acceptance arithmetic: decisions bit-exact vs the oracle running the reference's revert."""

@@ -172,3 +172,20 @@ def test_small_box_stencil_dedup():
     b = O.OracleSystem(pos, sp, box, 1.0, M.MODEL_LJ, par, O.LINKEDLIST)
     assert list(b.ncells()) == [1, 1, 1]
     assert np.allclose(a.local_energies(), b.local_energies(), rtol=1e-13, atol=1e-13)
+
+
+def test_molecule_flip_is_reversible(molecule):
+    """MoleculeFlip (moves.jl:301-323): exchanging the species of two unlike sites of a trimer twice restores the
+    energy; a rejected flip leaves species and energy untouched."""
+    par = M.flatten_model_matrix(M.Trimer())
+    s = O.OracleSystem(molecule["position"], molecule["species"], molecule["box"], molecule["temperature"],
+                       M.MODEL_KG, par, O.LINKEDLIST, bonds=zero_based(molecule["bonds"]))
+    e0 = s.energy
+    acc, e1, e2 = s.step_flip(0, 2, 0.0, revert_mode=0)          # u = 0: accepted unless the energy is infinite
+    if acc:
+        assert s.state()[1][0] == 3 and s.state()[1][2] == 1
+        assert abs(s.energy - s.total_energy()) < 1e-8
+        acc2, f1, f2 = s.step_flip(0, 2, 0.0, revert_mode=0)
+        assert acc2 and abs(s.energy - e0) < 1e-8 and abs((f2 - f1) + (e2 - e1)) < 1e-8
+    acc3, g1, g2 = s.step_flip(3, 4, 1.0, revert_mode=0)        # u = 1: always rejected
+    assert not acc3 and s.state()[1][3] == 1 and s.state()[1][4] == 2 and abs(s.energy - e0) < 1e-8
