@@ -93,6 +93,21 @@ def test_box_sweeps_keep_invariants():
         assert np.array_equal(p, p2)
 
 
+def radial_distribution(pos, box, sel_a, sel_b, rmax=3.0, nbins=60):
+    """g_ab(r) from one configuration (minimum image, cubic box), numpy on the host."""
+    a, b = pos[sel_a], pos[sel_b]
+    L = box[0]
+    hist = np.zeros(nbins)
+    for chunk in np.array_split(np.arange(len(a)), 8):
+        d = a[chunk, None, :] - b[None, :, :]
+        d -= np.round(d / L) * L
+        r = np.sqrt((d * d).sum(-1)).ravel()
+        hist += np.histogram(r[(r > 1e-9) & (r < rmax)], bins=nbins, range=(0.0, rmax))[0]
+    edges = np.linspace(0.0, rmax, nbins + 1)
+    shell = 4.0 / 3.0 * np.pi * (edges[1:] ** 3 - edges[:-1] ** 3)
+    return hist / (len(a) * shell * len(b) / L ** 3)
+
+
 def test_checkerboard_samples_same_energy_as_sequential_chain():
     """Statistical parity (north_star: energy distribution within statistical error): mean energy per
     particle of the checkerboard sampler vs the sequential one-particle-at-a-time chain kernel, KA T=1."""
@@ -110,16 +125,27 @@ def test_checkerboard_samples_same_energy_as_sequential_chain():
             ctx.set_moves(moves)
             ctx.seed(5)
             ctx.run(eq * N)
-            es = []
-            for _ in range(nblk):
+            es, gs = [], []
+            for k in range(nblk):
                 ctx.run(blk * N)
                 es.append(ctx.energy()[0] / N)
+                if k % 4 == 3:
+                    p, s_ = ctx.download()
+                    p = p[0] - np.floor(p[0] / box) * box
+                    gs.append(radial_distribution(p, box, s_[0] == 1, s_[0] == 1))
             series[name] = np.array(es)
+            series[name + "_g"] = np.mean(gs, axis=0)
             calls, acc = ctx.counters()
             series[name + "_acc"] = acc[0, 0] / calls[0, 0]
     mb, mc = series["box"].mean(), series["chain"].mean()
     # block means are correlated; use a conservative error: 3 x std of block means / sqrt(nblk/4)
     err = 3.0 * max(series["box"].std(), series["chain"].std()) / np.sqrt(nblk / 4)
     assert abs(mb - mc) < max(err, 0.01), (mb, mc, err)
+    # g_AA(r): first peak position/height and the whole curve agree within sampling noise (north_star: g(r))
+    gb, gc = series["box_g"], series["chain_g"]
+    assert abs(np.argmax(gb) - np.argmax(gc)) <= 1
+    assert abs(gb.max() - gc.max()) < 0.08 * gc.max()
+    assert np.max(np.abs(gb - gc)) < 0.15 and np.mean(np.abs(gb - gc)) < 0.03
+    assert gc[:15].max() < 1e-3 and abs(gc[-5:].mean() - 1.0) < 0.1  # excluded core, plateau ~ 1
     # acceptance: the checkerboard additionally rejects cell-crossing proposals (~ 3*sigma*sqrt(2/pi)/cell side)
     assert abs(series["box_acc"] - series["chain_acc"]) < 0.06
