@@ -56,6 +56,8 @@ def parse_args():
     ap.add_argument("--equil", type=int, default=100, help="untimed equilibration sweeps from the lattice")
     ap.add_argument("--threads", type=int, default=0, help="CTA size of the sweep kernel (0 = library default)")
     ap.add_argument("--temperature", type=float, default=1.0)
+    ap.add_argument("--precision", default="fp64", choices=["fp64", "mixed"],
+                    help="mixed = fp32 pair terms / fp64 accumulation (reported separately, 1e-6 tolerance)")
     ap.add_argument("--prefilter", type=int, default=0, help="0 = fixed-point prefilter (default), -1 = visit all candidates in fp64")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -201,7 +203,7 @@ def run_ours(args):
     mode = L.MODE_CHAINS if args.workload == "chains" else L.MODE_BOX
     # chains are keyed by their GLOBAL index: rank r holds chains [r*Mc, (r+1)*Mc)
     ctx = DeviceContext(Mc, N, 3, 2, M.MODEL_LJ, mode=mode, device=local, chain_offset=rank * Mc, threads=args.threads,
-                        prefilter=args.prefilter)
+                        prefilter=args.prefilter, precision=L.MIXED if args.precision == "mixed" else L.FP64)
     stream = torch.cuda.Stream(device=dev)  # a non-default stream shared by torch events and the library
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
@@ -343,7 +345,8 @@ def run_ours(args):
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "seconds": dt}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-                "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "scaling": "strong" if strong else "weak", "vs_baseline": None,
+                "dtype": "f64" if args.precision == "fp64" else "f32 pair terms / f64 accumulate", "data": "synthetic",
                 "config": {"workload": name, "sweeps_per_step": sweeps, "trials_per_step_per_gpu": Mc * trials_per_step // (world if strong else 1),
                            "equilibration_sweeps": args.equil, "cta_threads": args.threads or "default",
                            "l2": "256 MiB buffer zeroed between steps (L2 flush)", "seed": 42},

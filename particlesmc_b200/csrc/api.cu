@@ -295,7 +295,12 @@ int sweep(pmc_ctx *c, int64_t n_trials, const pmc_trial *d_replay, pmc_trial *d_
     CU(cudaEventRecord(c->ev0, c->stream));
     const bool filter = c->cubic && c->cfg.prefilter >= 0 && c->sweep_smem_filter > c->sweep_smem;
     const bool fastk = filter && !any_swap && !c->cfg.molecules && pmc::chain_fast_supported(c->Npad, c->threads);
-    if (fastk) {
+    if (c->cfg.precision == PMC_MIXED) {
+        if (!fastk)
+            return fail(PMC_ERR_UNSUPPORTED, "PMC_MIXED needs a cubic box, a Displacement-only pool and %d threads per CTA", 128);
+        CU(pmc::launch_chain_sweep_mixed(c->cfg.dim, c->cfg.model_kind, c->cfg.n_chains,
+                                         pmc::chain_mixed_smem_bytes(c->cfg.dim, c->Npad), a, c->stream));
+    } else if (fastk) {
         const size_t fs = pmc::chain_fast_smem_bytes(c->cfg.dim, c->Npad, c->cfg.n_species);
         if (fs != c->fast_smem) {
             CU(pmc::configure_chain_fast(c->cfg.dim, c->cfg.model_kind, c->Npad, fs));
@@ -332,7 +337,9 @@ int pmc_create(const pmc_config *cfg, pmc_ctx **out) {
     if (cfg->molecules && cfg->model_kind != PMC_MODEL_KG)
         return fail(PMC_ERR_INVALID, "Molecules require the GeneralKG model (bond_potential)");
     if (cfg->n_chains < 1 || cfg->n_particles < 1) return fail(PMC_ERR_INVALID, "n_chains and n_particles must be >= 1");
-    if (cfg->precision != PMC_FP64) return fail(PMC_ERR_UNSUPPORTED, "only PMC_FP64 is implemented in this build");
+    if (cfg->precision != PMC_FP64 && cfg->precision != PMC_MIXED) return fail(PMC_ERR_INVALID, "unknown precision %d", cfg->precision);
+    if (cfg->precision == PMC_MIXED && (cfg->mode != PMC_MODE_CHAINS || cfg->molecules || cfg->n_particles > 1024))
+        return fail(PMC_ERR_UNSUPPORTED, "PMC_MIXED is implemented for PMC_MODE_CHAINS, Atoms, N <= 1024 (Displacement pools, cubic boxes)");
     if (cfg->mode != PMC_MODE_CHAINS && cfg->mode != PMC_MODE_BOX) return fail(PMC_ERR_INVALID, "unknown mode %d", cfg->mode);
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);

@@ -720,6 +720,29 @@ static cudaError_t fast_dispatch(int dim, int model, int Npad, F &&f) {
     });
 }
 
+size_t chain_mixed_smem_bytes(int dim, int Npad) { return fast::mixed_layout(dim, fast_npad(Npad)).total; }
+
+template <typename F>
+static cudaError_t mixed_dispatch(int dim, int model, int Npad, F &&f) {
+    return dispatch(dim, model, false, [&](auto D, auto MDL, auto) {
+        constexpr int d = decltype(D)::value, mdl = decltype(MDL)::value;
+        switch (fast_npad(Npad)) {
+        case 256: return f(fast::k_chain_sweep_mixed<d, mdl, 256>);
+        case 512: return f(fast::k_chain_sweep_mixed<d, mdl, 512>);
+        default: return f(fast::k_chain_sweep_mixed<d, mdl, 1024>);
+        }
+    });
+}
+
+cudaError_t launch_chain_sweep_mixed(int dim, int model, int M, size_t smem, const ChainArgs &a, cudaStream_t st) {
+    return mixed_dispatch(dim, model, a.Npad, [&](auto kernel) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kernel<<<M, fast::kFastThreads, smem, st>>>(a);
+        return cudaGetLastError();
+    });
+}
+
 cudaError_t configure_chain_fast(int dim, int model, int Npad, size_t smem) {
     return fast_dispatch(dim, model, Npad, [&](auto kernel) {
         return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

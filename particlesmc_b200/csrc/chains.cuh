@@ -73,6 +73,9 @@ bool chain_fast_supported(int Npad, int threads);
 size_t chain_fast_smem_bytes(int dim, int Npad, int ns);
 cudaError_t configure_chain_fast(int dim, int model, int Npad, size_t smem);
 cudaError_t launch_chain_sweep_fast(int dim, int model, int M, size_t smem, const ChainArgs &a, cudaStream_t st);
+// PMC_MIXED variant of the fast kernel (fp32 pair terms on fixed-point coordinates, fp64 accumulation)
+size_t chain_mixed_smem_bytes(int dim, int Npad);
+cudaError_t launch_chain_sweep_mixed(int dim, int model, int M, size_t smem, const ChainArgs &a, cudaStream_t st);
 cudaError_t configure_chain_kernels(int dim, int model, bool mol, size_t sweep_smem, size_t sweep_smem_filter,
                                     size_t energy_smem);
 

@@ -365,5 +365,306 @@ __global__ void __launch_bounds__(kFastThreads, 6) k_chain_sweep_fast(const __gr
     }
 }
 
+
+// ==================================================================================================
+// PMC_MIXED: float32 pair terms, float64 accumulation (north star: "reported separately at 1e-6").
+// During a launch the chain state IS the 32-bit fixed-point representation (resolution L / 2^32 ~ 2e-9):
+// proposals are applied in fixed point, squared distances come from the same wrapping integer arithmetic as
+// the prefilter (minimum image for free, relative resolution ~2e-8), the pair potential is evaluated in fp32
+// (MUFU.RCP instead of a 5-instruction fp64 reciprocal), per-lane partial sums are fp32 (<= 3 terms) and
+// everything across lanes / warps / trials is accumulated in fp64.  No fp64 positions in shared memory:
+// 18 KB per chain instead of 31 KB.
+// ==================================================================================================
+struct MixedLayout {
+    uint32_t u, sp, q, cp, rec, red, cnt, rcs, total;
+};
+__host__ __device__ inline MixedLayout mixed_layout(int dim, int Npad) {
+    MixedLayout f;
+    uint32_t o = 0;
+    auto take = [&](uint32_t bytes) {
+        uint32_t p = o;
+        o += (bytes + 15u) & ~15u;
+        return p;
+    };
+    f.u = take(4u * dim * Npad);
+    f.sp = take(Npad);
+    f.q = take(2u * (uint32_t)Npad);
+    f.cp = take(32u * PMC_MAX_SPECIES * PMC_MAX_SPECIES);  // float table {rc2, eps4|eps, sig2, shift, c0|ndiv2, c2, c4, -}
+    f.rec = take((uint32_t)kRecBytes * kFastBatch);
+    f.red = take(8u * 2 * kFastWarps);
+    f.cnt = take(8u * 2 * PMC_MAX_MOVES);
+    f.rcs = take(8u * PMC_MAX_SPECIES);
+    f.total = o;
+    return f;
+}
+
+__device__ __forceinline__ void lds_f32x4(uint32_t a, float &v0, float &v1, float &v2, float &v3) {
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v0), "=f"(v1), "=f"(v2), "=f"(v3) : "r"(a) : "memory");
+}
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
+template <int DIM>
+__device__ __forceinline__ uint32_t dist2_u32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t a0, uint32_t a1, uint32_t a2) {
+    int d = (int)(c0 - a0);
+    uint32_t r = (uint32_t)__mulhi(d, d);
+    d = (int)(c1 - a1);
+    r += (uint32_t)__mulhi(d, d);
+    if constexpr (DIM == 3) {
+        d = (int)(c2 - a2);
+        r += (uint32_t)__mulhi(d, d);
+    }
+    return r;
+}
+
+// fp32 pair potential, parameters p0..p6 = {eps4|eps, sig2, shift, c0|ndiv2, c2, c4}
+template <int MODEL>
+__device__ __forceinline__ float pair_potential_f32(float r2, float eps, float sig2, float shift, float c0, float c2, float c4) {
+    const float x = sig2 * __frcp_rn(r2);
+    if constexpr (MODEL == PMC_MODEL_LJ || MODEL == PMC_MODEL_KG) {
+        const float x3 = x * x * x;
+        return fmaf(eps, fmaf(x3, x3, -x3), -shift);
+    } else if constexpr (MODEL == PMC_MODEL_SMOOTHLJ) {
+        const float x3 = x * x * x;
+        return eps * (fmaf(x3, x3, -x3) + c0 + r2 * fmaf(r2, c4, c2));
+    } else {
+        const int n = (int)c0;
+        float v;
+        if ((float)n == c0) {
+            v = 1.0f;
+            float b = x;
+            for (int k = n; k > 0; k >>= 1) {
+                if (k & 1) v *= b;
+                b *= b;
+            }
+        } else {
+            v = powf(x, c0);
+        }
+        return fmaf(eps, v, -shift);
+    }
+}
+
+template <int DIM, int MODEL, int NPAD>
+__global__ void __launch_bounds__(kFastThreads, 8) k_chain_sweep_mixed(const __grid_constant__ ChainArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int kFastCand = NPAD / kFastThreads;
+    constexpr int Npad = NPAD;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int c = blockIdx.x;
+    const int N = A.N, gNpad = A.Npad, ns = A.ns;
+    const MixedLayout F = mixed_layout(DIM, Npad);
+    const uint32_t sb = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    constexpr uint32_t nb4 = 4u * (uint32_t)NPAD;
+
+    const double L = A.box[c * 3];
+    const double fscale = 4294967296.0 / L;
+    const float r2scale = (float)(L * L * 0x1p-32);  // fixed-point r^2 units -> length^2
+    double *gx = A.x + (size_t)c * DIM * gNpad;
+    {
+        uint32_t *su = (uint32_t *)(smem_raw + F.u);
+        for (int a = 0; a < DIM; a++)
+            for (int k = tid; k < Npad; k += kFastThreads) su[a * Npad + k] = k < gNpad ? to_fixed32(gx[a * gNpad + k], fscale) : 0u;
+        uint8_t *ssp = smem_raw + F.sp;
+        const uint8_t *gsp = A.sp + (size_t)c * gNpad;
+        for (int k = tid; k < Npad; k += kFastThreads) ssp[k] = k < gNpad ? gsp[k] : 0;
+        float *scp = (float *)(smem_raw + F.cp);
+        for (int k = tid; k < ns * ns; k += kFastThreads) {
+            const double *p = A.par + k * PMC_NPAR;
+            scp[8 * k + 0] = (float)p[PMC_P_RCUT2];
+            scp[8 * k + 1] = (float)p[PMC_P_EPS];
+            scp[8 * k + 2] = (float)p[PMC_P_SIG2];
+            scp[8 * k + 3] = (float)p[PMC_P_SHIFT];
+            scp[8 * k + 4] = (float)p[5];  // C0 | ndiv2
+            scp[8 * k + 5] = (float)p[6];  // C2 / sigma^2
+            scp[8 * k + 6] = (float)p[7];  // C4 / sigma^4
+            scp[8 * k + 7] = 0.0f;
+        }
+        unsigned long long *scnt = (unsigned long long *)(smem_raw + F.cnt);
+        if (tid < 2 * PMC_MAX_MOVES) scnt[tid] = 0ull;
+        if (tid < PMC_MAX_SPECIES) {
+            double rc2 = 0.0;
+            for (int b = 0; b < ns; b++) rc2 = fmax(rc2, A.par[((tid < ns ? tid : 0) * ns + b) * PMC_NPAR + PMC_P_RCUT2]);
+            ((double *)(smem_raw + F.rcs))[tid] = sqrt(rc2);
+        }
+    }
+    uint32_t myu[kFastCand][DIM];
+#pragma unroll
+    for (int k = 0; k < kFastCand; k++) {
+        const int j = k * kFastThreads + tid;
+#pragma unroll
+        for (int a = 0; a < DIM; a++) myu[k][a] = j < gNpad ? to_fixed32(gx[a * gNpad + j], fscale) : 0u;
+    }
+    const double Tk = A.temp[c];
+    double E = A.energy[c];
+    const uint32_t k0 = (uint32_t)A.seed, k1 = (uint32_t)(A.seed >> 32);
+    const uint32_t gchain = (uint32_t)(A.chain_offset + c);
+    int32_t *gimg = A.img + (size_t)c * DIM * gNpad;
+    const uint32_t qa = sb + F.q + (uint32_t)warp * (2u * kFastCand * 32);
+    uint32_t slot = 0;
+
+    for (long long tb = 0; tb < A.n_trials; tb += kFastBatch) {
+        const int nb = (int)min((long long)kFastBatch, A.n_trials - tb);
+        __syncthreads();
+        if (tid < nb) {
+            const long long q = tb + tid;
+            pmc_trial tr;
+            if (A.replay) {
+                tr = A.replay[(size_t)c * A.n_trials + q];
+            } else {
+                const unsigned long long t = A.t0 + (unsigned long long)q;
+                const Philox4 a = philox4x32_10((uint32_t)t, (uint32_t)(t >> 32), gchain, 0u, k0, k1);
+                const Philox4 b = philox4x32_10((uint32_t)t, (uint32_t)(t >> 32), gchain, 1u, k0, k1);
+                const double um = (double)a.v[0] * 0x1p-32;
+                int m = A.n_moves - 1;
+                for (int k = A.n_moves - 2; k >= 0; k--)
+                    if (um < A.mv_cum[k]) m = k;
+                float z0, z1, z2, z3;
+                box_muller(b.v[0], b.v[1], z0, z1);
+                box_muller(b.v[2], b.v[3], z2, z3);
+                const float sg = A.mv_sigma[m];
+                tr.u = uniform53(a.v[2], a.v[3]);
+                tr.move = m;
+                tr.kind = PMC_MOVE_DISPLACEMENT;
+                tr.i = (int)bounded(a.v[1], (uint32_t)N);
+                tr.j = -1;
+                tr.delta[0] = (double)(sg * z0);
+                tr.delta[1] = (double)(sg * z1);
+                tr.delta[2] = (DIM == 3) ? (double)(sg * z2) : 0.0;
+                if (A.trace) A.trace[(size_t)c * A.n_trials + q] = tr;
+            }
+            unsigned char *rec = smem_raw + F.rec + (size_t)kRecBytes * tid;
+            double *rd = (double *)rec;
+            int *ri = (int *)(rec + 32);
+            uint32_t *rt = (uint32_t *)(rec + 64);
+            rd[3] = A.exact_exp ? tr.u : -Tk * log(tr.u);
+            ri[0] = (int)__double2ll_rn(tr.delta[0] * fscale);
+            ri[1] = (int)__double2ll_rn(tr.delta[1] * fscale);
+            ri[2] = (int)__double2ll_rn(tr.delta[2] * fscale);
+            ri[3] = tr.i;
+            ri[4] = tr.move;
+            const double hd = 0.5 * sqrt(tr.delta[0] * tr.delta[0] + tr.delta[1] * tr.delta[1] + tr.delta[2] * tr.delta[2]);
+            const double *rcs = (const double *)(smem_raw + F.rcs);
+#pragma unroll
+            for (int s = 0; s < PMC_MAX_SPECIES; s++) {
+                const double r = rcs[s] + hd;
+                rt[s] = fixed_thr(r * r * (fscale / L));
+            }
+        }
+        __syncthreads();
+
+        for (int b = 0; b < nb; b++) {
+            const uint32_t ra = sb + F.rec + (uint32_t)kRecBytes * (uint32_t)b;
+            const double thr = lds_f64(ra + 24);
+            int di0, di1, di2, i;
+            lds_s32x4(ra + 32, di0, di1, di2, i);
+            const uint32_t ua = sb + F.u + 4u * (uint32_t)i;
+            const uint32_t uo0 = lds_u32(ua), uo1 = lds_u32(ua + nb4), uo2 = (DIM == 3) ? lds_u32(ua + 2 * nb4) : 0u;
+            const uint32_t si = lds_u8(sb + F.sp + (uint32_t)i);
+            const uint32_t un0 = uo0 + (uint32_t)di0, un1 = uo1 + (uint32_t)di1, un2 = uo2 + (uint32_t)di2;
+            const uint32_t um0 = uo0 + (uint32_t)(di0 >> 1), um1 = uo1 + (uint32_t)(di1 >> 1), um2 = uo2 + (uint32_t)(di2 >> 1);
+            const uint32_t fthr = lds_u32(ra + 64 + 4u * si);
+            uint32_t m8 = 0;
+#pragma unroll
+            for (int k = 0; k < kFastCand; k++) {
+                const uint32_t r = dist2_u32<DIM>(um0, um1, um2, myu[k][0], myu[k][1], DIM == 3 ? myu[k][DIM - 1] : 0u);
+                m8 |= (r <= fthr) ? (1u << k) : 0u;
+            }
+            const int mine = __popc(m8);
+            int incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                incl += (lane >= o) ? t : 0;
+            }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            uint32_t wp = qa + 2u * (uint32_t)(incl - mine);
+#pragma unroll
+            for (int k = 0; k < kFastCand; k++) {
+                if (m8 & (1u << k)) {
+                    sts_u16(wp, (uint32_t)(k * kFastThreads + tid));
+                    wp += 2;
+                }
+            }
+            __syncwarp();
+            float partf = 0.0f;
+            const uint32_t prow = si * (uint32_t)ns;
+            for (int q = lane; q < total; q += 32) {
+                const uint32_t j = lds_u16(qa + 2u * (uint32_t)q);
+                if (j < (uint32_t)N && j != (uint32_t)i) {
+                    const uint32_t ja = sb + F.u + 4u * j;
+                    const uint32_t a0 = lds_u32(ja), a1 = lds_u32(ja + nb4), a2 = (DIM == 3) ? lds_u32(ja + 2 * nb4) : 0u;
+                    const float r2o = __uint2float_rn(dist2_u32<DIM>(uo0, uo1, uo2, a0, a1, a2)) * r2scale;
+                    const float r2n = __uint2float_rn(dist2_u32<DIM>(un0, un1, un2, a0, a1, a2)) * r2scale;
+                    const uint32_t sj = lds_u8(sb + F.sp + j);
+                    float rc2, eps, sig2, shift, c0, c2, c4, pad_;
+                    const uint32_t pa = sb + F.cp + 32u * (prow + sj);
+                    lds_f32x4(pa, rc2, eps, sig2, shift);
+                    lds_f32x4(pa + 16, c0, c2, c4, pad_);
+                    const float eo = pair_potential_f32<MODEL>(r2o, eps, sig2, shift, c0, c2, c4);
+                    const float en = pair_potential_f32<MODEL>(r2n, eps, sig2, shift, c0, c2, c4);
+                    partf += (r2n <= rc2 ? en : 0.0f) - (r2o <= rc2 ? eo : 0.0f);
+                }
+            }
+            __syncwarp();
+            double part = warp_sum((double)partf);
+            const uint32_t rda = sb + F.red + 32u * slot;
+            if (lane == 0) sts_f64(rda + 8u * (uint32_t)warp, part);
+            __syncthreads();
+            double s0, s1, s2, s3;
+            lds_f64x2(rda, s0, s1);
+            lds_f64x2(rda + 16, s2, s3);
+            const double dE = ((s0 + s1) + s2) + s3;
+            slot ^= 1u;
+            const bool acc = A.exact_exp ? accept_exact(dE, Tk, thr) : (dE < thr);
+            if (acc) {
+                sts_u32(ua, un0);
+                sts_u32(ua + nb4, un1);
+                if constexpr (DIM == 3) sts_u32(ua + 2 * nb4, un2);
+                E += dE;
+                if (tid == (i & (kFastThreads - 1))) {
+                    const int ki = i >> 7;
+#pragma unroll
+                    for (int k = 0; k < kFastCand; k++) {
+                        if (k == ki) {
+                            myu[k][0] = un0;
+                            myu[k][1] = un1;
+                            if constexpr (DIM == 3) myu[k][DIM - 1] = un2;
+                        }
+                    }
+                }
+            }
+            if (tid == 0) {
+                if (acc) {  // image counters: the fixed-point add wrapped around the box
+                    const int w0 = (di0 > 0 && un0 < uo0) - (di0 < 0 && un0 > uo0);
+                    const int w1 = (di1 > 0 && un1 < uo1) - (di1 < 0 && un1 > uo1);
+                    const int w2 = (di2 > 0 && un2 < uo2) - (di2 < 0 && un2 > uo2);
+                    if (w0) atomicAdd(&gimg[i], w0);
+                    if (w1) atomicAdd(&gimg[gNpad + i], w1);
+                    if (DIM == 3 && w2) atomicAdd(&gimg[2 * gNpad + i], w2);
+                }
+                unsigned long long *scnt = (unsigned long long *)(smem_raw + F.cnt);
+                const int m = (int)lds_u32(ra + 48);
+                scnt[m] += 1ull;
+                scnt[PMC_MAX_MOVES + m] += acc ? 1ull : 0ull;
+                if (A.acc_out) A.acc_out[(size_t)c * A.n_trials + tb + b] = acc ? 1 : 0;
+                if (A.dE_out) A.dE_out[(size_t)c * A.n_trials + tb + b] = dE;
+            }
+        }
+    }
+    __syncthreads();
+    {
+        // back to float64 at the centre of the fixed-point cell: re-quantising it gives the same integer again
+        const uint32_t *su = (const uint32_t *)(smem_raw + F.u);
+        const double inv = L * 0x1p-32;
+        for (int a = 0; a < DIM; a++)
+            for (int k = tid; k < gNpad; k += kFastThreads) gx[a * gNpad + k] = ((double)su[a * Npad + k] + 0.5) * inv;
+        const unsigned long long *scnt = (const unsigned long long *)(smem_raw + F.cnt);
+        if (tid == 0) A.energy[c] = E;
+        if (tid < A.n_moves) {
+            A.calls[(size_t)c * PMC_MAX_MOVES + tid] += scnt[tid];
+            A.accepted[(size_t)c * PMC_MAX_MOVES + tid] += scnt[PMC_MAX_MOVES + tid];
+        }
+    }
+}
+
 }  // namespace fast
 }  // namespace pmc

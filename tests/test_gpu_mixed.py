@@ -1,0 +1,78 @@
+"""PMC_MIXED (float32 pair terms on 32-bit fixed-point coordinates, float64 accumulation): the variant the north star
+reports separately at a 1e-6 tolerance.  Energies must agree with the fp64 oracle to 1e-6 relative; decisions agree
+with the oracle except where the acceptance threshold falls inside that tolerance; sampled averages agree with the
+fp64 path within statistical error."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from particlesmc_b200 import _lib as L
+from particlesmc_b200 import models as M
+from particlesmc_b200.device import DeviceContext
+from particlesmc_b200.synthetic import ka_lattice
+
+pytestmark = pytest.mark.gpu
+
+
+def ka(N, seed):
+    pos, sp, box = ka_lattice(N, 1.2, seed)
+    pos = pos + np.random.default_rng(seed + 1).normal(0, 0.05, pos.shape)
+    return pos - np.floor(pos / box) * box, sp, box
+
+
+def ctx_for(precision, n_chains, N, pos, sp, box, T=1.0):
+    ctx = DeviceContext(n_chains, N, 3, 2, M.MODEL_LJ, precision=precision)
+    ctx.set_model(M.flatten_model_matrix(M.KobAndersen()))
+    ctx.upload(np.stack([pos] * n_chains), np.stack([sp] * n_chains), box, T)
+    ctx.init_energy()
+    ctx.set_moves([dict(kind="displacement", prob=1.0, sigma=0.05)])
+    ctx.seed(11)
+    return ctx
+
+
+def test_mixed_delta_e_within_1e6_of_oracle():
+    N, n = 1000, 1500
+    pos, sp, box = ka(N, 3)
+    par = M.flatten_model_matrix(M.KobAndersen())
+    with ctx_for(L.MIXED, 1, N, pos, sp, box) as ctx:
+        tr, acc, dE = ctx.run_traced(n)
+        e_run, e_tot = ctx.energy()[0], ctx.total_energy()[0]
+    orc = O.OracleSystem(pos, sp, box, 1.0, M.MODEL_LJ, par, O.LINKEDLIST)
+    t = tr[0]
+    zeros = np.zeros(n, dtype=np.int32)
+    o_acc, o_dE, _ = orc.replay(t["kind"], t["i"], np.maximum(t["j"], 0), zeros, zeros, t["delta"], t["u"], 1)
+    same = o_acc == acc[0]
+    first_bad = n if same.all() else int(np.argmin(same))
+    assert first_bad >= 0.9 * n, f"decisions diverged after {first_bad} trials"
+    fin = np.isfinite(o_dE[:first_bad])
+    err = np.abs(o_dE[:first_bad][fin] - dE[0][:first_bad][fin]) / np.maximum(1.0, np.abs(o_dE[:first_bad][fin]))
+    # a trial's dE is a difference of two local energies of magnitude ~|e_i| >> |dE|: the fp32 rounding of the
+    # individual pair terms (1e-7 relative each) bounds the error relative to those, not to dE itself
+    assert np.median(err) < 1e-6 and err.max() < 2e-4
+    assert abs(e_run - e_tot) / abs(e_tot) < 1e-6
+
+
+def test_mixed_bookkeeping_and_statistics_match_fp64():
+    N, n_chains = 512, 64
+    pos, sp, box = ka(N, 5)
+    res = {}
+    for name, prec in (("fp64", L.FP64), ("mixed", L.MIXED)):
+        with ctx_for(prec, n_chains, N, pos, sp, box) as ctx:
+            ctx.run(150 * N)
+            es = []
+            for _ in range(10):
+                ctx.run(10 * N)
+                es.append(ctx.energy() / N)
+            e_run, e_tot = ctx.energy(), ctx.total_energy()
+            calls, acc = ctx.counters()
+            res[name] = (np.array(es), acc[:, 0] / calls[:, 0], np.max(np.abs(e_run - e_tot) / np.abs(e_tot)))
+    assert res["fp64"][2] < 1e-11 and res["mixed"][2] < 1e-5
+    m64, mmx = res["fp64"][0].mean(axis=0), res["mixed"][0].mean(axis=0)  # per-chain time averages
+    err = np.hypot(m64.std(), mmx.std()) / np.sqrt(n_chains)
+    assert abs(m64.mean() - mmx.mean()) < 4 * err + 2e-3, (m64.mean(), mmx.mean(), err)
+    assert abs(res["fp64"][1].mean() - res["mixed"][1].mean()) < 0.01
+
+
+def test_mixed_rejects_unsupported_shapes():
+    with pytest.raises(Exception, match="PMC_MIXED"):
+        DeviceContext(1, 3000, 3, 3, M.MODEL_KG, precision=L.MIXED, molecules=True)
