@@ -294,16 +294,18 @@ int sweep(pmc_ctx *c, int64_t n_trials, const pmc_trial *d_replay, pmc_trial *d_
     a.exact_exp = exact_exp ? 1 : 0;
     CU(cudaEventRecord(c->ev0, c->stream));
     const bool filter = c->cubic && c->cfg.prefilter >= 0 && c->sweep_smem_filter > c->sweep_smem;
-    const bool fastk = filter && !any_swap && !c->cfg.molecules && pmc::chain_fast_supported(c->Npad, c->threads);
+    bool flips = false;  // MoleculeFlip stays in the general kernel (molecules are excluded here anyway)
+    for (auto &m : c->pool) flips = flips || m.kind == PMC_MOVE_FLIP;
+    const bool fastk = filter && !flips && !c->cfg.molecules && pmc::chain_fast_supported(c->Npad, c->threads);
     if (c->cfg.precision == PMC_MIXED) {
-        if (!fastk)
+        if (!fastk || any_swap)
             return fail(PMC_ERR_UNSUPPORTED, "PMC_MIXED needs a cubic box, a Displacement-only pool and %d threads per CTA", 128);
         CU(pmc::launch_chain_sweep_mixed(c->cfg.dim, c->cfg.model_kind, c->cfg.n_chains,
                                          pmc::chain_mixed_smem_bytes(c->cfg.dim, c->Npad), a, c->stream));
     } else if (fastk) {
-        const size_t fs = pmc::chain_fast_smem_bytes(c->cfg.dim, c->Npad, c->cfg.n_species);
+        const size_t fs = pmc::chain_fast_smem_bytes(c->cfg.dim, c->Npad, c->cfg.n_species, any_swap);
         if (fs != c->fast_smem) {
-            CU(pmc::configure_chain_fast(c->cfg.dim, c->cfg.model_kind, c->Npad, fs));
+            CU(pmc::configure_chain_fast(c->cfg.dim, c->cfg.model_kind, c->Npad, any_swap, fs));
             c->fast_smem = fs;
         }
         CU(pmc::launch_chain_sweep_fast(c->cfg.dim, c->cfg.model_kind, c->cfg.n_chains, fs, a, c->stream));

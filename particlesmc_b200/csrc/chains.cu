@@ -704,19 +704,23 @@ bool chain_fast_supported(int Npad, int threads) {
 
 static int fast_npad(int Npad) { return Npad <= 256 ? 256 : (Npad <= 512 ? 512 : 1024); }
 
-size_t chain_fast_smem_bytes(int dim, int Npad, int) {
-    return fast::fast_layout(dim, fast_npad(Npad), PMC_MAX_SPECIES).total;
+size_t chain_fast_smem_bytes(int dim, int Npad, int, bool swaps) {
+    return fast::fast_layout(dim, fast_npad(Npad), PMC_MAX_SPECIES, swaps).total;
 }
 
 template <typename F>
-static cudaError_t fast_dispatch(int dim, int model, int Npad, F &&f) {
+static cudaError_t fast_dispatch(int dim, int model, int Npad, bool swaps, F &&f) {
     return dispatch(dim, model, false, [&](auto D, auto MDL, auto) {
         constexpr int d = decltype(D)::value, mdl = decltype(MDL)::value;
-        switch (fast_npad(Npad)) {
-        case 256: return f(fast::k_chain_sweep_fast<d, mdl, 256>);
-        case 512: return f(fast::k_chain_sweep_fast<d, mdl, 512>);
-        default: return f(fast::k_chain_sweep_fast<d, mdl, 1024>);
+        const int np = fast_npad(Npad);
+        if (swaps) {
+            if (np == 256) return f(fast::k_chain_sweep_fast<d, mdl, 256, true>);
+            if (np == 512) return f(fast::k_chain_sweep_fast<d, mdl, 512, true>);
+            return f(fast::k_chain_sweep_fast<d, mdl, 1024, true>);
         }
+        if (np == 256) return f(fast::k_chain_sweep_fast<d, mdl, 256, false>);
+        if (np == 512) return f(fast::k_chain_sweep_fast<d, mdl, 512, false>);
+        return f(fast::k_chain_sweep_fast<d, mdl, 1024, false>);
     });
 }
 
@@ -743,14 +747,14 @@ cudaError_t launch_chain_sweep_mixed(int dim, int model, int M, size_t smem, con
     });
 }
 
-cudaError_t configure_chain_fast(int dim, int model, int Npad, size_t smem) {
-    return fast_dispatch(dim, model, Npad, [&](auto kernel) {
+cudaError_t configure_chain_fast(int dim, int model, int Npad, bool swaps, size_t smem) {
+    return fast_dispatch(dim, model, Npad, swaps, [&](auto kernel) {
         return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     });
 }
 
 cudaError_t launch_chain_sweep_fast(int dim, int model, int M, size_t smem, const ChainArgs &a, cudaStream_t st) {
-    return fast_dispatch(dim, model, a.Npad, [&](auto kernel) {
+    return fast_dispatch(dim, model, a.Npad, a.any_swap != 0, [&](auto kernel) {
         kernel<<<M, fast::kFastThreads, smem, st>>>(a);
         return cudaGetLastError();
     });

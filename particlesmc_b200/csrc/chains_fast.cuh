@@ -63,9 +63,9 @@ __device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) {
 
 // Dynamic shared-memory layout (byte offsets from the base), all 16-byte aligned.
 struct FastLayout {
-    uint32_t x, sp, q, cp, rec, red, cnt, par, rcs, total;
+    uint32_t x, sp, q, cp, rec, red, cnt, par, rcs, spids, heads, spoff, total;
 };
-__host__ __device__ inline FastLayout fast_layout(int dim, int Npad, int ns) {
+__host__ __device__ inline FastLayout fast_layout(int dim, int Npad, int ns, bool swaps = false) {
     FastLayout f;
     uint32_t o = 0;
     auto take = [&](uint32_t bytes) {
@@ -82,6 +82,9 @@ __host__ __device__ inline FastLayout fast_layout(int dim, int Npad, int ns) {
     f.cnt = take(8u * 2 * PMC_MAX_MOVES);
     f.par = take(8u * ns * ns * PMC_NPAR);                 // full parameter table (non-LJ models)
     f.rcs = take(8u * PMC_MAX_SPECIES);                    // largest cutoff radius per species of the moved particle
+    f.spids = take(swaps ? 2u * (uint32_t)Npad : 0u);      // SpeciesList (src/utils.jl:31-49), DiscreteSwap only
+    f.heads = take(swaps ? 2u * (uint32_t)Npad : 0u);
+    f.spoff = take(32u);                                   // species offsets [5] + fixed-point global cutoff [1]
     f.total = o;
     return f;
 }
@@ -102,7 +105,7 @@ __device__ __forceinline__ double mi_acc(double xi, double xj, double L, double 
 
 // NPAD (compile time): padded particle count of the shared-memory planes, one of 256 / 512 / 1024; makes every
 // shared-memory offset a constant and fixes the number of register-resident candidates per thread.
-template <int DIM, int MODEL, int NPAD>
+template <int DIM, int MODEL, int NPAD, bool SWAPS>
 __global__ void __launch_bounds__(kFastThreads, 6) k_chain_sweep_fast(const __grid_constant__ ChainArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int kFastCand = NPAD / kFastThreads;
@@ -110,7 +113,7 @@ __global__ void __launch_bounds__(kFastThreads, 6) k_chain_sweep_fast(const __gr
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int c = blockIdx.x;
     const int N = A.N, gNpad = A.Npad, ns = A.ns;  // gNpad: stride of the GLOBAL arrays (multiple of 32)
-    const FastLayout F = fast_layout(DIM, Npad, PMC_MAX_SPECIES);
+    const FastLayout F = fast_layout(DIM, Npad, PMC_MAX_SPECIES, SWAPS);
     const uint32_t sb = (uint32_t)__cvta_generic_to_shared(smem_raw);
     const uint32_t nb8 = 8u * (uint32_t)Npad;  // byte stride between coordinate planes
 
@@ -135,6 +138,21 @@ __global__ void __launch_bounds__(kFastThreads, 6) k_chain_sweep_fast(const __gr
         }
         unsigned long long *scnt = (unsigned long long *)(smem_raw + F.cnt);
         if (tid < 2 * PMC_MAX_MOVES) scnt[tid] = 0ull;
+        int *sso = (int *)(smem_raw + F.spoff);
+        if (tid <= PMC_MAX_SPECIES) sso[tid] = A.spoff[c * (PMC_MAX_SPECIES + 1) + tid];
+        if (tid == 0) {  // conservative fixed-point cutoff over all species pairs (swap filter)
+            double rc2 = 0.0;
+            for (int k = 0; k < ns * ns; k++) rc2 = fmax(rc2, A.par[k * PMC_NPAR + PMC_P_RCUT2]);
+            ((uint32_t *)sso)[PMC_MAX_SPECIES + 1] = fixed_thr(rc2 * (fscale / L));
+        }
+        if constexpr (SWAPS) {
+            uint16_t *si_ = (uint16_t *)(smem_raw + F.spids), *sh_ = (uint16_t *)(smem_raw + F.heads);
+            const uint16_t *gi = A.spids + (size_t)c * gNpad, *gh = A.heads + (size_t)c * gNpad;
+            for (int k = tid; k < Npad; k += kFastThreads) {
+                si_[k] = k < gNpad ? gi[k] : 0;
+                sh_[k] = k < gNpad ? gh[k] : 0;
+            }
+        }
     }
     // fixed-point coordinates of this thread's candidates j = k * 128 + tid, k = 0..7 (registers)
     uint32_t myu[kFastCand][DIM];
@@ -174,21 +192,30 @@ __global__ void __launch_bounds__(kFastThreads, 6) k_chain_sweep_fast(const __gr
                 int m = A.n_moves - 1;
                 for (int k = A.n_moves - 2; k >= 0; k--)
                     if (um < A.mv_cum[k]) m = k;
-                float z0, z1, z2, z3;
-                box_muller(b.v[0], b.v[1], z0, z1);
-                box_muller(b.v[2], b.v[3], z2, z3);
-                const float sg = A.mv_sigma[m];
                 tr.u = uniform53(a.v[2], a.v[3]);
                 tr.move = m;
-                tr.kind = PMC_MOVE_DISPLACEMENT;
-                tr.i = (int)bounded(a.v[1], (uint32_t)N);
-                tr.j = -1;
-                tr.delta[0] = (double)(sg * z0);
-                tr.delta[1] = (double)(sg * z1);
-                tr.delta[2] = (DIM == 3) ? (double)(sg * z2) : 0.0;
+                tr.kind = A.mv_kind[m];
+                if (!SWAPS || tr.kind == PMC_MOVE_DISPLACEMENT) {
+                    float z0, z1, z2, z3;
+                    box_muller(b.v[0], b.v[1], z0, z1);
+                    box_muller(b.v[2], b.v[3], z2, z3);
+                    const float sg = A.mv_sigma[m];
+                    tr.kind = PMC_MOVE_DISPLACEMENT;
+                    tr.i = (int)bounded(a.v[1], (uint32_t)N);
+                    tr.j = -1;
+                    tr.delta[0] = (double)(sg * z0);
+                    tr.delta[1] = (double)(sg * z1);
+                    tr.delta[2] = (DIM == 3) ? (double)(sg * z2) : 0.0;
+                } else {  // slots in the species lists; resolved to particles when the trial executes
+                    const int *sso = (const int *)(smem_raw + F.spoff);
+                    const int nA = sso[A.mv_a[m] + 1] - sso[A.mv_a[m]], nB = sso[A.mv_b[m] + 1] - sso[A.mv_b[m]];
+                    tr.i = (nA > 0 && nB > 0) ? (int)bounded(a.v[1], (uint32_t)nA) : -1;
+                    tr.j = (nA > 0 && nB > 0) ? (int)bounded(b.v[0], (uint32_t)nB) : -1;
+                    tr.delta[0] = tr.delta[1] = tr.delta[2] = 0.0;
+                }
                 if (A.trace) A.trace[(size_t)c * A.n_trials + q] = tr;
             }
-            // record layout: f64 delta[3], f64 thr | s32 dint[3], s32 i | s32 m, pad[3] | u32 thr_t[4]
+            // record layout: f64 delta[3], f64 thr | s32 dint[3], s32 i | s32 m, kind, j, pool species | u32 thr_t[4]
             unsigned char *rec = smem_raw + F.rec + (size_t)kRecBytes * tid;
             double *rd = (double *)rec;
             int *ri = (int *)(rec + 32);
@@ -202,6 +229,9 @@ __global__ void __launch_bounds__(kFastThreads, 6) k_chain_sweep_fast(const __gr
             ri[2] = (int)__double2ll_rn(tr.delta[2] * fscale);
             ri[3] = tr.i;
             ri[4] = tr.move;
+            ri[5] = tr.kind;
+            ri[6] = tr.j;
+            ri[7] = (tr.kind == PMC_MOVE_SWAP && !A.replay) ? (A.mv_a[tr.move] | (A.mv_b[tr.move] << 8)) : 0;
             // one sphere around the midpoint of old and new position covers both cutoff spheres
             const double hd = 0.5 * sqrt(tr.delta[0] * tr.delta[0] + tr.delta[1] * tr.delta[1] + tr.delta[2] * tr.delta[2]);
             const double *rcs = (const double *)(smem_raw + F.rcs);
@@ -221,6 +251,131 @@ __global__ void __launch_bounds__(kFastThreads, 6) k_chain_sweep_fast(const __gr
             lds_f64x2(ra, d0, d1);
             lds_f64x2(ra + 16, d2, thr);
             lds_s32x4(ra + 32, di0, di1, di2, i);
+            if constexpr (SWAPS) {
+                int mv, kind, j, sab;
+                lds_s32x4(ra + 48, mv, kind, j, sab);
+                if (kind == PMC_MOVE_SWAP) {
+                    // ---- DiscreteSwap: positions fixed, four local energies in one pass (src/moves.jl:159-167) ----
+                    const uint32_t soa = sb + F.spoff;
+                    if (!A.replay && i >= 0) {  // slots -> particles through the species lists
+                        const uint32_t oa = lds_u32(soa + 4u * (uint32_t)(sab & 0xFF)), ob = lds_u32(soa + 4u * (uint32_t)(sab >> 8));
+                        i = (int)lds_u16(sb + F.spids + 2u * (oa + (uint32_t)i));
+                        j = (int)lds_u16(sb + F.spids + 2u * (ob + (uint32_t)j));
+                    }
+                    const bool valid = i >= 0 && j >= 0;
+                    const uint32_t iu = valid ? (uint32_t)i : 0u, ju = valid ? (uint32_t)j : 0u;
+                    const uint32_t xia = sb + F.x + 8u * iu, xja = sb + F.x + 8u * ju;
+                    const double xi0 = lds_f64(xia), xi1 = lds_f64(xia + nb8), xi2 = DIM == 3 ? lds_f64(xia + 2 * nb8) : 0.0;
+                    const double xj0 = lds_f64(xja), xj1 = lds_f64(xja + nb8), xj2 = DIM == 3 ? lds_f64(xja + 2 * nb8) : 0.0;
+                    const uint32_t si = lds_u8(sb + F.sp + iu), sj = lds_u8(sb + F.sp + ju);
+                    // list slots are read BEFORE the barrier: the commit below overwrites them (read-modify-write)
+                    const uint32_t hi = lds_u16(sb + F.heads + 2u * iu), hj = lds_u16(sb + F.heads + 2u * ju);
+                    const uint32_t oi = lds_u32(soa + 4u * si), oj = lds_u32(soa + 4u * sj);
+                    const uint32_t ui0 = to_fixed32(xi0, fscale), ui1 = to_fixed32(xi1, fscale), ui2 = DIM == 3 ? to_fixed32(xi2, fscale) : 0u;
+                    const uint32_t uj0 = to_fixed32(xj0, fscale), uj1 = to_fixed32(xj1, fscale), uj2 = DIM == 3 ? to_fixed32(xj2, fscale) : 0u;
+                    const uint32_t gthr = lds_u32(soa + 4u * (PMC_MAX_SPECIES + 1));
+                    uint32_t m8 = 0;
+                    if (valid) {
+#pragma unroll
+                        for (int k = 0; k < kFastCand; k++) {
+                            const uint32_t a2 = DIM == 3 ? myu[k][DIM - 1] : 0u;
+                            int d = (int)(ui0 - myu[k][0]), e = (int)(uj0 - myu[k][0]);
+                            uint32_t r1 = (uint32_t)__mulhi(d, d), r2 = (uint32_t)__mulhi(e, e);
+                            d = (int)(ui1 - myu[k][1]), e = (int)(uj1 - myu[k][1]);
+                            r1 += (uint32_t)__mulhi(d, d), r2 += (uint32_t)__mulhi(e, e);
+                            if constexpr (DIM == 3) {
+                                d = (int)(ui2 - a2), e = (int)(uj2 - a2);
+                                r1 += (uint32_t)__mulhi(d, d), r2 += (uint32_t)__mulhi(e, e);
+                            }
+                            m8 |= (min(r1, r2) <= gthr) ? (1u << k) : 0u;
+                        }
+                    }
+                    const int mine = __popc(m8);
+                    int incl = mine;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                        incl += (lane >= o) ? t : 0;
+                    }
+                    const int total = __shfl_sync(0xffffffffu, incl, 31);
+                    uint32_t wp = qa + 2u * (uint32_t)(incl - mine);
+#pragma unroll
+                    for (int k = 0; k < kFastCand; k++) {
+                        if (m8 & (1u << k)) {
+                            sts_u16(wp, (uint32_t)(k * kFastThreads + tid));
+                            wp += 2;
+                        }
+                    }
+                    __syncwarp();
+                    double part = 0.0;
+                    auto pair_e = [&](uint32_t sa, uint32_t sb_, double r2) -> double {
+                        if constexpr (MODEL == PMC_MODEL_LJ || MODEL == PMC_MODEL_KG) {
+                            double rc2, eps4, sig2, shift;
+                            const uint32_t pa = sb + F.cp + 32u * (sa * (uint32_t)ns + sb_);
+                            lds_f64x2(pa, rc2, eps4);
+                            lds_f64x2(pa + 16, sig2, shift);
+                            return r2 <= rc2 ? lj_core(r2, eps4, sig2) - shift : 0.0;
+                        } else {
+                            const double *p = (const double *)(smem_raw + F.par) + (sa * (uint32_t)ns + sb_) * PMC_NPAR;
+                            return r2 <= p[PMC_P_RCUT2] ? pair_potential<MODEL>(p, r2) : 0.0;
+                        }
+                    };
+                    for (int q = lane; q < total; q += 32) {
+                        const uint32_t k = lds_u16(qa + 2u * (uint32_t)q);
+                        if (k < (uint32_t)N) {
+                            const uint32_t ka = sb + F.x + 8u * k;
+                            const double xk0 = lds_f64(ka), xk1 = lds_f64(ka + nb8), xk2 = DIM == 3 ? lds_f64(ka + 2 * nb8) : 0.0;
+                            const uint32_t sk = lds_u8(sb + F.sp + k);
+                            const uint32_t skn = k == iu ? sj : (k == ju ? si : sk);  // species of k after the exchange
+                            if (k != iu) {  // k-term of particle i's local energy: (si, sk) -> (sj, sk')
+                                double r2 = mi_acc(xi0, xk0, L, 0.0);
+                                r2 = mi_acc(xi1, xk1, L, r2);
+                                if constexpr (DIM == 3) r2 = mi_acc(xi2, xk2, L, r2);
+                                part += pair_e(sj, skn, r2) - pair_e(si, sk, r2);
+                            }
+                            if (k != ju) {  // k-term of particle j's local energy: (sj, sk) -> (si, sk')
+                                double r2 = mi_acc(xj0, xk0, L, 0.0);
+                                r2 = mi_acc(xj1, xk1, L, r2);
+                                if constexpr (DIM == 3) r2 = mi_acc(xj2, xk2, L, r2);
+                                part += pair_e(si, skn, r2) - pair_e(sj, sk, r2);
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    part = warp_sum(part);
+                    const uint32_t rda = sb + F.red + 32u * slot;
+                    if (lane == 0) sts_f64(rda + 8u * (uint32_t)warp, part);
+                    __syncthreads();
+                    double s0, s1, s2, s3;
+                    lds_f64x2(rda, s0, s1);
+                    lds_f64x2(rda + 16, s2, s3);
+                    const double dE = ((s0 + s1) + s2) + s3;
+                    slot ^= 1u;
+                    const bool acc = valid && (A.exact_exp ? accept_exact(dE, Tk, thr) : (dE < thr));
+                    if (acc) {  // every thread performs the identical stores (see the displacement commit)
+                        asm volatile("st.shared.u8 [%0], %1;" ::"r"(sb + F.sp + iu), "r"(sj) : "memory");
+                        asm volatile("st.shared.u8 [%0], %1;" ::"r"(sb + F.sp + ju), "r"(si) : "memory");
+                        sts_u16(sb + F.spids + 2u * (oi + hi), ju);  // update_species_list! (src/moves.jl:175-179)
+                        sts_u16(sb + F.spids + 2u * (oj + hj), iu);
+                        sts_u16(sb + F.heads + 2u * iu, hj);
+                        sts_u16(sb + F.heads + 2u * ju, hi);
+                        E += dE;
+                    }
+                    if (tid == 0) {
+                        unsigned long long *scnt = (unsigned long long *)(smem_raw + F.cnt);
+                        scnt[mv] += 1ull;
+                        scnt[PMC_MAX_MOVES + mv] += acc ? 1ull : 0ull;
+                        if (A.acc_out) A.acc_out[(size_t)c * A.n_trials + tb + b] = acc ? 1 : 0;
+                        if (A.dE_out) A.dE_out[(size_t)c * A.n_trials + tb + b] = dE;
+                        if (A.trace) {
+                            pmc_trial *tr = A.trace + (size_t)c * A.n_trials + tb + b;
+                            tr->i = i;
+                            tr->j = j;
+                        }
+                    }
+                    continue;
+                }
+            }
             const uint32_t xa = sb + F.x + 8u * (uint32_t)i;
             double xo[3], xn[3];
             xo[0] = lds_f64(xa);
@@ -356,6 +511,16 @@ __global__ void __launch_bounds__(kFastThreads, 6) k_chain_sweep_fast(const __gr
         const double *sx = (const double *)(smem_raw + F.x);
         for (int a = 0; a < DIM; a++)
             for (int k = tid; k < gNpad; k += kFastThreads) gx[a * gNpad + k] = sx[a * Npad + k];
+        if constexpr (SWAPS) {
+            uint8_t *gsp = A.sp + (size_t)c * gNpad;
+            uint16_t *gi = A.spids + (size_t)c * gNpad, *gh = A.heads + (size_t)c * gNpad;
+            const uint16_t *si_ = (const uint16_t *)(smem_raw + F.spids), *sh_ = (const uint16_t *)(smem_raw + F.heads);
+            for (int k = tid; k < gNpad; k += kFastThreads) {
+                gsp[k] = smem_raw[F.sp + k];
+                gi[k] = si_[k];
+                gh[k] = sh_[k];
+            }
+        }
         const unsigned long long *scnt = (const unsigned long long *)(smem_raw + F.cnt);
         if (tid == 0) A.energy[c] = E;
         if (tid < A.n_moves) {
