@@ -14,10 +14,10 @@ ROOT = os.path.dirname(_HERE)
 CSRC = os.path.join(_HERE, "csrc")
 LIB_DIR = os.path.join(_HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libpmc_b200.so")
-SOURCES = ["api.cu", "chains.cu", "box.cu"]
+SOURCES = ["api.cu", "chains.cu", "chains_fast.cu", "box.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared", "-ccbin", "/usr/bin/g++",
+    "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++",
 ]
 
 
@@ -38,15 +38,32 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= _newest_source_mtime():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [find_nvcc(), *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", LIB_PATH,
-           *[os.path.join(CSRC, s) for s in SOURCES]]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr)
+    obj_dir = os.path.join(_HERE, "build")
+    os.makedirs(obj_dir, exist_ok=True)
+    nvcc = find_nvcc()
+    inc = ["-I", os.path.join(ROOT, "include"), "-I", CSRC]
+
+    def compile_one(src: str):
+        obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
+        cmd = [nvcc, *NVCC_FLAGS, *inc, "-c", os.path.join(CSRC, src), "-o", obj]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        return src, obj, res
+
+    # the translation units are independent: compile them concurrently, then link
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
+        results = list(pool.map(compile_one, SOURCES))
+    for src, _, res in results:
+        if res.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n" + res.stdout + res.stderr)
+        if verbose:
+            print(res.stderr)
+    link = subprocess.run([nvcc, "-shared", "-ccbin", "/usr/bin/g++", "-o", LIB_PATH, *[o for _, o, _ in results]],
+                          capture_output=True, text=True)
+    if link.returncode != 0:
+        raise RuntimeError("link failed:\n" + link.stdout + link.stderr)
     return LIB_PATH
 
 

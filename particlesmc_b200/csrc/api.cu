@@ -296,7 +296,7 @@ int sweep(pmc_ctx *c, int64_t n_trials, const pmc_trial *d_replay, pmc_trial *d_
     const bool filter = c->cubic && c->cfg.prefilter >= 0 && c->sweep_smem_filter > c->sweep_smem;
     bool flips = false;  // MoleculeFlip stays in the general kernel (molecules are excluded here anyway)
     for (auto &m : c->pool) flips = flips || m.kind == PMC_MOVE_FLIP;
-    const bool fastk = filter && !flips && !c->cfg.molecules && pmc::chain_fast_supported(c->Npad, c->threads);
+    const bool fastk = filter && !flips && !c->cfg.molecules && pmc::chain_fast_supported(c->cfg.dim, c->Npad, c->threads);
     if (c->cfg.precision == PMC_MIXED) {
         if (!fastk || any_swap)
             return fail(PMC_ERR_UNSUPPORTED, "PMC_MIXED needs a cubic box, a Displacement-only pool and %d threads per CTA", 128);

@@ -103,7 +103,7 @@ __device__ __forceinline__ double mi_acc(double xi, double xj, double L, double 
     return fma(r, r, acc);
 }
 
-// NPAD (compile time): padded particle count of the shared-memory planes, one of 256 / 512 / 1024; makes every
+// NPAD (compile time): padded particle count of the shared-memory planes, one of 256 / 512 / 1024 (/ 2048 in 2-D); makes every
 // shared-memory offset a constant and fixes the number of register-resident candidates per thread.
 template <int DIM, int MODEL, int NPAD, bool SWAPS>
 __global__ void __launch_bounds__(kFastThreads, 6) k_chain_sweep_fast(const __grid_constant__ ChainArgs A) {
