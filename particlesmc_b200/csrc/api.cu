@@ -353,7 +353,9 @@ int pmc_create(const pmc_config *cfg, pmc_ctx **out) {
     pmc_ctx *c = new pmc_ctx();
     c->cfg = *cfg;
     c->Npad = (cfg->n_particles + 31) / 32 * 32;
-    c->threads = cfg->threads > 0 ? cfg->threads : 128;
+    // default CTA size: 128 threads while a chain fits the register-resident kernels (several CTAs per SM), 256 for
+    // large chains whose shared-memory footprint allows only one or two CTAs per SM
+    c->threads = cfg->threads > 0 ? cfg->threads : (c->Npad > (cfg->dim == 2 ? 2048 : 1024) ? 256 : 128);
     if (c->threads % 32 != 0 || c->threads > 256) {
         delete c;
         return fail(PMC_ERR_INVALID, "threads must be a multiple of 32, at most 256");
