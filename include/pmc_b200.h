@@ -164,6 +164,12 @@ int pmc_total_energy(pmc_ctx *ctx, double *energy /*[n_chains]*/);
 /* compute_energy_particle(system, i) for all i of one chain (src/atoms.jl:81-88, molecules.jl:206-215). */
 int pmc_local_energy(pmc_ctx *ctx, int32_t chain, double *e /*[N]*/);
 int pmc_download(pmc_ctx *ctx, int32_t first, int32_t count, double *position, int64_t *species);
+/* Pair-distance histogram of the current configurations (the raw counts behind g(r)): unordered
+ * pairs (i < j) with species (a, b) in either order (label 0 = any species), minimum-image distance < rmax,
+ * nbins equal bins on [0, rmax), summed over all chains of this context.  rmax must not exceed half the box
+ * (PMC_MODE_BOX: the cell side).  Multi-GPU: sum the histograms of the ranks (an all-reduce of nbins integers). */
+int pmc_pair_histogram(pmc_ctx *ctx, int32_t species_a, int32_t species_b, double rmax, int32_t nbins,
+                       uint64_t *hist /*[nbins]*/);
 /* Move.total_calls / accepted_calls per chain and pool entry: [n_chains][n_moves]. */
 int pmc_counters(pmc_ctx *ctx, int64_t *calls, int64_t *accepted);
 /* Number of kernel launches issued by this context so far (bench.py's gpu_launches). */

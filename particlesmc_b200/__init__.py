@@ -13,6 +13,7 @@ from .systems import (Atoms, CellList, EmptyList, LinkedList, Molecules, Neighbo
 from .simulation import (Metropolis, PrintTimeSteps, Simulation, StoreAcceptance, StoreCallbacks, StoreLastFrames,
                          StoreTrajectories, build_schedule, run)
 from .device import DeviceContext, measure_fma_peak
+from .observables import radial_distribution
 from ._lib import PMCError
 
 __all__ = [n for n in dir() if not n.startswith("_")]

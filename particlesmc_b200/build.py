@@ -38,7 +38,8 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= _newest_source_mtime():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
-    obj_dir = os.path.join(_HERE, "build")
+    import tempfile
+    obj_dir = os.path.join(tempfile.gettempdir(), "pmc_b200_build")  # objects stay out of the repo snapshot
     os.makedirs(obj_dir, exist_ok=True)
     nvcc = find_nvcc()
     inc = ["-I", os.path.join(ROOT, "include"), "-I", CSRC]

@@ -755,6 +755,43 @@ int pmc_download(pmc_ctx *c, int32_t first, int32_t count, double *position, int
     return PMC_OK;
 }
 
+int pmc_pair_histogram(pmc_ctx *c, int32_t sa, int32_t sb, double rmax, int32_t nbins, uint64_t *hist) {
+    if (!c || !hist) return fail(PMC_ERR_INVALID, "null argument");
+    if (!c->uploaded) return fail(PMC_ERR_STATE, "nothing uploaded yet");
+    if (nbins < 1 || nbins > 8192 || !(rmax > 0.0)) return fail(PMC_ERR_INVALID, "need 1 <= nbins <= 8192 and rmax > 0");
+    if (sa < 0 || sa > c->cfg.n_species || sb < 0 || sb > c->cfg.n_species) return fail(PMC_ERR_INVALID, "species labels must lie in 0..%d", c->cfg.n_species);
+    CU(cudaSetDevice(c->cfg.device));
+    unsigned long long *d_hist = nullptr;
+    CU(cudaMalloc((void **)&d_hist, sizeof(unsigned long long) * nbins));
+    cudaError_t e = cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * nbins, c->stream);
+    int rc = PMC_OK;
+    if (e == cudaSuccess) {
+        if (c->cfg.mode == PMC_MODE_BOX) {
+            rc = pmc::box_pair_histogram(c->boxst, sa - 1, sb - 1, rmax, nbins, d_hist);
+            c->launches += pmc::box_take_launches(c->boxst);
+        } else {
+            std::vector<double> hb((size_t)c->cfg.n_chains * 3);
+            e = cudaMemcpyAsync(hb.data(), c->box, sizeof(double) * hb.size(), cudaMemcpyDeviceToHost, c->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+            for (int k = 0; e == cudaSuccess && k < c->cfg.n_chains; k++)
+                for (int a = 0; a < c->cfg.dim; a++)
+                    if (rmax > 0.5 * hb[(size_t)k * 3 + a]) rc = PMC_ERR_INVALID;
+            if (rc == PMC_OK && e == cudaSuccess) {
+                e = pmc::launch_chain_pair_histogram(c->cfg.dim, c->cfg.n_chains, c->cfg.n_particles, c->Npad, c->x, c->sp, c->box,
+                                                     sa - 1, sb - 1, rmax, nbins, d_hist, c->stream);
+                c->launches++;
+            }
+        }
+    }
+    if (e == cudaSuccess && rc == PMC_OK) e = cudaMemcpyAsync(hist, d_hist, sizeof(unsigned long long) * nbins, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_hist);
+    if (rc == PMC_ERR_INVALID) return fail(rc, "rmax must not exceed half the box length (minimum image)");
+    if (rc) return fail(rc, "%s", pmc::box_error());
+    if (e != cudaSuccess) return fail(PMC_ERR_CUDA, "pair histogram: %s", cudaGetErrorString(e));
+    return PMC_OK;
+}
+
 int pmc_counters(pmc_ctx *c, int64_t *calls, int64_t *accepted) {
     if (!c || !calls || !accepted) return fail(PMC_ERR_INVALID, "null argument");
     CU(cudaSetDevice(c->cfg.device));

@@ -1025,6 +1025,57 @@ __global__ void k_peer_barrier(volatile uint32_t *local_flags, uint32_t *const *
     }
 }
 
+// ---- pair-distance histogram through the cell list (raw counts of g(r)); rmax <= cell side ------------------
+template <int DIM>
+__global__ void __launch_bounds__(kBoxThreads) k_box_pair_histogram(const __grid_constant__ BoxArgs A, int sa, int sb, double rmax,
+                                                                    int nbins, unsigned long long *hist) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ Stencil<DIM> st;
+    double *sr = (double *)smem_raw;
+    uint8_t *ssp = (uint8_t *)(sr + DIM * A.cap);
+    int *sid = (int *)(ssp + ((A.cap + 3) & ~3));
+    unsigned int *sh = (unsigned int *)(sid + A.cap);
+    const int tid = threadIdx.x;
+    for (int k = tid; k < nbins; k += kBoxThreads) sh[k] = 0u;
+    int cc[3] = {0, 0, 0};
+    {
+        int l = blockIdx.x;
+        if constexpr (DIM == 3) { cc[2] = l % A.g.nc[2]; l /= A.g.nc[2]; }
+        cc[1] = l % A.g.nc[1];
+        cc[0] = l / A.g.nc[1];
+    }
+    const int ncand = load_stencil<DIM, false>(A, cc, &st, sr, ssp);
+    if (ncand < 0) return;
+    // particle ids of the candidates (to count every unordered pair once: only id_i < id_j)
+    for (int s = 0; s < Stencil<DIM>::NST; s++) {
+        const int b = A.start[st.cell[s]], n = st.off[s + 1] - st.off[s];
+        for (int p = tid; p < n; p += kBoxThreads) sid[st.off[s] + p] = A.ids[b + p];
+    }
+    __syncthreads();
+    const int ncen = st.off[1];
+    const double inv_dr = (double)nbins / rmax, rmax2 = rmax * rmax;
+    for (int k = 0; k < ncen; k++) {
+        const double xi[3] = {sr[k], sr[A.cap + k], DIM == 3 ? sr[2 * A.cap + k] : 0.0};
+        const int si = ssp[k], idi = sid[k];
+        for (int j = tid; j < ncand; j += kBoxThreads) {
+            if (sid[j] <= idi) continue;
+            const int sj = ssp[j];
+            const bool match = (sa < 0 && sb < 0) || (sa < 0 && (si == sb || sj == sb)) || (sb < 0 && (si == sa || sj == sa)) ||
+                               (si == sa && sj == sb) || (si == sb && sj == sa);
+            if (!match) continue;
+            const double r2 = d2_frame<DIM>(sr, A.cap, j, xi);
+            if (r2 < rmax2) {
+                int bin = (int)(sqrt(r2) * inv_dr);
+                bin = bin < nbins ? bin : nbins - 1;
+                atomicAdd(&sh[bin], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    for (int k = tid; k < nbins; k += kBoxThreads)
+        if (sh[k]) atomicAdd(&hist[k], (unsigned long long)sh[k]);
+}
+
 // deterministic reduction of per-cell values: out[0] (+)= scale * sum(cellE), acc[0] += sum(cell_acc)
 __global__ void k_box_reduce(const double *__restrict__ cellE, const uint32_t *__restrict__ cell_acc, int n, double scale,
                              int accumulate, double *outE, unsigned long long *out_acc) {
@@ -1343,6 +1394,28 @@ int peer_barrier(BoxState *b) {
 const char *box_error() { return g_box_err.c_str(); }
 
 int box_check(BoxState *b) { return check_overflow(b); }
+
+int box_pair_histogram(BoxState *b, int sa, int sb, double rmax, int nbins, unsigned long long *d_hist) {
+    if (!b->geom_ready) return bfail(PMC_ERR_STATE, "nothing uploaded yet");
+    for (int a = 0; a < b->dim; a++)
+        if (rmax > b->g.cs[a]) return bfail(PMC_ERR_INVALID, "rmax %g exceeds the cell side %g of the device cell list", rmax, b->g.cs[a]);
+    for (int a = 0; a < 3; a++) b->g.shift[a] = 0.0;
+    int rc = build_cells(b);
+    if (rc) return rc;
+    BoxArgs A;
+    fill_args(b, A);
+    const size_t smem = b->smem + sizeof(int) * (size_t)b->cap + sizeof(unsigned int) * (size_t)nbins + 16;
+    if (b->dim == 3) {
+        BCU(cudaFuncSetAttribute(k_box_pair_histogram<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_box_pair_histogram<3><<<b->g.ncell, kBoxThreads, smem, b->stream>>>(A, sa, sb, rmax, nbins, d_hist);
+    } else {
+        BCU(cudaFuncSetAttribute(k_box_pair_histogram<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_box_pair_histogram<2><<<b->g.ncell, kBoxThreads, smem, b->stream>>>(A, sa, sb, rmax, nbins, d_hist);
+    }
+    BCU(cudaGetLastError());
+    b->launches++;
+    return check_overflow(b);
+}
 
 int box_peer_export(BoxState *b, unsigned char *handle64) {
     if (!b->geom_ready) return bfail(PMC_ERR_STATE, "pmc_upload must precede pmc_box_peer_export");

@@ -30,5 +30,6 @@ int64_t box_take_launches(BoxState *b);
 int box_peer_export(BoxState *b, unsigned char *handle64);
 int box_peer_attach(BoxState *b, int rank, int world, const unsigned char *handles);
 int box_check(BoxState *b);
+int box_pair_histogram(BoxState *b, int sa, int sb, double rmax, int nbins, unsigned long long *d_hist);
 
 }  // namespace pmc

@@ -631,6 +631,46 @@ __global__ void k_chain_energy(const __grid_constant__ EnergyArgs A) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Pair-distance histogram (raw counts of g(r)): one CTA per chain, positions in shared memory, all i < j,
+// per-CTA histogram in shared memory flushed with one atomicAdd per bin.  Integer counts: deterministic.
+// ------------------------------------------------------------------------------------------------
+template <int DIM>
+__global__ void k_chain_pair_histogram(const double *__restrict__ x, const uint8_t *__restrict__ sp,
+                                       const double *__restrict__ box, int N, int Npad, int sa, int sb, double rmax,
+                                       int nbins, unsigned long long *hist) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *sx = (double *)smem_raw;
+    unsigned int *sh = (unsigned int *)(sx + DIM * Npad);
+    uint8_t *ssp = (uint8_t *)(sh + nbins);
+    const int tid = threadIdx.x, NT = blockDim.x, c = blockIdx.x;
+    for (int k = tid; k < DIM * Npad; k += NT) sx[k] = x[(size_t)c * DIM * Npad + k];
+    for (int k = tid; k < Npad; k += NT) ssp[k] = sp[(size_t)c * Npad + k];
+    for (int k = tid; k < nbins; k += NT) sh[k] = 0u;
+    const double L[3] = {box[c * 3 + 0], box[c * 3 + 1], box[c * 3 + 2]};
+    const double inv_dr = (double)nbins / rmax, rmax2 = rmax * rmax;
+    __syncthreads();
+    for (int i = 0; i < N - 1; i++) {
+        const double xi[3] = {sx[i], sx[Npad + i], DIM == 3 ? sx[2 * Npad + i] : 0.0};
+        const int si = ssp[i];
+        for (int j = i + 1 + tid; j < N; j += NT) {
+            const int sj = ssp[j];
+            const bool match = (sa < 0 && sb < 0) || (sa < 0 && (si == sb || sj == sb)) || (sb < 0 && (si == sa || sj == sa)) ||
+                               (si == sa && sj == sb) || (si == sb && sj == sa);
+            if (!match) continue;
+            const double r2 = dist2<DIM>(sx, Npad, j, xi, L);
+            if (r2 < rmax2) {
+                int bin = (int)(sqrt(r2) * inv_dr);
+                bin = bin < nbins ? bin : nbins - 1;
+                atomicAdd(&sh[bin], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    for (int k = tid; k < nbins; k += NT)
+        if (sh[k]) atomicAdd(&hist[k], (unsigned long long)sh[k]);
+}
+
 template <typename F>
 cudaError_t dispatch(int dim, int model, bool mol, F &&f) {
 #define PMC_CASE(D, MDL, ML) \
@@ -695,6 +735,23 @@ cudaError_t launch_chain_sweep(int dim, int model, bool mol, bool filter, int M,
         }
         return cudaGetLastError();
     });
+}
+
+cudaError_t launch_chain_pair_histogram(int dim, int M, int N, int Npad, const double *x, const uint8_t *sp,
+                                        const double *box, int sa, int sb, double rmax, int nbins,
+                                        unsigned long long *hist, cudaStream_t st) {
+    const size_t smem = sizeof(double) * (size_t)dim * Npad + sizeof(unsigned int) * nbins + Npad + 16;
+    cudaError_t e;
+    if (dim == 3) {
+        e = cudaFuncSetAttribute(k_chain_pair_histogram<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        k_chain_pair_histogram<3><<<M, 256, smem, st>>>(x, sp, box, N, Npad, sa, sb, rmax, nbins, hist);
+    } else {
+        e = cudaFuncSetAttribute(k_chain_pair_histogram<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        k_chain_pair_histogram<2><<<M, 256, smem, st>>>(x, sp, box, N, Npad, sa, sb, rmax, nbins, hist);
+    }
+    return cudaGetLastError();
 }
 
 cudaError_t launch_chain_energy(int dim, int model, bool mol, int M, size_t smem, const EnergyArgs &a,

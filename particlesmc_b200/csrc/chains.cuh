@@ -62,6 +62,10 @@ struct EnergyArgs {
     int32_t N, Npad, ns;
 };
 
+// pair-distance histogram of every chain (observable behind g(r)); hist is [nbins] u64, accumulated
+cudaError_t launch_chain_pair_histogram(int dim, int M, int N, int Npad, const double *x, const uint8_t *sp,
+                                        const double *box, int sa, int sb, double rmax, int nbins,
+                                        unsigned long long *hist, cudaStream_t st);
 size_t chain_sweep_smem_bytes(int dim, int Npad, int ns, int threads, bool mol, bool any_swap, bool filter);
 size_t chain_energy_smem_bytes(int dim, int Npad, int ns, bool mol);
 cudaError_t launch_chain_sweep(int dim, int model, bool mol, bool filter, int M, int threads, size_t smem,

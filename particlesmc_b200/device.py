@@ -183,6 +183,13 @@ class DeviceContext:
         L.check(self.lib.pmc_download(self._h, first, count, C.cast(pos_ptr, C.POINTER(C.c_double)),
                                       C.cast(sp_ptr, C.POINTER(C.c_int64))))
 
+    def pair_histogram(self, species_a: int = 0, species_b: int = 0, rmax: float = 3.0, nbins: int = 60) -> np.ndarray:
+        """Raw pair-distance counts (i < j, summed over chains); label 0 = any species."""
+        h = np.zeros(nbins, dtype=np.uint64)
+        L.check(self.lib.pmc_pair_histogram(self._h, species_a, species_b, float(rmax), nbins,
+                                            h.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return h
+
     def counters(self):
         nm = max(self.n_moves, 1)
         calls = np.zeros((self.n_chains, nm), dtype=np.int64)

@@ -1,0 +1,30 @@
+"""On-device observables used to establish statistical parity: pair-distance histograms -> g(r).
+
+The counting runs on the GPU (``pmc_pair_histogram``); this module only normalises.  With chains sharded over
+GPUs the raw counts of the ranks are summed with one all-reduce (``sharding.allreduce_sum``) -- the only place a
+collective appears outside the timing of bench.py.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def radial_distribution(ctx, n_a: int, n_b: int, volume: float, species_a: int = 0, species_b: int = 0,
+                        rmax: float = 3.0, nbins: int = 60, n_configs: int | None = None, allreduce=None):
+    """g_ab(r) of the configurations currently held by ``ctx``.
+
+    n_a, n_b: particles of species a / b per configuration (n_b = n_a for a == b); volume: box volume (d-dim);
+    n_configs: configurations contributing (default: all chains of ctx); allreduce: optional callable summing a
+    numpy array over ranks."""
+    counts = ctx.pair_histogram(species_a, species_b, rmax, nbins).astype(np.float64)
+    n_configs = ctx.n_chains if n_configs is None else n_configs
+    if allreduce is not None:
+        counts = allreduce(counts)
+    edges = np.linspace(0.0, rmax, nbins + 1)
+    d = ctx.dim
+    shell = (4.0 / 3.0 * np.pi * (edges[1:] ** 3 - edges[:-1] ** 3)) if d == 3 else (np.pi * (edges[1:] ** 2 - edges[:-1] ** 2))
+    same = species_a == species_b
+    n_pairs = n_a * (n_a - 1) / 2.0 if same else n_a * n_b  # unordered pairs per configuration
+    ideal = n_pairs * shell / volume
+    r = 0.5 * (edges[1:] + edges[:-1])
+    return r, counts / (n_configs * ideal)

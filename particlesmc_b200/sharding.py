@@ -62,3 +62,16 @@ def attach_box_peers(ctx) -> None:
         handles = torch.stack(out).numpy()
     ctx.box_peer_attach(rank, world, handles)
     dist.barrier()
+
+
+def allreduce_sum(values: np.ndarray) -> np.ndarray:
+    """Sum a small numpy array over all ranks (observable reductions: histograms, acceptance counters)."""
+    import torch
+    import torch.distributed as dist
+
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
+        return np.asarray(values)
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    t = torch.from_numpy(np.ascontiguousarray(values, dtype=np.float64)).to(dev)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t.cpu().numpy()

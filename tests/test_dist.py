@@ -14,7 +14,7 @@ def _free_port():
 
 def _worker(rank, world, port, n_chains, q):
     import torch.distributed as dist
-    from particlesmc_b200.sharding import gather_chain_values, shard_range
+    from particlesmc_b200.sharding import allreduce_sum, gather_chain_values, shard_range
 
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -27,6 +27,8 @@ def _worker(rank, world, port, n_chains, q):
     import torch
     t = torch.tensor([10.0 + rank])
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    hist = allreduce_sum(np.arange(5, dtype=np.float64) * (rank + 1))  # observable reduction (g(r) counts)
+    assert np.array_equal(hist, np.arange(5) * 3.0)
     q.put((rank, off, cnt, full, float(t.item())))
     dist.barrier()
     dist.destroy_process_group()
