@@ -12,7 +12,9 @@
 //   * no forwarding registers: every thread performs the (identical) commit stores, so each thread's own
 //     program order makes committed positions visible to it without a second barrier.
 //
-// The kernel is issue-bound (ncu: profiles/), so instruction count per trial is the figure of merit.
+// The kernel is issue-bound (ncu: profiles/), so instruction count per trial is the figure of merit -- but not the only
+// one: a 96-thread variant (11 candidates per thread, 21 % fewer instructions per trial) measured 11 % SLOWER than
+// 128 threads at N = 1000 because three warps per chain hide less latency (7 x 3 vs 6 x 4 warps per SM).
 #pragma once
 #include "chains.cuh"
 #include "common.cuh"
@@ -105,10 +107,12 @@ __device__ __forceinline__ double mi_acc(double xi, double xj, double L, double 
 
 // NPAD (compile time): padded particle count of the shared-memory planes, one of 256 / 512 / 1024 (/ 2048 in 2-D); makes every
 // shared-memory offset a constant and fixes the number of register-resident candidates per thread.
-template <int DIM, int MODEL, int NPAD, bool SWAPS>
-__global__ void __launch_bounds__(kFastThreads, 6) k_chain_sweep_fast(const __grid_constant__ ChainArgs A) {
+template <int DIM, int MODEL, int NPAD, bool SWAPS, int NT = kFastThreads>
+__global__ void __launch_bounds__(NT, NT == 128 ? 6 : 7) k_chain_sweep_fast(const __grid_constant__ ChainArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int kFastCand = NPAD / kFastThreads;
+    constexpr int kThreads = NT, kWarps = NT / 32;  // CTA size is a compile-time constant of this kernel
+    constexpr int kFastCand = NPAD / kThreads;
+    static_assert(NPAD % NT == 0 && NT % 32 == 0 && NT <= 128, "NPAD must be a multiple of the CTA size");
     constexpr int Npad = NPAD;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int c = blockIdx.x;
@@ -124,13 +128,13 @@ __global__ void __launch_bounds__(kFastThreads, 6) k_chain_sweep_fast(const __gr
     {
         double *sx = (double *)(smem_raw + F.x);
         for (int a = 0; a < DIM; a++)
-            for (int k = tid; k < Npad; k += kFastThreads) sx[a * Npad + k] = k < gNpad ? gx[a * gNpad + k] : 0.0;
+            for (int k = tid; k < Npad; k += kThreads) sx[a * Npad + k] = k < gNpad ? gx[a * gNpad + k] : 0.0;
         uint8_t *ssp = smem_raw + F.sp;
         const uint8_t *gsp = A.sp + (size_t)c * gNpad;
-        for (int k = tid; k < Npad; k += kFastThreads) ssp[k] = k < gNpad ? gsp[k] : 0;
+        for (int k = tid; k < Npad; k += kThreads) ssp[k] = k < gNpad ? gsp[k] : 0;
         double *spar = (double *)(smem_raw + F.par), *scp = (double *)(smem_raw + F.cp);
-        for (int k = tid; k < ns * ns * PMC_NPAR; k += kFastThreads) spar[k] = A.par[k];
-        for (int k = tid; k < ns * ns; k += kFastThreads) {
+        for (int k = tid; k < ns * ns * PMC_NPAR; k += kThreads) spar[k] = A.par[k];
+        for (int k = tid; k < ns * ns; k += kThreads) {
             scp[4 * k + 0] = A.par[k * PMC_NPAR + PMC_P_RCUT2];
             scp[4 * k + 1] = A.par[k * PMC_NPAR + PMC_P_EPS];
             scp[4 * k + 2] = A.par[k * PMC_NPAR + PMC_P_SIG2];
@@ -148,7 +152,7 @@ __global__ void __launch_bounds__(kFastThreads, 6) k_chain_sweep_fast(const __gr
         if constexpr (SWAPS) {
             uint16_t *si_ = (uint16_t *)(smem_raw + F.spids), *sh_ = (uint16_t *)(smem_raw + F.heads);
             const uint16_t *gi = A.spids + (size_t)c * gNpad, *gh = A.heads + (size_t)c * gNpad;
-            for (int k = tid; k < Npad; k += kFastThreads) {
+            for (int k = tid; k < Npad; k += kThreads) {
                 si_[k] = k < gNpad ? gi[k] : 0;
                 sh_[k] = k < gNpad ? gh[k] : 0;
             }
@@ -158,7 +162,7 @@ __global__ void __launch_bounds__(kFastThreads, 6) k_chain_sweep_fast(const __gr
     uint32_t myu[kFastCand][DIM];
 #pragma unroll
     for (int k = 0; k < kFastCand; k++) {
-        const int j = k * kFastThreads + tid;
+        const int j = k * kThreads + tid;
 #pragma unroll
         for (int a = 0; a < DIM; a++) myu[k][a] = j < gNpad ? to_fixed32(gx[a * gNpad + j], fscale) : 0u;
     }
@@ -302,7 +306,7 @@ __global__ void __launch_bounds__(kFastThreads, 6) k_chain_sweep_fast(const __gr
 #pragma unroll
                     for (int k = 0; k < kFastCand; k++) {
                         if (m8 & (1u << k)) {
-                            sts_u16(wp, (uint32_t)(k * kFastThreads + tid));
+                            sts_u16(wp, (uint32_t)(k * kThreads + tid));
                             wp += 2;
                         }
                     }
@@ -346,10 +350,10 @@ __global__ void __launch_bounds__(kFastThreads, 6) k_chain_sweep_fast(const __gr
                     const uint32_t rda = sb + F.red + 32u * slot;
                     if (lane == 0) sts_f64(rda + 8u * (uint32_t)warp, part);
                     __syncthreads();
-                    double s0, s1, s2, s3;
+                    double s0, s1, s2 = 0.0, s3 = 0.0;
                     lds_f64x2(rda, s0, s1);
-                    lds_f64x2(rda + 16, s2, s3);
-                    const double dE = ((s0 + s1) + s2) + s3;
+                    if constexpr (kWarps > 2) lds_f64x2(rda + 16, s2, s3);
+                    const double dE = kWarps == 4 ? ((s0 + s1) + s2) + s3 : (kWarps == 3 ? (s0 + s1) + s2 : (kWarps == 2 ? s0 + s1 : s0));
                     slot ^= 1u;
                     const bool acc = valid && (A.exact_exp ? accept_exact(dE, Tk, thr) : (dE < thr));
                     if (acc) {  // every thread performs the identical stores (see the displacement commit)
@@ -421,7 +425,7 @@ __global__ void __launch_bounds__(kFastThreads, 6) k_chain_sweep_fast(const __gr
 #pragma unroll
             for (int k = 0; k < kFastCand; k++) {
                 if (m8 & (1u << k)) {
-                    sts_u16(wp, (uint32_t)(k * kFastThreads + tid));
+                    sts_u16(wp, (uint32_t)(k * kThreads + tid));
                     wp += 2;
                 }
             }
@@ -465,10 +469,10 @@ __global__ void __launch_bounds__(kFastThreads, 6) k_chain_sweep_fast(const __gr
             const uint32_t rda = sb + F.red + 32u * slot;
             if (lane == 0) sts_f64(rda + 8u * (uint32_t)warp, part);
             __syncthreads();
-            double s0, s1, s2, s3;
+            double s0, s1, s2 = 0.0, s3 = 0.0;
             lds_f64x2(rda, s0, s1);
-            lds_f64x2(rda + 16, s2, s3);
-            const double dE = ((s0 + s1) + s2) + s3;
+            if constexpr (kWarps > 2) lds_f64x2(rda + 16, s2, s3);
+            const double dE = kWarps == 4 ? ((s0 + s1) + s2) + s3 : (kWarps == 3 ? (s0 + s1) + s2 : (kWarps == 2 ? s0 + s1 : s0));
             slot ^= 1u;
             const bool acc = A.exact_exp ? accept_exact(dE, Tk, thr) : (dE < thr);
             if (acc) {
@@ -478,8 +482,8 @@ __global__ void __launch_bounds__(kFastThreads, 6) k_chain_sweep_fast(const __gr
                 sts_f64(xa + nb8, xn[1]);
                 if constexpr (DIM == 3) sts_f64(xa + 2 * nb8, xn[2]);
                 E += dE;
-                if (tid == (i & (kFastThreads - 1))) {  // owner refreshes its register copy
-                    const int ki = i >> 7;  // kFastThreads == 128
+                if (tid == (i % kThreads)) {  // owner refreshes its register copy
+                    const int ki = i / kThreads;
 #pragma unroll
                     for (int k = 0; k < kFastCand; k++) {
                         if (k == ki) {
@@ -510,12 +514,12 @@ __global__ void __launch_bounds__(kFastThreads, 6) k_chain_sweep_fast(const __gr
     {
         const double *sx = (const double *)(smem_raw + F.x);
         for (int a = 0; a < DIM; a++)
-            for (int k = tid; k < gNpad; k += kFastThreads) gx[a * gNpad + k] = sx[a * Npad + k];
+            for (int k = tid; k < gNpad; k += kThreads) gx[a * gNpad + k] = sx[a * Npad + k];
         if constexpr (SWAPS) {
             uint8_t *gsp = A.sp + (size_t)c * gNpad;
             uint16_t *gi = A.spids + (size_t)c * gNpad, *gh = A.heads + (size_t)c * gNpad;
             const uint16_t *si_ = (const uint16_t *)(smem_raw + F.spids), *sh_ = (const uint16_t *)(smem_raw + F.heads);
-            for (int k = tid; k < gNpad; k += kFastThreads) {
+            for (int k = tid; k < gNpad; k += kThreads) {
                 gsp[k] = smem_raw[F.sp + k];
                 gi[k] = si_[k];
                 gh[k] = sh_[k];
