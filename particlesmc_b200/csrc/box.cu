@@ -700,8 +700,10 @@ __global__ void __launch_bounds__(kBoxThreads) k_box_sweep(const __grid_constant
 // sphere test (midpoint of old/new, radius rc + |delta|/2) per candidate on the integer pipes, survivors
 // compacted with one warp prefix sum, fp64 only for survivors (no minimum image in the cell frame), explicit
 // 32-bit shared addressing.  Needs cubic cells (one fixed-point scale); otherwise k_box_sweep is used.
-constexpr int kBfThreads = 64;
+constexpr int kBfThreads = 128;
 constexpr int kBfWarps = kBfThreads / 32;
+// register candidates per thread offered (capacity = threads x KC): 512 / 640 / 768 / 1024 candidates
+constexpr int kBfKc0 = 512 / kBfThreads, kBfKc1 = 640 / kBfThreads, kBfKc2 = 768 / kBfThreads, kBfKc3 = 1024 / kBfThreads;
 constexpr int kBfBatch = 32;
 constexpr int kBfRec = 80;
 
@@ -763,7 +765,7 @@ __device__ __forceinline__ void bf_sts_u8(uint32_t a, uint32_t v) { asm volatile
 __device__ __forceinline__ uint32_t bf_fixed(double r, double cs, double scale) { return (uint32_t)__double2ull_rd((r + cs) * scale); }
 
 template <int DIM, int MODEL, int KC>
-__global__ void __launch_bounds__(kBfThreads, 12) k_box_sweep_fast(const __grid_constant__ BoxArgs A, int colour) {
+__global__ void __launch_bounds__(kBfThreads, kBfThreads == 64 ? 12 : 8) k_box_sweep_fast(const __grid_constant__ BoxArgs A, int colour) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ Stencil<DIM> st;
     constexpr int CAP = kBfThreads * KC;
@@ -943,12 +945,13 @@ __global__ void __launch_bounds__(kBfThreads, 12) k_box_sweep_fast(const __grid_
             }
             __syncwarp();
             part = warp_sum(part);
-            const uint32_t rda = sb + F.red + 16u * slot;
+            const uint32_t rda = sb + F.red + 8u * kBfWarps * slot;
             if (lane == 0) bf_sts_f64(rda + 8u * (uint32_t)warp, part);
             __syncthreads();
-            double s0, s1;
+            double s0, s1, s2 = 0.0, s3 = 0.0;
             bf_lds_f64x2(rda, s0, s1);
-            const double dE = s0 + s1;
+            if constexpr (kBfWarps == 4) bf_lds_f64x2(rda + 16, s2, s3);
+            const double dE = kBfWarps == 4 ? ((s0 + s1) + s2) + s3 : s0 + s1;
             slot ^= 1u;
             if (dE < thr) {
                 bf_sts_f64(xa, xn[0]);
@@ -1297,10 +1300,9 @@ int setup_geometry(BoxState *b, const double *box3) {
                                         : (cs * cs + 4 * cs * rc + pi * rc * rc) / (9 * cs * cs);
         (void)frac;  // the pruned loader did not pay for itself (two passes over the stencil); kept for reference
         const int need = (int)(occ * nst * 1.45) + 16;
-        if (need <= kBfThreads * 8) b->fast_kc = 8;
-        else if (need <= kBfThreads * 10) b->fast_kc = 10;
-        else if (need <= kBfThreads * 12) b->fast_kc = 12;
-        else if (need <= kBfThreads * 16) b->fast_kc = 16;
+        constexpr int kcs[4] = {kBfKc0, kBfKc1, kBfKc2, kBfKc3};
+        for (int q = 3; q >= 0; q--)
+            if (need <= kBfThreads * kcs[q]) b->fast_kc = kcs[q];
     }
     if (b->fast_kc) {
         b->cap = kBfThreads * b->fast_kc;
@@ -1309,14 +1311,14 @@ int setup_geometry(BoxState *b, const double *box3) {
     }
     int rc = bdispatch(b->dim, b->cfg.model_kind, [&](auto D, auto MDL) {
         if (b->fast_kc) {
-            BCU(cudaFuncSetAttribute(k_box_sweep_fast<decltype(D)::value, decltype(MDL)::value, 8>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bf_layout(b->dim, kBfThreads * 8).total));
-            BCU(cudaFuncSetAttribute(k_box_sweep_fast<decltype(D)::value, decltype(MDL)::value, 10>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bf_layout(b->dim, kBfThreads * 10).total));
-            BCU(cudaFuncSetAttribute(k_box_sweep_fast<decltype(D)::value, decltype(MDL)::value, 12>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bf_layout(b->dim, kBfThreads * 12).total));
-            BCU(cudaFuncSetAttribute(k_box_sweep_fast<decltype(D)::value, decltype(MDL)::value, 16>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bf_layout(b->dim, kBfThreads * 16).total));
+            BCU(cudaFuncSetAttribute(k_box_sweep_fast<decltype(D)::value, decltype(MDL)::value, kBfKc0>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bf_layout(b->dim, kBfThreads * kBfKc0).total));
+            BCU(cudaFuncSetAttribute(k_box_sweep_fast<decltype(D)::value, decltype(MDL)::value, kBfKc1>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bf_layout(b->dim, kBfThreads * kBfKc1).total));
+            BCU(cudaFuncSetAttribute(k_box_sweep_fast<decltype(D)::value, decltype(MDL)::value, kBfKc2>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bf_layout(b->dim, kBfThreads * kBfKc2).total));
+            BCU(cudaFuncSetAttribute(k_box_sweep_fast<decltype(D)::value, decltype(MDL)::value, kBfKc3>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bf_layout(b->dim, kBfThreads * kBfKc3).total));
         }
         BCU(cudaFuncSetAttribute(k_box_sweep<decltype(D)::value, decltype(MDL)::value>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem));
@@ -1606,14 +1608,14 @@ int box_run(BoxState *b, int64_t n_trials) {
             constexpr int d = decltype(D)::value, mdl = decltype(MDL)::value;
             for (int k = 0; k < ncol; k++) {
                 if (hi > lo) {
-                    if (b->fast_kc == 8)
-                        k_box_sweep_fast<d, mdl, 8><<<hi - lo, kBfThreads, b->fast_smem, b->stream>>>(A, order[k]);
-                    else if (b->fast_kc == 10)
-                        k_box_sweep_fast<d, mdl, 10><<<hi - lo, kBfThreads, b->fast_smem, b->stream>>>(A, order[k]);
-                    else if (b->fast_kc == 12)
-                        k_box_sweep_fast<d, mdl, 12><<<hi - lo, kBfThreads, b->fast_smem, b->stream>>>(A, order[k]);
-                    else if (b->fast_kc == 16)
-                        k_box_sweep_fast<d, mdl, 16><<<hi - lo, kBfThreads, b->fast_smem, b->stream>>>(A, order[k]);
+                    if (b->fast_kc == kBfKc0)
+                        k_box_sweep_fast<d, mdl, kBfKc0><<<hi - lo, kBfThreads, b->fast_smem, b->stream>>>(A, order[k]);
+                    else if (b->fast_kc == kBfKc1)
+                        k_box_sweep_fast<d, mdl, kBfKc1><<<hi - lo, kBfThreads, b->fast_smem, b->stream>>>(A, order[k]);
+                    else if (b->fast_kc == kBfKc2)
+                        k_box_sweep_fast<d, mdl, kBfKc2><<<hi - lo, kBfThreads, b->fast_smem, b->stream>>>(A, order[k]);
+                    else if (b->fast_kc == kBfKc3)
+                        k_box_sweep_fast<d, mdl, kBfKc3><<<hi - lo, kBfThreads, b->fast_smem, b->stream>>>(A, order[k]);
                     else
                         k_box_sweep<d, mdl><<<hi - lo, kBoxThreads, b->smem, b->stream>>>(A, order[k]);
                 }
