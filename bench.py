@@ -78,7 +78,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -115,7 +115,7 @@ def workload_config(args):
         name = f"KA LJ 80:20 N={N} rho=1.2 T={args.temperature} x {M} independent chains per GPU, Displacement sigma=0.05"
     else:
         N = args.particles or (1 << 20)
-        sweeps = args.sweeps or 2
+        sweeps = args.sweeps or 8
         M = 1
         name = f"single KA LJ 80:20 box N={N} rho=1.2 T={args.temperature}, checkerboard cell sweeps, Displacement sigma=0.05"
     pos, sp, box = ka_lattice(N, 1.2, seed=0)
@@ -245,13 +245,21 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- device-resident throughput -----------------------------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         flush.zero_()
         ctx.run(trials_per_step, sync=False)
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    # nvidia-smi needs ~0.2 s to deliver its first sample: keep the GPU under the same load (untimed steps, all
+    # ranks alike) until it is up, so that the clock record covers the timed region even when a step is short
+    extra = 0
+    t_wait = time.perf_counter()
+    while world == 1 and rank == 0 and sampler.proc and not sampler.rows and time.perf_counter() - t_wait < 1.0:
+        ctx.run(trials_per_step, sync=True)
+        extra += 1
+    n_pre = len(sampler.rows)
     launches0 = ctx.launch_count()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     kernel_ms = []
@@ -264,7 +272,13 @@ def run_ours(args):
     barrier()
     ms_total = ev[0].elapsed_time(ev[1])
     launches = ctx.launch_count() - launches0
+    if rank == 0 and world == 1 and sampler.proc and len(sampler.rows) == n_pre:  # very short timed region:
+        t_wait = time.perf_counter()                                                # extend the load until one more sample
+        while len(sampler.rows) == n_pre and time.perf_counter() - t_wait < 0.5:
+            ctx.run(trials_per_step, sync=True)
     clocks = sampler.stop() if rank == 0 else None
+    if clocks is not None:
+        clocks["note"] = "sampled every 50 ms from the last warm-up step through the timed region (same load)"
     # per-launch duration of the sweep kernel(s), CUDA events recorded inside the library on the same stream
     for _ in range(args.steps):
         ctx.run(trials_per_step, sync=True)
@@ -313,13 +327,13 @@ def run_ours(args):
         peak32 = measure_fma_peak(False, local)
         achieved = Mc * trials_per_step * work["P"] * work["F"] / (kms * 1e-3) / 1e12
         # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from the committed ncu --set full captures
-        # (profiles/r01_v3_k_chain_sweep_fast_ncu_full_summary.csv: 4096 chains x N=1000; profiles/
-        # r01_k_box_sweep_fast_ncu_full_summary.csv: one colour of N=2^20); null for any other shape
+        # (profiles/r01_final_k_chain_sweep_fast_ncu_full_summary.csv: 4096 chains x N=1000; profiles/
+        # r01_final_k_box_sweep_fast_ncu_full_summary.csv: one colour of N=2^20); null for any other shape
         traffic = None
-        if args.workload == "chains" and Mc == 4096 and N == 1000:
-            traffic = 105.618176e6 + 44.477952e6
+        if args.workload == "chains" and Mc == 4096 and N == 1000 and args.precision == "fp64":
+            traffic = 105.820416e6 + 44.805632e6
         elif args.workload == "box" and N == (1 << 20):
-            traffic = 27.703552e6 + 0.18432e6
+            traffic = 35.759360e6 + 0.189952e6
         roofline = {"bound": "fp64_pipe", "achieved": achieved, "peak": peak64, "unit": "TFLOP/s",
                     "frac": achieved / peak64, "traffic": traffic,
                     "kernel": "k_chain_sweep" if args.workload == "chains" else "k_box_sweep (8 colours + cell rebuild)",
