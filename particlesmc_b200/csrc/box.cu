@@ -71,7 +71,6 @@ struct BoxArgs {
     int32_t *ids;     // [N] particle id of each sorted slot
     int32_t *start;   // [ncell+1]
     const double *par;
-    double rc2max;  // largest squared cutoff of the model matrix
     double T;
     float sigma;
     unsigned long long seed;
@@ -276,18 +275,14 @@ template <int DIM>
 struct Stencil {
     static constexpr int NST = DIM == 3 ? 27 : 9;
     int cell[NST];
-    int off[NST + 1];  // candidate offsets of the stencil cells in the gathered list (after pruning)
+    int off[NST + 1];  // candidate offsets of the stencil cells in the gathered list
     int cnt[NST];      // particles in each stencil cell
-    int kept[NST];     // PRUNE: particles of each stencil cell that survive the dilated-box test
+    int base[NST];     // first sorted slot of each stencil cell
     int cwrap[NST][3];
     int o[NST][3];
 };
 
-// PRUNE: keep only stencil particles within rc_max of the central cell's box [0, cs)^d.  The movable particles
-// never leave that box, so anything farther can never come inside a cutoff sphere during this phase; for cells
-// of side ~ rc this drops ~24 % of the 3^d-cell stencil.  Deterministic two-pass compaction (count, prefix,
-// write): the candidate order -- and with it the fp64 summation order -- does not depend on scheduling.
-template <int DIM, bool PRUNE>
+template <int DIM>
 __device__ int load_stencil(const BoxArgs &A, const int (&cc)[3], Stencil<DIM> *st, double *sr, uint8_t *ssp) {
     constexpr int NST = Stencil<DIM>::NST;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
@@ -311,40 +306,9 @@ __device__ int load_stencil(const BoxArgs &A, const int (&cc)[3], Stencil<DIM> *
         st->off[tid + 1] = A.start[l + 1] - A.start[l];
     }
     __syncthreads();
-    const double keep2 = A.rc2max * (1.0 + 1e-9);
-    auto frame = [&](int s, int slot, double (&r)[3]) {
-        bool keep = true;
-        double d2 = 0.0;
-#pragma unroll
-        for (int a = 0; a < DIM; a++) {
-            r[a] = in_frame(A.xs[(size_t)a * A.N + slot], A.g.shift[a], A.g.L[a], A.g.cs[a], st->cwrap[s][a]) +
-                   (double)st->o[s][a] * A.g.cs[a];
-            const double out = fmax(fmax(-r[a], r[a] - A.g.cs[a]), 0.0);
-            d2 = fma(out, out, d2);
-        }
-        if constexpr (PRUNE) keep = (s == 0) || (d2 <= keep2);
-        return keep;
-    };
-    if constexpr (PRUNE) {  // pass 1: survivors per stencil cell
-        for (int s = warp; s < NST; s += nwarp) {
-            const int b = A.start[st->cell[s]], n = st->off[s + 1];
-            int cnt = 0;
-            for (int p0 = 0; p0 < n; p0 += 32) {
-                double r[3];
-                const bool keep = (p0 + lane < n) && frame(s, b + p0 + lane, r);
-                cnt += __popc(__ballot_sync(0xffffffffu, keep));
-            }
-            if (lane == 0) st->kept[s] = cnt;
-        }
-        __syncthreads();
-    }
     if (tid == 0) {
         st->off[0] = 0;
-        for (int k = 0; k < NST; k++) {
-            const int n = st->off[k + 1];
-            st->cnt[k] = n;
-            st->off[k + 1] = st->off[k] + (PRUNE ? st->kept[k] : n);
-        }
+        for (int k = 0; k < NST; k++) st->off[k + 1] += st->off[k];
     }
     __syncthreads();
     const int ncand = st->off[NST];
@@ -353,19 +317,14 @@ __device__ int load_stencil(const BoxArgs &A, const int (&cc)[3], Stencil<DIM> *
         return -1;
     }
     for (int s = warp; s < NST; s += nwarp) {
-        const int b = A.start[st->cell[s]], n = st->cnt[s];
-        int dst = st->off[s];
-        for (int p0 = 0; p0 < n; p0 += 32) {
-            double r[3] = {0.0, 0.0, 0.0};
-            const bool keep = (p0 + lane < n) && frame(s, b + p0 + lane, r);
-            const unsigned m = __ballot_sync(0xffffffffu, keep);
-            if (keep) {
-                const int q = dst + __popc(m & ((1u << lane) - 1u));
+        const int b = A.start[st->cell[s]], n = st->off[s + 1] - st->off[s], dst = st->off[s];
+        for (int p = lane; p < n; p += 32) {
 #pragma unroll
-                for (int a = 0; a < DIM; a++) sr[a * A.cap + q] = r[a];
-                ssp[q] = A.sps[b + p0 + lane];
+            for (int a = 0; a < DIM; a++) {
+                const double r = in_frame(A.xs[(size_t)a * A.N + b + p], A.g.shift[a], A.g.L[a], A.g.cs[a], st->cwrap[s][a]);
+                sr[a * A.cap + dst + p] = r + (double)st->o[s][a] * A.g.cs[a];
             }
-            dst += __popc(m);
+            ssp[dst + p] = A.sps[b + p];
         }
     }
     __syncthreads();
@@ -374,14 +333,13 @@ __device__ int load_stencil(const BoxArgs &A, const int (&cc)[3], Stencil<DIM> *
 
 // Flat variant used by the fast sweep kernel: the candidate index space of the whole stencil is spread over ALL
 // threads (thread t handles candidates t, t + NT, ...), so the global loads of one CTA are independent and in
-// flight together instead of one dependent start[] -> xs[] chain per stencil cell.  Same candidate order and the
-// same pruning rule as load_stencil<DIM, true>; the compaction is done per (iteration, warp) with ballots and a
-// prefix over those counts, i.e. in candidate-index order: deterministic.
-template <int DIM, int NT, int MAXIT, bool PRUNE>
-__device__ int load_stencil_flat(const BoxArgs &A, const int (&cc)[3], Stencil<DIM> *st, double *sr, uint8_t *ssp,
-                                 int *s_cnt /* [MAXIT * NT/32 + 1] */) {
-    constexpr int NST = Stencil<DIM>::NST, NW = NT / 32;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+// flight together instead of one dependent start[] -> xs[] chain per stencil cell.  Same candidate order as
+// load_stencil.  (A variant that also dropped candidates farther than rc from the central cell -- 24 % of the
+// stencil -- was measured slower: the second pass over the stencil costs more than the smaller scan saves.)
+template <int DIM, int NT>
+__device__ int load_stencil_flat(const BoxArgs &A, const int (&cc)[3], Stencil<DIM> *st, double *sr, uint8_t *ssp) {
+    constexpr int NST = Stencil<DIM>::NST;
+    const int tid = threadIdx.x;
     if (tid < NST) {
         int k = tid == 0 ? (NST / 2) : (tid <= NST / 2 ? tid - 1 : tid);
         int c[3] = {0, 0, 0};
@@ -399,7 +357,7 @@ __device__ int load_stencil_flat(const BoxArgs &A, const int (&cc)[3], Stencil<D
         const int l = lin_cell<DIM>(c, A.g.nc);
         const int b = A.start[l];
         st->cell[tid] = l;
-        st->kept[tid] = b;  // (re-used) first sorted slot of the stencil cell
+        st->base[tid] = b;
         st->cnt[tid] = A.start[l + 1] - b;
     }
     __syncthreads();
@@ -408,102 +366,26 @@ __device__ int load_stencil_flat(const BoxArgs &A, const int (&cc)[3], Stencil<D
         for (int k = 0; k < NST; k++) st->off[k + 1] = st->off[k] + st->cnt[k];
     }
     __syncthreads();
-    const int nall = st->off[NST], ncen = st->cnt[0];
-    if (PRUNE && nall > MAXIT * NT) {
+    const int nall = st->off[NST];
+    if (nall > A.cap) {
         if (tid == 0) atomicExch(A.overflow, 1);
         return -1;
     }
-    if constexpr (!PRUNE) {  // single pass: candidate t goes to place t
-        if (nall > A.cap) {
-            if (tid == 0) atomicExch(A.overflow, 1);
-            return -1;
+    for (int t = tid; t < nall; t += NT) {
+        int lo = 0, hi = NST;  // stencil cell of flat index t: binary search over the 3^d offsets
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (t >= st->off[mid]) lo = mid; else hi = mid;
         }
-        for (int t = tid; t < nall; t += NT) {
-            int lo = 0, hi = NST;
-            while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                if (t >= st->off[mid]) lo = mid; else hi = mid;
-            }
-            const int slot = st->kept[lo] + (t - st->off[lo]);
+        const int slot = st->base[lo] + (t - st->off[lo]);
 #pragma unroll
-            for (int a = 0; a < DIM; a++)
-                sr[a * A.cap + t] = in_frame(A.xs[(size_t)a * A.N + slot], A.g.shift[a], A.g.L[a], A.g.cs[a], st->cwrap[lo][a]) +
-                                    (double)st->o[lo][a] * A.g.cs[a];
-            ssp[t] = A.sps[slot];
-        }
-        __syncthreads();
-        return nall;
-    }
-    const double keep2 = A.rc2max * (1.0 + 1e-9);
-    auto fetch = [&](int t, double (&r)[3], int &slot) {
-        int s = 0;  // stencil cell of flat index t: binary search over the 3^d offsets
-        {
-            int lo = 0, hi = NST;
-            while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                if (t >= st->off[mid]) lo = mid; else hi = mid;
-            }
-            s = lo;
-        }
-        slot = st->kept[s] + (t - st->off[s]);
-        double d2 = 0.0;
-#pragma unroll
-        for (int a = 0; a < DIM; a++) {
-            r[a] = in_frame(A.xs[(size_t)a * A.N + slot], A.g.shift[a], A.g.L[a], A.g.cs[a], st->cwrap[s][a]) +
-                   (double)st->o[s][a] * A.g.cs[a];
-            const double out = fmax(fmax(-r[a], r[a] - A.g.cs[a]), 0.0);
-            d2 = fma(out, out, d2);
-        }
-        return t < ncen || d2 <= keep2;
-    };
-    // pass 1: keep flags (bit k of `mask` = candidate tid + k*NT survives) and per-(iteration, warp) counts
-    uint32_t mask = 0;
-#pragma unroll
-    for (int k = 0; k < MAXIT; k++) {
-        const int t = k * NT + tid;
-        bool keep = false;
-        if (t < nall) {
-            double r[3];
-            int slot;
-            keep = fetch(t, r, slot);
-        }
-        const unsigned m = __ballot_sync(0xffffffffu, keep);
-        if (keep) mask |= 1u << k;
-        if (lane == 0) s_cnt[k * NW + warp] = __popc(m);
+        for (int a = 0; a < DIM; a++)
+            sr[a * A.cap + t] = in_frame(A.xs[(size_t)a * A.N + slot], A.g.shift[a], A.g.L[a], A.g.cs[a], st->cwrap[lo][a]) +
+                                (double)st->o[lo][a] * A.g.cs[a];
+        ssp[t] = A.sps[slot];
     }
     __syncthreads();
-    if (tid == 0) {  // exclusive prefix in (iteration, warp) order
-        int run = 0;
-        for (int k = 0; k < MAXIT * NW; k++) {
-            const int c = s_cnt[k];
-            s_cnt[k] = run;
-            run += c;
-        }
-        s_cnt[MAXIT * NW] = run;
-    }
-    __syncthreads();
-    const int ncand = s_cnt[MAXIT * NW];
-    // pass 2: survivors re-read their position (L2) and write it to their compacted place
-#pragma unroll
-    for (int k = 0; k < MAXIT; k++) {
-        const bool keep = (mask >> k) & 1u;
-        const unsigned m = __ballot_sync(0xffffffffu, keep);
-        if (keep) {
-            double r[3] = {0.0, 0.0, 0.0};
-            int slot;
-            fetch(k * NT + tid, r, slot);
-            const int q = s_cnt[k * NW + warp] + __popc(m & ((1u << lane) - 1u));
-#pragma unroll
-            for (int a = 0; a < DIM; a++) sr[a * A.cap + q] = r[a];
-            ssp[q] = A.sps[slot];
-        }
-    }
-    if (tid == 0) {
-        st->off[1] = ncen;
-        st->off[NST] = ncand;
-    }
-    __syncthreads();
-    return ncand;
+    return nall;
 }
 
 template <int DIM>
@@ -540,7 +422,7 @@ __global__ void __launch_bounds__(kBoxThreads) k_box_energy(const __grid_constan
         cc[1] = l % A.g.nc[1];
         cc[0] = l / A.g.nc[1];
     }
-    const int ncand = load_stencil<DIM, false>(A, cc, &st, sr, ssp);
+    const int ncand = load_stencil<DIM>(A, cc, &st, sr, ssp);
     if (ncand < 0) return;
     const int ncen = st.off[1], b = A.start[st.cell[0]];
     double wsum = 0.0;
@@ -590,7 +472,7 @@ __global__ void __launch_bounds__(kBoxThreads) k_box_sweep(const __grid_constant
         cc[1] = 2 * (l % (A.g.nc[1] / 2)) + ((colour >> 1) & 1);
         cc[0] = 2 * (l / (A.g.nc[1] / 2)) + (colour & 1);
     }
-    const int ncand = load_stencil<DIM, false>(A, cc, &st, sr, ssp);
+    const int ncand = load_stencil<DIM>(A, cc, &st, sr, ssp);
     if (ncand < 0) return;
     const int cell = st.cell[0], ncen = st.off[1], b = A.start[cell];
     for (int k = tid; k < ncen; k += kBoxThreads) moved[k] = 0;
@@ -797,13 +679,8 @@ __global__ void __launch_bounds__(kBfThreads, kBfThreads == 64 ? 12 : 8) k_box_s
         cc[1] = 2 * (l % (A.g.nc[1] / 2)) + ((colour >> 1) & 1);
         cc[0] = 2 * (l / (A.g.nc[1] / 2)) + (colour & 1);
     }
-    __shared__ int s_cnt[16 * kBfWarps + 1];
-    const int ncand = load_stencil_flat<DIM, kBfThreads, 16, false>(A, cc, &st, sr, ssp, s_cnt);  // A.cap == CAP on this path
+    const int ncand = load_stencil_flat<DIM, kBfThreads>(A, cc, &st, sr, ssp);  // A.cap == CAP on this path
     if (ncand < 0) return;
-    if (ncand > CAP) {
-        if (tid == 0) atomicExch(A.overflow, 1);
-        return;
-    }
     const int cell = st.cell[0], ncen = st.off[1], bstart = A.start[cell];
     for (int k = tid; k < ncen; k += kBfThreads) smem_raw[F.mv + k] = 0;
     const double cs = A.g.cs[0];
@@ -1047,7 +924,7 @@ __global__ void __launch_bounds__(kBoxThreads) k_box_pair_histogram(const __grid
         cc[1] = l % A.g.nc[1];
         cc[0] = l / A.g.nc[1];
     }
-    const int ncand = load_stencil<DIM, false>(A, cc, &st, sr, ssp);
+    const int ncand = load_stencil<DIM>(A, cc, &st, sr, ssp);
     if (ncand < 0) return;
     // particle ids of the candidates (to count every unordered pair once: only id_i < id_j)
     for (int s = 0; s < Stencil<DIM>::NST; s++) {
@@ -1208,7 +1085,6 @@ void fill_args(BoxState *b, BoxArgs &a) {
     a.ids = b->ids;
     a.start = b->start;
     a.par = b->par;
-    a.rc2max = b->rcut_max * b->rcut_max;
     a.T = b->T;
     a.sigma = (float)b->sigma;
     a.seed = b->seed;
@@ -1294,11 +1170,6 @@ int setup_geometry(BoxState *b, const double *box3) {
     if (cubic && b->cfg.prefilter >= 0) {
         // register-candidate budget: 1.45 x the mean stencil occupancy covers a simple-cubic lattice start, where a
         // 3-cell span holds 8 or 9 lattice planes (overflow is detected and reported, never silent)
-        // ... times the fraction of the stencil volume within rc of the central cell (what the pruned loader keeps)
-        const double cs = b->g.cs[0], rc = b->rcut_max, pi = 3.14159265358979323846;
-        const double frac = b->dim == 3 ? (cs * cs * cs + 6 * cs * cs * rc + 3 * pi * cs * rc * rc + 4.0 / 3.0 * pi * rc * rc * rc) / (27 * cs * cs * cs)
-                                        : (cs * cs + 4 * cs * rc + pi * rc * rc) / (9 * cs * cs);
-        (void)frac;  // the pruned loader did not pay for itself (two passes over the stencil); kept for reference
         const int need = (int)(occ * nst * 1.45) + 16;
         constexpr int kcs[4] = {kBfKc0, kBfKc1, kBfKc2, kBfKc3};
         for (int q = 3; q >= 0; q--)
