@@ -98,11 +98,20 @@ __device__ __forceinline__ uint32_t fixed_thr(double r2_scaled) {
     return t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
 }
 
-// wrapped-coordinate nearest image, squared, accumulated
-__device__ __forceinline__ double mi_acc(double xi, double xj, double L, double acc) {
-    const double a = fabs(xi - xj);
-    const double r = fmin(a, L - a);
+// wrapped-coordinate nearest image, squared, accumulated.  |a - L| == L - a and the square drops the sign, so this
+// is fmin(a, L - a)^2 bit for bit, issued as compare + subtract + select (fmin() costs six instructions in fp64:
+// DSETP.MIN + two selects + NaN fix-up + moves).
+__device__ __forceinline__ double mi_acc(double xi, double xj, double L, double hL, double acc) {
+    const double a = xi - xj;
+    const double r = fabs(a) > hL ? fabs(a) - L : a;
     return fma(r, r, acc);
+}
+// x in [-L, 2L) -> [0, L): the two sequential folds of the displacement move as predicated adds
+__device__ __forceinline__ double wrap_once(double x, double L) {
+    asm("{ .reg .pred p, q; setp.ge.f64 p, %0, %1; @p sub.f64 %0, %0, %1; setp.lt.f64 q, %0, 0d0000000000000000; @q add.f64 %0, %0, %1; }"
+        : "+d"(x)
+        : "d"(L));
+    return x;
 }
 
 // NPAD (compile time): padded particle count of the shared-memory planes, one of 256 / 512 / 1024 (/ 2048 in 2-D); makes every
@@ -112,6 +121,7 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 6 : 7) k_chain_sweep_fast(cons
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int kThreads = NT, kWarps = NT / 32;  // CTA size is a compile-time constant of this kernel
     constexpr int kFastCand = NPAD / kThreads;
+    constexpr int kImgThread = kThreads > 32 ? 32 : 0, kCntThread = kThreads > 64 ? 64 : 0;  // bookkeeping lanes
     static_assert(NPAD % NT == 0 && NT % 32 == 0 && NT <= 128, "NPAD must be a multiple of the CTA size");
     constexpr int Npad = NPAD;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -122,7 +132,7 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 6 : 7) k_chain_sweep_fast(cons
     const uint32_t nb8 = 8u * (uint32_t)Npad;  // byte stride between coordinate planes
 
     // ---- load chain state -----------------------------------------------------------------------------
-    const double L = A.box[c * 3];
+    const double L = A.box[c * 3], hL = 0.5 * L;
     const double fscale = 4294967296.0 / L;
     double *gx = A.x + (size_t)c * DIM * gNpad;
     {
@@ -332,15 +342,15 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 6 : 7) k_chain_sweep_fast(cons
                             const uint32_t sk = lds_u8(sb + F.sp + k);
                             const uint32_t skn = k == iu ? sj : (k == ju ? si : sk);  // species of k after the exchange
                             if (k != iu) {  // k-term of particle i's local energy: (si, sk) -> (sj, sk')
-                                double r2 = mi_acc(xi0, xk0, L, 0.0);
-                                r2 = mi_acc(xi1, xk1, L, r2);
-                                if constexpr (DIM == 3) r2 = mi_acc(xi2, xk2, L, r2);
+                                double r2 = mi_acc(xi0, xk0, L, hL, 0.0);
+                                r2 = mi_acc(xi1, xk1, L, hL, r2);
+                                if constexpr (DIM == 3) r2 = mi_acc(xi2, xk2, L, hL, r2);
                                 part += pair_e(sj, skn, r2) - pair_e(si, sk, r2);
                             }
                             if (k != ju) {  // k-term of particle j's local energy: (sj, sk) -> (si, sk')
-                                double r2 = mi_acc(xj0, xk0, L, 0.0);
-                                r2 = mi_acc(xj1, xk1, L, r2);
-                                if constexpr (DIM == 3) r2 = mi_acc(xj2, xk2, L, r2);
+                                double r2 = mi_acc(xj0, xk0, L, hL, 0.0);
+                                r2 = mi_acc(xj1, xk1, L, hL, r2);
+                                if constexpr (DIM == 3) r2 = mi_acc(xj2, xk2, L, hL, r2);
                                 part += pair_e(si, skn, r2) - pair_e(sj, sk, r2);
                             }
                         }
@@ -365,7 +375,7 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 6 : 7) k_chain_sweep_fast(cons
                         sts_u16(sb + F.heads + 2u * ju, hi);
                         E += dE;
                     }
-                    if (tid == 0) {
+                    if (tid == kCntThread) {
                         unsigned long long *scnt = (unsigned long long *)(smem_raw + F.cnt);
                         scnt[mv] += 1ull;
                         scnt[PMC_MAX_MOVES + mv] += acc ? 1ull : 0ull;
@@ -390,10 +400,7 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 6 : 7) k_chain_sweep_fast(cons
             xn[1] = xo[1] + d1;
             xn[2] = xo[2] + d2;
 #pragma unroll
-            for (int a = 0; a < DIM; a++) {
-                xn[a] = xn[a] >= L ? xn[a] - L : xn[a];
-                xn[a] = xn[a] < 0.0 ? xn[a] + L : xn[a];
-            }
+            for (int a = 0; a < DIM; a++) xn[a] = wrap_once(xn[a], L);
             // filter sphere: midpoint of old and new in fixed point, radius from the parked record
             const uint32_t um0 = to_fixed32(xo[0], fscale) + (uint32_t)(di0 >> 1);
             const uint32_t um1 = to_fixed32(xo[1], fscale) + (uint32_t)(di1 >> 1);
@@ -438,13 +445,13 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 6 : 7) k_chain_sweep_fast(cons
                 if (j < (uint32_t)N && j != (uint32_t)i) {
                     const uint32_t ja = sb + F.x + 8u * j;
                     const double xj0 = lds_f64(ja), xj1 = lds_f64(ja + nb8);
-                    double r2o = mi_acc(xo[0], xj0, L, 0.0), r2n = mi_acc(xn[0], xj0, L, 0.0);
-                    r2o = mi_acc(xo[1], xj1, L, r2o);
-                    r2n = mi_acc(xn[1], xj1, L, r2n);
+                    double r2o = mi_acc(xo[0], xj0, L, hL, 0.0), r2n = mi_acc(xn[0], xj0, L, hL, 0.0);
+                    r2o = mi_acc(xo[1], xj1, L, hL, r2o);
+                    r2n = mi_acc(xn[1], xj1, L, hL, r2n);
                     if constexpr (DIM == 3) {
                         const double xj2 = lds_f64(ja + 2 * nb8);
-                        r2o = mi_acc(xo[2], xj2, L, r2o);
-                        r2n = mi_acc(xn[2], xj2, L, r2n);
+                        r2o = mi_acc(xo[2], xj2, L, hL, r2o);
+                        r2n = mi_acc(xn[2], xj2, L, hL, r2n);
                     }
                     const uint32_t sj = lds_u8(sb + F.sp + j);
                     if constexpr (MODEL == PMC_MODEL_LJ || MODEL == PMC_MODEL_KG) {
@@ -484,23 +491,28 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 6 : 7) k_chain_sweep_fast(cons
                 E += dE;
                 if (tid == (i % kThreads)) {  // owner refreshes its register copy
                     const int ki = i / kThreads;
+                    uint32_t f[DIM];
+#pragma unroll
+                    for (int a = 0; a < DIM; a++) f[a] = to_fixed32(xn[a], fscale);
 #pragma unroll
                     for (int k = 0; k < kFastCand; k++) {
                         if (k == ki) {
 #pragma unroll
-                            for (int a = 0; a < DIM; a++) myu[k][a] = to_fixed32(xn[a], fscale);
+                            for (int a = 0; a < DIM; a++) myu[k][a] = f[a];
                         }
                     }
                 }
-            }
-            if (tid == 0) {
-                if (acc) {  // image counters: which way did the coordinate wrap
+                // image counters (which way did the coordinate wrap) and move counters are kept by threads of
+                // different warps: every warp waits at the next barrier, so the per-trial bookkeeping is spread out
+                if (tid == kImgThread) {
                     const double t0 = xo[0] + d0, t1 = xo[1] + d1, t2 = xo[2] + d2;
                     const int w0 = (t0 >= L) - (t0 < 0.0), w1 = (t1 >= L) - (t1 < 0.0), w2 = (t2 >= L) - (t2 < 0.0);
                     if (w0) atomicAdd(&gimg[i], w0);
                     if (w1) atomicAdd(&gimg[gNpad + i], w1);
                     if (DIM == 3 && w2) atomicAdd(&gimg[2 * gNpad + i], w2);
                 }
+            }
+            if (tid == kCntThread) {
                 unsigned long long *scnt = (unsigned long long *)(smem_raw + F.cnt);
                 const int m = (int)lds_u32(ra + 48);
                 scnt[m] += 1ull;
