@@ -98,6 +98,25 @@ __device__ __forceinline__ uint32_t fixed_thr(double r2_scaled) {
     return t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
 }
 
+// ---- 8-bit prefilter ---------------------------------------------------------------------------------------
+// A candidate is three bytes (top 8 bits of the fixed-point fraction of L per axis) in one register.  Per byte
+// VABSDIFF4.U8 gives |a - b| in [0, 255]; read as a SIGNED byte by IDP.4A that is the wrapped difference
+// (d >= 128 -> d - 256), so one IDP.4A.S8.S8 returns the minimum-image squared distance in units of (L/256)^2,
+// and its accumulator input subtracts the threshold: the sign bit is the verdict.  Three instructions per candidate
+// (VABSDIFF4, IDP.4A, SHF funnel) instead of 3 IADD + 3 IMAD.HI + compare + select on 32-bit coordinates.
+// Quantisation: both bytes are floors of exact scaled coordinates, so each component differs from the true one
+// by less than 1 unit and sum q_a^2 <= (r + sqrt(3))^2 -- the threshold carries that margin, so no in-range
+// candidate is ever dropped (survivors are then treated exactly, in fp64).
+__device__ __forceinline__ uint32_t pack8(uint32_t u0, uint32_t u1, uint32_t u2) {
+    return __byte_perm(__byte_perm(u0, u1, 0x4473), u2 >> 24, 0x5410);  // bytes: u0>>24, u1>>24, u2>>24, 0
+}
+// ~threshold (== -(thr + 1)): IDP.4A(t, t, ~thr) < 0  <=>  r2 <= thr
+__device__ __forceinline__ uint32_t neg_thr8(double r_units) {
+    const double t = r_units + 1.7320526;
+    const double t2 = t * t + 1.0;
+    return ~(t2 >= 60000.0 ? 60000u : (uint32_t)t2);
+}
+
 // wrapped-coordinate nearest image, squared, accumulated.  |a - L| == L - a and the square drops the sign, so this
 // is fmin(a, L - a)^2 bit for bit, issued as compare + subtract + select (fmin() costs six instructions in fp64:
 // DSETP.MIN + two selects + NaN fix-up + moves).
@@ -157,7 +176,7 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 6 : 7) k_chain_sweep_fast(cons
         if (tid == 0) {  // conservative fixed-point cutoff over all species pairs (swap filter)
             double rc2 = 0.0;
             for (int k = 0; k < ns * ns; k++) rc2 = fmax(rc2, A.par[k * PMC_NPAR + PMC_P_RCUT2]);
-            ((uint32_t *)sso)[PMC_MAX_SPECIES + 1] = fixed_thr(rc2 * (fscale / L));
+            ((uint32_t *)sso)[PMC_MAX_SPECIES + 1] = neg_thr8(sqrt(rc2) * fscale * 0x1p-24);
         }
         if constexpr (SWAPS) {
             uint16_t *si_ = (uint16_t *)(smem_raw + F.spids), *sh_ = (uint16_t *)(smem_raw + F.heads);
@@ -169,12 +188,14 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 6 : 7) k_chain_sweep_fast(cons
         }
     }
     // fixed-point coordinates of this thread's candidates j = k * 128 + tid, k = 0..7 (registers)
-    uint32_t myu[kFastCand][DIM];
+    uint32_t myq[kFastCand];
 #pragma unroll
     for (int k = 0; k < kFastCand; k++) {
         const int j = k * kThreads + tid;
+        uint32_t u[3] = {0u, 0u, 0u};
 #pragma unroll
-        for (int a = 0; a < DIM; a++) myu[k][a] = j < gNpad ? to_fixed32(gx[a * gNpad + j], fscale) : 0u;
+        for (int a = 0; a < DIM; a++) u[a] = j < gNpad ? to_fixed32(gx[a * gNpad + j], fscale) : 0u;
+        myq[k] = pack8(u[0], u[1], u[2]);
     }
     if (tid < PMC_MAX_SPECIES) {  // largest cutoff radius per species of the moved particle (filter sphere)
         double rc2 = 0.0;
@@ -251,8 +272,7 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 6 : 7) k_chain_sweep_fast(cons
             const double *rcs = (const double *)(smem_raw + F.rcs);
 #pragma unroll
             for (int s = 0; s < PMC_MAX_SPECIES; s++) {
-                const double r = rcs[s] + hd;
-                rt[s] = fixed_thr(r * r * (fscale / L));
+                rt[s] = neg_thr8((rcs[s] + hd) * fscale * 0x1p-24);
             }
         }
         __syncthreads();
@@ -287,21 +307,15 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 6 : 7) k_chain_sweep_fast(cons
                     const uint32_t oi = lds_u32(soa + 4u * si), oj = lds_u32(soa + 4u * sj);
                     const uint32_t ui0 = to_fixed32(xi0, fscale), ui1 = to_fixed32(xi1, fscale), ui2 = DIM == 3 ? to_fixed32(xi2, fscale) : 0u;
                     const uint32_t uj0 = to_fixed32(xj0, fscale), uj1 = to_fixed32(xj1, fscale), uj2 = DIM == 3 ? to_fixed32(xj2, fscale) : 0u;
-                    const uint32_t gthr = lds_u32(soa + 4u * (PMC_MAX_SPECIES + 1));
+                    const int gthr = (int)lds_u32(soa + 4u * (PMC_MAX_SPECIES + 1));
+                    const uint32_t uiq = pack8(ui0, ui1, ui2), ujq = pack8(uj0, uj1, uj2);
                     uint32_t m8 = 0;
                     if (valid) {
 #pragma unroll
-                        for (int k = 0; k < kFastCand; k++) {
-                            const uint32_t a2 = DIM == 3 ? myu[k][DIM - 1] : 0u;
-                            int d = (int)(ui0 - myu[k][0]), e = (int)(uj0 - myu[k][0]);
-                            uint32_t r1 = (uint32_t)__mulhi(d, d), r2 = (uint32_t)__mulhi(e, e);
-                            d = (int)(ui1 - myu[k][1]), e = (int)(uj1 - myu[k][1]);
-                            r1 += (uint32_t)__mulhi(d, d), r2 += (uint32_t)__mulhi(e, e);
-                            if constexpr (DIM == 3) {
-                                d = (int)(ui2 - a2), e = (int)(uj2 - a2);
-                                r1 += (uint32_t)__mulhi(d, d), r2 += (uint32_t)__mulhi(e, e);
-                            }
-                            m8 |= (min(r1, r2) <= gthr) ? (1u << k) : 0u;
+                        for (int k = 0; k < kFastCand; k++) {  // survivor of either sphere: bit kFastCand-1-k
+                            const uint32_t t1 = __vabsdiffu4(uiq, myq[k]), t2 = __vabsdiffu4(ujq, myq[k]);
+                            const int v = __dp4a((int)t1, (int)t1, gthr) | __dp4a((int)t2, (int)t2, gthr);
+                            m8 = __funnelshift_l((uint32_t)v, m8, 1);
                         }
                     }
                     const int mine = __popc(m8);
@@ -315,7 +329,7 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 6 : 7) k_chain_sweep_fast(cons
                     uint32_t wp = qa + 2u * (uint32_t)(incl - mine);
 #pragma unroll
                     for (int k = 0; k < kFastCand; k++) {
-                        if (m8 & (1u << k)) {
+                        if (m8 & (1u << (kFastCand - 1 - k))) {
                             sts_u16(wp, (uint32_t)(k * kThreads + tid));
                             wp += 2;
                         }
@@ -405,19 +419,13 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 6 : 7) k_chain_sweep_fast(cons
             const uint32_t um0 = to_fixed32(xo[0], fscale) + (uint32_t)(di0 >> 1);
             const uint32_t um1 = to_fixed32(xo[1], fscale) + (uint32_t)(di1 >> 1);
             const uint32_t um2 = (DIM == 3) ? to_fixed32(xo[2], fscale) + (uint32_t)(di2 >> 1) : 0u;
-            const uint32_t fthr = lds_u32(ra + 64 + 4u * si);
+            const int fthr = (int)lds_u32(ra + 64 + 4u * si);
+            const uint32_t umq = pack8(um0, um1, um2);
             uint32_t m8 = 0;
 #pragma unroll
-            for (int k = 0; k < kFastCand; k++) {
-                int d = (int)(um0 - myu[k][0]);
-                uint32_t r = (uint32_t)__mulhi(d, d);
-                d = (int)(um1 - myu[k][1]);
-                r += (uint32_t)__mulhi(d, d);
-                if constexpr (DIM == 3) {
-                    d = (int)(um2 - myu[k][DIM - 1]);
-                    r += (uint32_t)__mulhi(d, d);
-                }
-                m8 |= (r <= fthr) ? (1u << k) : 0u;
+            for (int k = 0; k < kFastCand; k++) {  // survivor: bit kFastCand-1-k
+                const uint32_t t = __vabsdiffu4(umq, myq[k]);
+                m8 = __funnelshift_l((uint32_t)__dp4a((int)t, (int)t, fthr), m8, 1);
             }
             // compaction: warp prefix sum of the per-thread survivor counts
             const int mine = __popc(m8);
@@ -431,7 +439,7 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 6 : 7) k_chain_sweep_fast(cons
             uint32_t wp = qa + 2u * (uint32_t)(incl - mine);
 #pragma unroll
             for (int k = 0; k < kFastCand; k++) {
-                if (m8 & (1u << k)) {
+                if (m8 & (1u << (kFastCand - 1 - k))) {
                     sts_u16(wp, (uint32_t)(k * kThreads + tid));
                     wp += 2;
                 }
@@ -491,16 +499,9 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 6 : 7) k_chain_sweep_fast(cons
                 E += dE;
                 if (tid == (i % kThreads)) {  // owner refreshes its register copy
                     const int ki = i / kThreads;
-                    uint32_t f[DIM];
+                    const uint32_t f = pack8(to_fixed32(xn[0], fscale), to_fixed32(xn[1], fscale), DIM == 3 ? to_fixed32(xn[2], fscale) : 0u);
 #pragma unroll
-                    for (int a = 0; a < DIM; a++) f[a] = to_fixed32(xn[a], fscale);
-#pragma unroll
-                    for (int k = 0; k < kFastCand; k++) {
-                        if (k == ki) {
-#pragma unroll
-                            for (int a = 0; a < DIM; a++) myu[k][a] = f[a];
-                        }
-                    }
+                    for (int k = 0; k < kFastCand; k++) myq[k] = k == ki ? f : myq[k];
                 }
                 // image counters (which way did the coordinate wrap) and move counters are kept by threads of
                 // different warps: every warp waits at the next barrier, so the per-trial bookkeeping is spread out
