@@ -577,9 +577,9 @@ __global__ void __launch_bounds__(kBoxThreads) k_box_sweep(const __grid_constant
 }
 
 // ---- K5 (fast): checkerboard sweep with the integer prefilter ---------------------------------------------
-// Same trials and the same fp64 pair terms as k_box_sweep, issued the way chains_fast.cuh does it: 64 threads
-// per active cell, every thread keeps the fixed-point frame coordinates of its KC candidates in registers, one
-// sphere test (midpoint of old/new, radius rc + |delta|/2) per candidate on the integer pipes, survivors
+// Same trials and the same fp64 pair terms as k_box_sweep, issued the way chains_fast.cuh does it: 128 threads
+// per active cell, every thread keeps the packed 8-bit frame coordinates of its KC candidates in registers, one
+// sphere test (midpoint of old/new, radius rc + |delta|/2; VABSDIFF4 + IDP.4A + funnel shift) per candidate, survivors
 // compacted with one warp prefix sum, fp64 only for survivors (no minimum image in the cell frame), explicit
 // 32-bit shared addressing.  Needs cubic cells (one fixed-point scale); otherwise k_box_sweep is used.
 constexpr int kBfThreads = 128;
@@ -643,7 +643,9 @@ __device__ __forceinline__ void bf_sts_f64(uint32_t a, double v) { asm volatile(
 __device__ __forceinline__ void bf_sts_u16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void bf_sts_u8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 
-// frame coordinate r in [-cs, 2cs) -> fixed point in [0, 3 * 2^29): differences never wrap
+// frame coordinate r in [-cs, 2cs) -> fixed point in [0, 3 * 2^30); its top byte (pack8) counts units of cs / 64
+// in [0, 192).  The moved particle and its trial position lie in the centre cell [64, 128), so no byte difference
+// reaches 128 and the signed-byte reading of VABSDIFF4 (common.cuh) never aliases in the frame.
 __device__ __forceinline__ uint32_t bf_fixed(double r, double cs, double scale) { return (uint32_t)__double2ull_rd((r + cs) * scale); }
 
 template <int DIM, int MODEL, int KC>
@@ -684,13 +686,15 @@ __global__ void __launch_bounds__(kBfThreads, kBfThreads == 64 ? 12 : 8) k_box_s
     const int cell = st.cell[0], ncen = st.off[1], bstart = A.start[cell];
     for (int k = tid; k < ncen; k += kBfThreads) smem_raw[F.mv + k] = 0;
     const double cs = A.g.cs[0];
-    const double fscale = 536870912.0 / cs;  // 2^29 / cell side
-    uint32_t myu[KC][DIM];
+    const double fscale = 1073741824.0 / cs;  // 2^30 / cell side
+    uint32_t myq[KC];                          // packed 8-bit prefilter coordinates of this thread's candidates
 #pragma unroll
     for (int k = 0; k < KC; k++) {
         const int j = k * kBfThreads + tid;
+        uint32_t u[3] = {0u, 0u, 0u};
 #pragma unroll
-        for (int a = 0; a < DIM; a++) myu[k][a] = j < ncand ? bf_fixed(sr[a * CAP + j], cs, fscale) : 0u;
+        for (int a = 0; a < DIM; a++) u[a] = j < ncand ? bf_fixed(sr[a * CAP + j], cs, fscale) : 0u;
+        myq[k] = pack8(u[0], u[1], u[2]);
     }
     const uint32_t k0 = (uint32_t)A.seed, k1 = (uint32_t)(A.seed >> 32);
     const uint32_t qa = sb + F.q + (uint32_t)warp * (2u * KC * 32);
@@ -723,11 +727,7 @@ __global__ void __launch_bounds__(kBfThreads, kBfThreads == 64 ? 12 : 8) k_box_s
             const double hd = 0.5 * sqrt(dx * dx + dy * dy + dz * dz);
             const double *rcs = (const double *)(smem_raw + F.rcs);
 #pragma unroll
-            for (int s = 0; s < PMC_MAX_SPECIES; s++) {
-                const double r = rcs[s] + hd;
-                const double t = r * r * fscale * fscale * 0x1p-32 * (1.0 + 1e-9) + 64.0;
-                rt[s] = t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
-            }
+            for (int s = 0; s < PMC_MAX_SPECIES; s++) rt[s] = neg_thr8((rcs[s] + hd) * fscale * 0x1p-24);
         }
         __syncthreads();
         for (int t = 0; t < nb; t++) {
@@ -752,19 +752,13 @@ __global__ void __launch_bounds__(kBfThreads, kBfThreads == 64 ? 12 : 8) k_box_s
             const uint32_t um0 = bf_fixed(xo[0], cs, fscale) + (uint32_t)(di0 >> 1);
             const uint32_t um1 = bf_fixed(xo[1], cs, fscale) + (uint32_t)(di1 >> 1);
             const uint32_t um2 = DIM == 3 ? bf_fixed(xo[2], cs, fscale) + (uint32_t)(di2 >> 1) : 0u;
-            const uint32_t fthr = bf_lds_u32(ra + 64 + 4u * si);
+            const int fthr = (int)bf_lds_u32(ra + 64 + 4u * si);
+            const uint32_t umq = pack8(um0, um1, um2);
             uint32_t m = 0;
 #pragma unroll
-            for (int kk = 0; kk < KC; kk++) {
-                int d = (int)(um0 - myu[kk][0]);
-                uint32_t r = (uint32_t)__mulhi(d, d);
-                d = (int)(um1 - myu[kk][1]);
-                r += (uint32_t)__mulhi(d, d);
-                if constexpr (DIM == 3) {
-                    d = (int)(um2 - myu[kk][DIM - 1]);
-                    r += (uint32_t)__mulhi(d, d);
-                }
-                m |= (r <= fthr) ? (1u << kk) : 0u;
+            for (int kk = 0; kk < KC; kk++) {  // survivor: bit KC-1-kk
+                const uint32_t v = __vabsdiffu4(umq, myq[kk]);
+                m = __funnelshift_l((uint32_t)__dp4a((int)v, (int)v, fthr), m, 1);
             }
             const int mine = __popc(m);
             int incl = mine;
@@ -777,7 +771,7 @@ __global__ void __launch_bounds__(kBfThreads, kBfThreads == 64 ? 12 : 8) k_box_s
             uint32_t wp = qa + 2u * (uint32_t)(incl - mine);
 #pragma unroll
             for (int kk = 0; kk < KC; kk++) {
-                if (m & (1u << kk)) {
+                if (m & (1u << (KC - 1 - kk))) {
                     bf_sts_u16(wp, (uint32_t)(kk * kBfThreads + tid));
                     wp += 2;
                 }
@@ -839,13 +833,9 @@ __global__ void __launch_bounds__(kBfThreads, kBfThreads == 64 ? 12 : 8) k_box_s
                 nacc++;
                 if (tid == (k & (kBfThreads - 1))) {  // owner refreshes its register copy
                     const int ki = k / kBfThreads;
+                    const uint32_t f = pack8(bf_fixed(xn[0], cs, fscale), bf_fixed(xn[1], cs, fscale), DIM == 3 ? bf_fixed(xn[2], cs, fscale) : 0u);
 #pragma unroll
-                    for (int kk = 0; kk < KC; kk++) {
-                        if (kk == ki) {
-#pragma unroll
-                            for (int a = 0; a < DIM; a++) myu[kk][a] = bf_fixed(xn[a], cs, fscale);
-                        }
-                    }
+                    for (int kk = 0; kk < KC; kk++) myq[kk] = kk == ki ? f : myq[kk];
                 }
             }
         }
@@ -1163,7 +1153,7 @@ int setup_geometry(BoxState *b, const double *box3) {
     b->cap = cap;
     b->smem = sizeof(double) * (size_t)b->dim * cap + 2 * (size_t)cap + 16;
     if (b->smem > 200 * 1024) return bfail(PMC_ERR_UNSUPPORTED, "stencil of %d candidates does not fit shared memory", cap);
-    // fast sweep kernel: cubic cells, stencil fits 64 threads x KC register candidates
+    // fast sweep kernel: cubic cells, stencil fits kBfThreads x KC register candidates
     b->fast_kc = 0;
     bool cubic = true;
     for (int a = 1; a < b->dim; a++) cubic = cubic && b->g.cs[a] == b->g.cs[0];

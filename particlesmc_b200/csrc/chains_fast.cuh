@@ -93,30 +93,6 @@ __host__ __device__ inline FastLayout fast_layout(int dim, int Npad, int ns, boo
 
 __device__ __forceinline__ uint32_t to_fixed32(double x, double scale) { return (uint32_t)__double2ull_rd(x * scale); }
 
-__device__ __forceinline__ uint32_t fixed_thr(double r2_scaled) {
-    const double t = r2_scaled * (1.0 + 1e-9) + 64.0;
-    return t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
-}
-
-// ---- 8-bit prefilter ---------------------------------------------------------------------------------------
-// A candidate is three bytes (top 8 bits of the fixed-point fraction of L per axis) in one register.  Per byte
-// VABSDIFF4.U8 gives |a - b| in [0, 255]; read as a SIGNED byte by IDP.4A that is the wrapped difference
-// (d >= 128 -> d - 256), so one IDP.4A.S8.S8 returns the minimum-image squared distance in units of (L/256)^2,
-// and its accumulator input subtracts the threshold: the sign bit is the verdict.  Three instructions per candidate
-// (VABSDIFF4, IDP.4A, SHF funnel) instead of 3 IADD + 3 IMAD.HI + compare + select on 32-bit coordinates.
-// Quantisation: both bytes are floors of exact scaled coordinates, so each component differs from the true one
-// by less than 1 unit and sum q_a^2 <= (r + sqrt(3))^2 -- the threshold carries that margin, so no in-range
-// candidate is ever dropped (survivors are then treated exactly, in fp64).
-__device__ __forceinline__ uint32_t pack8(uint32_t u0, uint32_t u1, uint32_t u2) {
-    return __byte_perm(__byte_perm(u0, u1, 0x4473), u2 >> 24, 0x5410);  // bytes: u0>>24, u1>>24, u2>>24, 0
-}
-// ~threshold (== -(thr + 1)): IDP.4A(t, t, ~thr) < 0  <=>  r2 <= thr
-__device__ __forceinline__ uint32_t neg_thr8(double r_units) {
-    const double t = r_units + 1.7320526;
-    const double t2 = t * t + 1.0;
-    return ~(t2 >= 60000.0 ? 60000u : (uint32_t)t2);
-}
-
 // wrapped-coordinate nearest image, squared, accumulated.  |a - L| == L - a and the square drops the sign, so this
 // is fmin(a, L - a)^2 bit for bit, issued as compare + subtract + select (fmin() costs six instructions in fp64:
 // DSETP.MIN + two selects + NaN fix-up + moves).
@@ -668,12 +644,14 @@ __global__ void __launch_bounds__(kFastThreads, 8) k_chain_sweep_mixed(const __g
             ((double *)(smem_raw + F.rcs))[tid] = sqrt(rc2);
         }
     }
-    uint32_t myu[kFastCand][DIM];
+    uint32_t myq[kFastCand];  // packed 8-bit prefilter coordinates of this thread's candidates (see pack8)
 #pragma unroll
     for (int k = 0; k < kFastCand; k++) {
         const int j = k * kFastThreads + tid;
+        uint32_t u[3] = {0u, 0u, 0u};
 #pragma unroll
-        for (int a = 0; a < DIM; a++) myu[k][a] = j < gNpad ? to_fixed32(gx[a * gNpad + j], fscale) : 0u;
+        for (int a = 0; a < DIM; a++) u[a] = j < gNpad ? to_fixed32(gx[a * gNpad + j], fscale) : 0u;
+        myq[k] = pack8(u[0], u[1], u[2]);
     }
     const double Tk = A.temp[c];
     double E = A.energy[c];
@@ -726,10 +704,7 @@ __global__ void __launch_bounds__(kFastThreads, 8) k_chain_sweep_mixed(const __g
             const double hd = 0.5 * sqrt(tr.delta[0] * tr.delta[0] + tr.delta[1] * tr.delta[1] + tr.delta[2] * tr.delta[2]);
             const double *rcs = (const double *)(smem_raw + F.rcs);
 #pragma unroll
-            for (int s = 0; s < PMC_MAX_SPECIES; s++) {
-                const double r = rcs[s] + hd;
-                rt[s] = fixed_thr(r * r * (fscale / L));
-            }
+            for (int s = 0; s < PMC_MAX_SPECIES; s++) rt[s] = neg_thr8((rcs[s] + hd) * fscale * 0x1p-24);
         }
         __syncthreads();
 
@@ -743,12 +718,13 @@ __global__ void __launch_bounds__(kFastThreads, 8) k_chain_sweep_mixed(const __g
             const uint32_t si = lds_u8(sb + F.sp + (uint32_t)i);
             const uint32_t un0 = uo0 + (uint32_t)di0, un1 = uo1 + (uint32_t)di1, un2 = uo2 + (uint32_t)di2;
             const uint32_t um0 = uo0 + (uint32_t)(di0 >> 1), um1 = uo1 + (uint32_t)(di1 >> 1), um2 = uo2 + (uint32_t)(di2 >> 1);
-            const uint32_t fthr = lds_u32(ra + 64 + 4u * si);
+            const int fthr = (int)lds_u32(ra + 64 + 4u * si);
+            const uint32_t umq = pack8(um0, um1, um2);
             uint32_t m8 = 0;
 #pragma unroll
-            for (int k = 0; k < kFastCand; k++) {
-                const uint32_t r = dist2_u32<DIM>(um0, um1, um2, myu[k][0], myu[k][1], DIM == 3 ? myu[k][DIM - 1] : 0u);
-                m8 |= (r <= fthr) ? (1u << k) : 0u;
+            for (int k = 0; k < kFastCand; k++) {  // survivor: bit kFastCand-1-k
+                const uint32_t t = __vabsdiffu4(umq, myq[k]);
+                m8 = __funnelshift_l((uint32_t)__dp4a((int)t, (int)t, fthr), m8, 1);
             }
             const int mine = __popc(m8);
             int incl = mine;
@@ -761,7 +737,7 @@ __global__ void __launch_bounds__(kFastThreads, 8) k_chain_sweep_mixed(const __g
             uint32_t wp = qa + 2u * (uint32_t)(incl - mine);
 #pragma unroll
             for (int k = 0; k < kFastCand; k++) {
-                if (m8 & (1u << k)) {
+                if (m8 & (1u << (kFastCand - 1 - k))) {
                     sts_u16(wp, (uint32_t)(k * kFastThreads + tid));
                     wp += 2;
                 }
@@ -804,18 +780,11 @@ __global__ void __launch_bounds__(kFastThreads, 8) k_chain_sweep_mixed(const __g
                 E += dE;
                 if (tid == (i & (kFastThreads - 1))) {
                     const int ki = i >> 7;
+                    const uint32_t f = pack8(un0, un1, un2);
 #pragma unroll
-                    for (int k = 0; k < kFastCand; k++) {
-                        if (k == ki) {
-                            myu[k][0] = un0;
-                            myu[k][1] = un1;
-                            if constexpr (DIM == 3) myu[k][DIM - 1] = un2;
-                        }
-                    }
+                    for (int k = 0; k < kFastCand; k++) myq[k] = k == ki ? f : myq[k];
                 }
-            }
-            if (tid == 0) {
-                if (acc) {  // image counters: the fixed-point add wrapped around the box
+                if (tid == 32) {  // image counters: the fixed-point add wrapped around the box
                     const int w0 = (di0 > 0 && un0 < uo0) - (di0 < 0 && un0 > uo0);
                     const int w1 = (di1 > 0 && un1 < uo1) - (di1 < 0 && un1 > uo1);
                     const int w2 = (di2 > 0 && un2 < uo2) - (di2 < 0 && un2 > uo2);
@@ -823,6 +792,8 @@ __global__ void __launch_bounds__(kFastThreads, 8) k_chain_sweep_mixed(const __g
                     if (w1) atomicAdd(&gimg[gNpad + i], w1);
                     if (DIM == 3 && w2) atomicAdd(&gimg[2 * gNpad + i], w2);
                 }
+            }
+            if (tid == 64) {  // bookkeeping is spread over warps, as in k_chain_sweep_fast
                 unsigned long long *scnt = (unsigned long long *)(smem_raw + F.cnt);
                 const int m = (int)lds_u32(ra + 48);
                 scnt[m] += 1ull;

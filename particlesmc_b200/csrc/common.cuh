@@ -108,4 +108,23 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+// ---- 8-bit prefilter ---------------------------------------------------------------------------------------
+// A candidate is three bytes (top 8 bits of the fixed-point fraction of L per axis) in one register.  Per byte
+// VABSDIFF4.U8 gives |a - b| in [0, 255]; read as a SIGNED byte by IDP.4A that is the wrapped difference
+// (d >= 128 -> d - 256), so one IDP.4A.S8.S8 returns the minimum-image squared distance in units of (L/256)^2,
+// and its accumulator input subtracts the threshold: the sign bit is the verdict.  Three instructions per candidate
+// (VABSDIFF4, IDP.4A, SHF funnel) instead of 3 IADD + 3 IMAD.HI + compare + select on 32-bit coordinates.
+// Quantisation: both bytes are floors of exact scaled coordinates, so each component differs from the true one
+// by less than 1 unit and sum q_a^2 <= (r + sqrt(3))^2 -- the threshold carries that margin, so no in-range
+// candidate is ever dropped (survivors are then treated exactly, in fp64).
+__device__ __forceinline__ uint32_t pack8(uint32_t u0, uint32_t u1, uint32_t u2) {
+    return __byte_perm(__byte_perm(u0, u1, 0x4473), u2 >> 24, 0x5410);  // bytes: u0>>24, u1>>24, u2>>24, 0
+}
+// ~threshold (== -(thr + 1)): IDP.4A(t, t, ~thr) < 0  <=>  r2 <= thr
+__device__ __forceinline__ uint32_t neg_thr8(double r_units) {
+    const double t = r_units + 1.7320526;
+    const double t2 = t * t + 1.0;
+    return ~(t2 >= 60000.0 ? 60000u : (uint32_t)t2);
+}
+
 }  // namespace pmc
