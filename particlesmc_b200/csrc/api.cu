@@ -303,7 +303,7 @@ int sweep(pmc_ctx *c, int64_t n_trials, const pmc_trial *d_replay, pmc_trial *d_
         CU(pmc::launch_chain_sweep_mixed(c->cfg.dim, c->cfg.model_kind, c->cfg.n_chains,
                                          pmc::chain_mixed_smem_bytes(c->cfg.dim, c->Npad), a, c->stream));
     } else if (fastk) {
-        const size_t fs = pmc::chain_fast_smem_bytes(c->cfg.dim, c->Npad, c->cfg.n_species, any_swap);
+        const size_t fs = pmc::chain_fast_smem_bytes(c->cfg.dim, c->Npad, c->cfg.model_kind, any_swap);
         if (fs != c->fast_smem) {
             CU(pmc::configure_chain_fast(c->cfg.dim, c->cfg.model_kind, c->Npad, any_swap, fs));
             c->fast_smem = fs;

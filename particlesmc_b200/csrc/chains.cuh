@@ -74,7 +74,7 @@ cudaError_t launch_chain_energy(int dim, int model, bool mol, int M, size_t smem
                                 cudaStream_t st);
 // hand-scheduled kernel for Atoms + Displacement-only pools + cubic boxes + N <= 1024 (chains_fast.cuh)
 bool chain_fast_supported(int dim, int Npad, int threads);
-size_t chain_fast_smem_bytes(int dim, int Npad, int ns, bool swaps);
+size_t chain_fast_smem_bytes(int dim, int Npad, int model, bool swaps);
 cudaError_t configure_chain_fast(int dim, int model, int Npad, bool swaps, size_t smem);
 cudaError_t launch_chain_sweep_fast(int dim, int model, int M, size_t smem, const ChainArgs &a, cudaStream_t st);
 // PMC_MIXED variant of the fast kernel (fp32 pair terms on fixed-point coordinates, fp64 accumulation)

@@ -36,8 +36,9 @@ bool chain_fast_supported(int dim, int Npad, int threads) {
 
 static int fast_npad(int Npad) { return Npad <= 256 ? 256 : (Npad <= 512 ? 512 : (Npad <= 1024 ? 1024 : 2048)); }
 
-size_t chain_fast_smem_bytes(int dim, int Npad, int, bool swaps) {
-    return fast::fast_layout(dim, fast_npad(Npad), PMC_MAX_SPECIES, swaps).total;
+size_t chain_fast_smem_bytes(int dim, int Npad, int model, bool swaps) {
+    const bool full_par = !(model == PMC_MODEL_LJ || model == PMC_MODEL_KG);
+    return fast::fast_layout(dim, fast_npad(Npad), PMC_MAX_SPECIES, swaps, full_par).total;
 }
 
 template <typename F>

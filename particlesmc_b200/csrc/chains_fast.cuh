@@ -67,7 +67,7 @@ __device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) {
 struct FastLayout {
     uint32_t x, sp, q, cp, rec, red, cnt, par, rcs, spids, heads, spoff, total;
 };
-__host__ __device__ inline FastLayout fast_layout(int dim, int Npad, int ns, bool swaps = false) {
+__host__ __device__ inline FastLayout fast_layout(int dim, int Npad, int ns, bool swaps, bool full_par) {
     FastLayout f;
     uint32_t o = 0;
     auto take = [&](uint32_t bytes) {
@@ -82,7 +82,7 @@ __host__ __device__ inline FastLayout fast_layout(int dim, int Npad, int ns, boo
     f.rec = take((uint32_t)kRecBytes * kFastBatch);        // parked proposals
     f.red = take(8u * 2 * kFastWarps);
     f.cnt = take(8u * 2 * PMC_MAX_MOVES);
-    f.par = take(8u * ns * ns * PMC_NPAR);                 // full parameter table (non-LJ models)
+    f.par = take(full_par ? 8u * ns * ns * PMC_NPAR : 0u); // full parameter table (non-LJ models only: 7 CTAs/SM need < 32 KB)
     f.rcs = take(8u * PMC_MAX_SPECIES);                    // largest cutoff radius per species of the moved particle
     f.spids = take(swaps ? 2u * (uint32_t)Npad : 0u);      // SpeciesList (src/utils.jl:31-49), DiscreteSwap only
     f.heads = take(swaps ? 2u * (uint32_t)Npad : 0u);
@@ -112,7 +112,7 @@ __device__ __forceinline__ double wrap_once(double x, double L) {
 // NPAD (compile time): padded particle count of the shared-memory planes, one of 256 / 512 / 1024 (/ 2048 in 2-D); makes every
 // shared-memory offset a constant and fixes the number of register-resident candidates per thread.
 template <int DIM, int MODEL, int NPAD, bool SWAPS, int NT = kFastThreads>
-__global__ void __launch_bounds__(NT, NT == 128 ? 6 : 7) k_chain_sweep_fast(const __grid_constant__ ChainArgs A) {
+__global__ void __launch_bounds__(NT, SWAPS ? 6 : 7) k_chain_sweep_fast(const __grid_constant__ ChainArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int kThreads = NT, kWarps = NT / 32;  // CTA size is a compile-time constant of this kernel
     constexpr int kFastCand = NPAD / kThreads;
@@ -122,7 +122,8 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 6 : 7) k_chain_sweep_fast(cons
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int c = blockIdx.x;
     const int N = A.N, gNpad = A.Npad, ns = A.ns;  // gNpad: stride of the GLOBAL arrays (multiple of 32)
-    const FastLayout F = fast_layout(DIM, Npad, PMC_MAX_SPECIES, SWAPS);
+    constexpr bool kFullPar = !(MODEL == PMC_MODEL_LJ || MODEL == PMC_MODEL_KG);
+    const FastLayout F = fast_layout(DIM, Npad, PMC_MAX_SPECIES, SWAPS, kFullPar);
     const uint32_t sb = (uint32_t)__cvta_generic_to_shared(smem_raw);
     const uint32_t nb8 = 8u * (uint32_t)Npad;  // byte stride between coordinate planes
 
@@ -138,7 +139,8 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 6 : 7) k_chain_sweep_fast(cons
         const uint8_t *gsp = A.sp + (size_t)c * gNpad;
         for (int k = tid; k < Npad; k += kThreads) ssp[k] = k < gNpad ? gsp[k] : 0;
         double *spar = (double *)(smem_raw + F.par), *scp = (double *)(smem_raw + F.cp);
-        for (int k = tid; k < ns * ns * PMC_NPAR; k += kThreads) spar[k] = A.par[k];
+        if constexpr (kFullPar)
+            for (int k = tid; k < ns * ns * PMC_NPAR; k += kThreads) spar[k] = A.par[k];
         for (int k = tid; k < ns * ns; k += kThreads) {
             scp[4 * k + 0] = A.par[k * PMC_NPAR + PMC_P_RCUT2];
             scp[4 * k + 1] = A.par[k * PMC_NPAR + PMC_P_EPS];
