@@ -88,8 +88,10 @@ typedef struct pmc_config {
                              index, so results do not depend on how chains are sharded over GPUs */
     int32_t threads;      /* CTA size of the sweep kernels; 0 = library default */
     int32_t prefilter;    /* chain kernels: 0 = integer fixed-point distance prefilter when all boxes are cubic
-                             (same fp64 pair terms, far fewer fp64 distance evaluations); -1 = always visit every
-                             candidate in fp64 (the reference-equivalent amount of work) */
+                             (same fp64 pair terms, far fewer fp64 distance evaluations), with four consecutive
+                             trials of a chain evaluated speculatively per round where supported (same sequential
+                             chain, see csrc/chains_spec.cuh); 1 = prefilter, one trial at a time; -1 = always
+                             visit every candidate in fp64 (the reference-equivalent amount of work) */
     int32_t reserved[4];
 } pmc_config;
 

@@ -14,7 +14,7 @@ ROOT = os.path.dirname(_HERE)
 CSRC = os.path.join(_HERE, "csrc")
 LIB_DIR = os.path.join(_HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libpmc_b200.so")
-SOURCES = ["api.cu", "chains.cu", "chains_fast.cu", "box.cu"]
+SOURCES = ["api.cu", "chains.cu", "chains_fast.cu", "chains_spec.cu", "box.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++",

@@ -160,7 +160,7 @@ struct pmc_ctx {
     unsigned long long seed = 0, t0 = 0;
     bool model_set = false, uploaded = false, energy_set = false, bonds_set = false;
     int64_t launches = 0;
-    size_t sweep_smem = 0, sweep_smem_filter = 0, energy_smem = 0, fast_smem = 0;
+    size_t sweep_smem = 0, sweep_smem_filter = 0, energy_smem = 0, fast_smem = 0, spec_smem = 0;
     bool sweep_swap_cfg = false;
     bool cubic = true;  // every uploaded chain has a cubic box (enables the fixed-point prefilter)
     pmc::BoxState *boxst = nullptr;
@@ -302,6 +302,13 @@ int sweep(pmc_ctx *c, int64_t n_trials, const pmc_trial *d_replay, pmc_trial *d_
             return fail(PMC_ERR_UNSUPPORTED, "PMC_MIXED needs a cubic box, a Displacement-only pool and %d threads per CTA", 128);
         CU(pmc::launch_chain_sweep_mixed(c->cfg.dim, c->cfg.model_kind, c->cfg.n_chains,
                                          pmc::chain_mixed_smem_bytes(c->cfg.dim, c->Npad), a, c->stream));
+    } else if (fastk && !any_swap && c->cfg.prefilter == 0 && pmc::chain_spec_supported(c->Npad, c->threads)) {
+        const size_t ss = pmc::chain_spec_smem_bytes(c->cfg.dim, c->Npad, c->cfg.model_kind);
+        if (ss != c->spec_smem) {
+            CU(pmc::configure_chain_spec(c->cfg.dim, c->cfg.model_kind, c->Npad, ss));
+            c->spec_smem = ss;
+        }
+        CU(pmc::launch_chain_sweep_spec(c->cfg.dim, c->cfg.model_kind, c->cfg.n_chains, ss, a, c->stream));
     } else if (fastk) {
         const size_t fs = pmc::chain_fast_smem_bytes(c->cfg.dim, c->Npad, c->cfg.model_kind, any_swap);
         if (fs != c->fast_smem) {

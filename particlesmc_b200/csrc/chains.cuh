@@ -77,6 +77,11 @@ bool chain_fast_supported(int dim, int Npad, int threads);
 size_t chain_fast_smem_bytes(int dim, int Npad, int model, bool swaps);
 cudaError_t configure_chain_fast(int dim, int model, int Npad, bool swaps, size_t smem);
 cudaError_t launch_chain_sweep_fast(int dim, int model, int M, size_t smem, const ChainArgs &a, cudaStream_t st);
+// speculative kernel, one warp per trial (chains_spec.cuh): Atoms + Displacement-only pools + cubic boxes + N <= 1024
+bool chain_spec_supported(int Npad, int threads);
+size_t chain_spec_smem_bytes(int dim, int Npad, int model);
+cudaError_t configure_chain_spec(int dim, int model, int Npad, size_t smem);
+cudaError_t launch_chain_sweep_spec(int dim, int model, int M, size_t smem, const ChainArgs &a, cudaStream_t st);
 // PMC_MIXED variant of the fast kernel (fp32 pair terms on fixed-point coordinates, fp64 accumulation)
 size_t chain_mixed_smem_bytes(int dim, int Npad);
 cudaError_t launch_chain_sweep_mixed(int dim, int model, int M, size_t smem, const ChainArgs &a, cudaStream_t st);

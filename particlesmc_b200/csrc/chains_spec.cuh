@@ -1,0 +1,405 @@
+// chains_spec.cuh -- speculative sweep kernel for the dominant PMC_MODE_CHAINS case (Atoms, Displacement-only pool,
+// cubic box, N <= 1024): ONE WARP PER TRIAL, four consecutive trials of a chain in flight per round.
+//
+// k_chain_sweep_fast (chains_fast.cuh) spends one CTA on one trial: the four warps each scan a quarter of the
+// candidates, but everything around the scan -- record and position loads, wrapping, the compaction scan, the block
+// reduction, the barrier, the commit -- is replicated in all four warps, and the fp64 pass runs with ~21 of 32 lanes.
+// Here warp w of the CTA evaluates trial t + w of the SAME chain against the current state, alone: it scans all
+// candidates (32 per lane, packed 8-bit coordinates in registers), compacts the survivors into its own queue, runs
+// the fp64 pass at ~86 % lane utilisation and reduces with shuffles only.  After ONE barrier per round every thread
+// resolves the four results in trial order (identical arithmetic in every thread, so no second barrier):
+//
+//   trial t+w stands  <=>  no earlier trial of this round was ACCEPTED with its particle inside the filter sphere of
+//                          t+w, tested on the old AND the new position with the very 8-bit test the scan uses.
+//
+// The survivors of a trial are defined by that test, so a trial that stands has exactly the survivor queue -- same
+// members, same order, same positions -- it would have had if it had been evaluated after the earlier trials were
+// committed: its dE is bit-identical to the sequential one.  The first trial that does not stand ends the round; it and
+// the ones after it are simply evaluated again in the next round.  The Markov chain is therefore the SEQUENTIAL chain
+// of the reference (src/moves.jl:11-20 applied one move at a time), not a checkerboard approximation of it; what
+// speculation costs is the re-evaluated trials (about 3 % per pair of trials at 35 % acceptance: 3.7 of 4 trials
+// retire per round).
+#pragma once
+#include "chains.cuh"
+#include "chains_fast.cuh"
+#include "common.cuh"
+#include "rng.cuh"
+
+namespace pmc {
+namespace spec {
+
+using namespace pmc::fast;
+
+constexpr int kSpecThreads = 128;
+constexpr int kSpecWarps = kSpecThreads / 32;  // speculation depth
+constexpr int kSpecBatch = 64;                 // parked proposals
+constexpr int kSpecQCap = 256;                 // survivor queue entries per warp (beyond: unqueued fallback)
+constexpr int kPubBytes = 64;                  // published result of one trial
+
+__device__ __forceinline__ void lds_u32x4(uint32_t a, uint32_t &v0, uint32_t &v1, uint32_t &v2, uint32_t &v3) {
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(a) : "memory");
+}
+__device__ __forceinline__ void sts_u32x4(uint32_t a, uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v0), "r"(v1), "r"(v2), "r"(v3) : "memory");
+}
+__device__ __forceinline__ void sts_f64x2(uint32_t a, double v0, double v1) {
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(v0), "d"(v1) : "memory");
+}
+
+struct SpecLayout {
+    uint32_t x, sp, q, cp, rec, pub, cnt, par, rcs, total;
+};
+__host__ __device__ inline SpecLayout spec_layout(int dim, int Npad, bool full_par) {
+    SpecLayout f;
+    uint32_t o = 0;
+    auto take = [&](uint32_t bytes) {
+        uint32_t p = o;
+        o += (bytes + 15u) & ~15u;
+        return p;
+    };
+    f.x = take(8u * dim * Npad);
+    f.sp = take(Npad);
+    f.q = take(2u * kSpecQCap * kSpecWarps);
+    f.cp = take(32u * PMC_MAX_SPECIES * PMC_MAX_SPECIES);
+    f.rec = take((uint32_t)kRecBytes * kSpecBatch);
+    f.pub = take(2u * kPubBytes * kSpecWarps);  // two alternating sets
+    f.cnt = take(8u * 2 * PMC_MAX_MOVES);
+    f.par = take(full_par ? 8u * PMC_MAX_SPECIES * PMC_MAX_SPECIES * PMC_NPAR : 0u);
+    f.rcs = take(8u * PMC_MAX_SPECIES);
+    f.total = o;
+    return f;
+}
+
+// myq[ki] = v for a warp-uniform ki: one indirect branch instead of KC predicated selects
+template <int KC>
+__device__ __forceinline__ void set_slot(uint32_t (&myq)[KC], int ki, uint32_t v, bool mine) {
+    switch (ki) {
+    case 0: if constexpr (KC > 0) { if (mine) myq[0 < KC ? 0 : 0] = v; } break;
+    case 1: if constexpr (KC > 1) { if (mine) myq[1 < KC ? 1 : 0] = v; } break;
+    case 2: if constexpr (KC > 2) { if (mine) myq[2 < KC ? 2 : 0] = v; } break;
+    case 3: if constexpr (KC > 3) { if (mine) myq[3 < KC ? 3 : 0] = v; } break;
+    case 4: if constexpr (KC > 4) { if (mine) myq[4 < KC ? 4 : 0] = v; } break;
+    case 5: if constexpr (KC > 5) { if (mine) myq[5 < KC ? 5 : 0] = v; } break;
+    case 6: if constexpr (KC > 6) { if (mine) myq[6 < KC ? 6 : 0] = v; } break;
+    case 7: if constexpr (KC > 7) { if (mine) myq[7 < KC ? 7 : 0] = v; } break;
+    case 8: if constexpr (KC > 8) { if (mine) myq[8 < KC ? 8 : 0] = v; } break;
+    case 9: if constexpr (KC > 9) { if (mine) myq[9 < KC ? 9 : 0] = v; } break;
+    case 10: if constexpr (KC > 10) { if (mine) myq[10 < KC ? 10 : 0] = v; } break;
+    case 11: if constexpr (KC > 11) { if (mine) myq[11 < KC ? 11 : 0] = v; } break;
+    case 12: if constexpr (KC > 12) { if (mine) myq[12 < KC ? 12 : 0] = v; } break;
+    case 13: if constexpr (KC > 13) { if (mine) myq[13 < KC ? 13 : 0] = v; } break;
+    case 14: if constexpr (KC > 14) { if (mine) myq[14 < KC ? 14 : 0] = v; } break;
+    case 15: if constexpr (KC > 15) { if (mine) myq[15 < KC ? 15 : 0] = v; } break;
+    case 16: if constexpr (KC > 16) { if (mine) myq[16 < KC ? 16 : 0] = v; } break;
+    case 17: if constexpr (KC > 17) { if (mine) myq[17 < KC ? 17 : 0] = v; } break;
+    case 18: if constexpr (KC > 18) { if (mine) myq[18 < KC ? 18 : 0] = v; } break;
+    case 19: if constexpr (KC > 19) { if (mine) myq[19 < KC ? 19 : 0] = v; } break;
+    case 20: if constexpr (KC > 20) { if (mine) myq[20 < KC ? 20 : 0] = v; } break;
+    case 21: if constexpr (KC > 21) { if (mine) myq[21 < KC ? 21 : 0] = v; } break;
+    case 22: if constexpr (KC > 22) { if (mine) myq[22 < KC ? 22 : 0] = v; } break;
+    case 23: if constexpr (KC > 23) { if (mine) myq[23 < KC ? 23 : 0] = v; } break;
+    case 24: if constexpr (KC > 24) { if (mine) myq[24 < KC ? 24 : 0] = v; } break;
+    case 25: if constexpr (KC > 25) { if (mine) myq[25 < KC ? 25 : 0] = v; } break;
+    case 26: if constexpr (KC > 26) { if (mine) myq[26 < KC ? 26 : 0] = v; } break;
+    case 27: if constexpr (KC > 27) { if (mine) myq[27 < KC ? 27 : 0] = v; } break;
+    case 28: if constexpr (KC > 28) { if (mine) myq[28 < KC ? 28 : 0] = v; } break;
+    case 29: if constexpr (KC > 29) { if (mine) myq[29 < KC ? 29 : 0] = v; } break;
+    case 30: if constexpr (KC > 30) { if (mine) myq[30 < KC ? 30 : 0] = v; } break;
+    case 31: if constexpr (KC > 31) { if (mine) myq[31 < KC ? 31 : 0] = v; } break;
+    default: break;
+    }
+}
+
+template <int DIM, int MODEL, int NPAD>
+__global__ void __launch_bounds__(kSpecThreads, 5) k_chain_sweep_spec(const __grid_constant__ ChainArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int KC = NPAD / 32;  // candidates per lane: candidate j = k * 32 + lane, held by EVERY warp
+    static_assert(KC >= 1 && KC <= 32, "survivor masks are 32 bits");
+    constexpr int Npad = NPAD;
+    constexpr int kImgThread = 32, kCntThread = 64;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int c = blockIdx.x;
+    const int N = A.N, gNpad = A.Npad, ns = A.ns;
+    constexpr bool kFullPar = !(MODEL == PMC_MODEL_LJ || MODEL == PMC_MODEL_KG);
+    const SpecLayout F = spec_layout(DIM, Npad, kFullPar);
+    const uint32_t sb = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    const uint32_t nb8 = 8u * (uint32_t)Npad;
+
+    // ---- load chain state -----------------------------------------------------------------------------
+    const double L = A.box[c * 3], hL = 0.5 * L;
+    const double fscale = 4294967296.0 / L;
+    double *gx = A.x + (size_t)c * DIM * gNpad;
+    {
+        double *sx = (double *)(smem_raw + F.x);
+        for (int a = 0; a < DIM; a++)
+            for (int k = tid; k < Npad; k += kSpecThreads) sx[a * Npad + k] = k < gNpad ? gx[a * gNpad + k] : 0.0;
+        uint8_t *ssp = smem_raw + F.sp;
+        const uint8_t *gsp = A.sp + (size_t)c * gNpad;
+        for (int k = tid; k < Npad; k += kSpecThreads) ssp[k] = k < gNpad ? gsp[k] : 0;
+        double *scp = (double *)(smem_raw + F.cp);
+        if constexpr (kFullPar) {
+            double *spar = (double *)(smem_raw + F.par);
+            for (int k = tid; k < ns * ns * PMC_NPAR; k += kSpecThreads) spar[k] = A.par[k];
+        }
+        for (int k = tid; k < ns * ns; k += kSpecThreads) {
+            scp[4 * k + 0] = A.par[k * PMC_NPAR + PMC_P_RCUT2];
+            scp[4 * k + 1] = A.par[k * PMC_NPAR + PMC_P_EPS];
+            scp[4 * k + 2] = A.par[k * PMC_NPAR + PMC_P_SIG2];
+            scp[4 * k + 3] = A.par[k * PMC_NPAR + PMC_P_SHIFT];
+        }
+        unsigned long long *scnt = (unsigned long long *)(smem_raw + F.cnt);
+        if (tid < 2 * PMC_MAX_MOVES) scnt[tid] = 0ull;
+        if (tid < PMC_MAX_SPECIES) {  // largest cutoff radius per species of the moved particle (filter sphere)
+            double rc2 = 0.0;
+            for (int b = 0; b < ns; b++) rc2 = fmax(rc2, A.par[((tid < ns ? tid : 0) * ns + b) * PMC_NPAR + PMC_P_RCUT2]);
+            ((double *)(smem_raw + F.rcs))[tid] = sqrt(rc2);
+        }
+    }
+    uint32_t myq[KC];  // packed 8-bit coordinates (common.cuh) of candidates k * 32 + lane
+#pragma unroll
+    for (int k = 0; k < KC; k++) {
+        const int j = k * 32 + lane;
+        uint32_t u[3] = {0u, 0u, 0u};
+#pragma unroll
+        for (int a = 0; a < DIM; a++) u[a] = j < gNpad ? to_fixed32(gx[a * gNpad + j], fscale) : 0u;
+        myq[k] = pack8(u[0], u[1], u[2]);
+    }
+    const double Tk = A.temp[c];
+    double E = A.energy[c];
+    const uint32_t k0 = (uint32_t)A.seed, k1 = (uint32_t)(A.seed >> 32);
+    const uint32_t gchain = (uint32_t)(A.chain_offset + c);
+    int32_t *gimg = A.img + (size_t)c * DIM * gNpad;
+    const uint32_t qa = sb + F.q + (uint32_t)warp * (2u * kSpecQCap);
+    uint32_t slot = 0;
+
+    for (long long tb = 0; tb < A.n_trials; tb += kSpecBatch) {
+        const int nb = (int)min((long long)kSpecBatch, A.n_trials - tb);
+        __syncthreads();
+        // ---- proposals of trials tb .. tb+nb-1, parked in shared memory (same stream as every other kernel) ----
+        if (tid < nb) {
+            const long long q = tb + tid;
+            pmc_trial tr;
+            if (A.replay) {
+                tr = A.replay[(size_t)c * A.n_trials + q];
+            } else {
+                const unsigned long long t = A.t0 + (unsigned long long)q;
+                const Philox4 a = philox4x32_10((uint32_t)t, (uint32_t)(t >> 32), gchain, 0u, k0, k1);
+                const Philox4 b = philox4x32_10((uint32_t)t, (uint32_t)(t >> 32), gchain, 1u, k0, k1);
+                const double um = (double)a.v[0] * 0x1p-32;
+                int m = A.n_moves - 1;
+                for (int k = A.n_moves - 2; k >= 0; k--)
+                    if (um < A.mv_cum[k]) m = k;
+                float z0, z1, z2, z3;
+                box_muller(b.v[0], b.v[1], z0, z1);
+                box_muller(b.v[2], b.v[3], z2, z3);
+                const float sg = A.mv_sigma[m];
+                tr.u = uniform53(a.v[2], a.v[3]);
+                tr.move = m;
+                tr.kind = PMC_MOVE_DISPLACEMENT;
+                tr.i = (int)bounded(a.v[1], (uint32_t)N);
+                tr.j = -1;
+                tr.delta[0] = (double)(sg * z0);
+                tr.delta[1] = (double)(sg * z1);
+                tr.delta[2] = (DIM == 3) ? (double)(sg * z2) : 0.0;
+                if (A.trace) A.trace[(size_t)c * A.n_trials + q] = tr;
+            }
+            // record: f64 delta[3], f64 thr | s32 dint[3], s32 i | s32 m, pad[3] | u32 ~thr8[4]
+            unsigned char *rec = smem_raw + F.rec + (size_t)kRecBytes * tid;
+            double *rd = (double *)rec;
+            int *ri = (int *)(rec + 32);
+            uint32_t *rt = (uint32_t *)(rec + 64);
+            rd[0] = tr.delta[0];
+            rd[1] = tr.delta[1];
+            rd[2] = tr.delta[2];
+            rd[3] = A.exact_exp ? tr.u : -Tk * log(tr.u);
+            ri[0] = (int)__double2ll_rn(tr.delta[0] * fscale);
+            ri[1] = (int)__double2ll_rn(tr.delta[1] * fscale);
+            ri[2] = (int)__double2ll_rn(tr.delta[2] * fscale);
+            ri[3] = tr.i;
+            ri[4] = tr.move;
+            const double hd = 0.5 * sqrt(tr.delta[0] * tr.delta[0] + tr.delta[1] * tr.delta[1] + tr.delta[2] * tr.delta[2]);
+            const double *rcs = (const double *)(smem_raw + F.rcs);
+#pragma unroll
+            for (int s = 0; s < PMC_MAX_SPECIES; s++) rt[s] = neg_thr8((rcs[s] + hd) * fscale * 0x1p-24);
+        }
+        __syncthreads();
+
+        int cur = 0;
+        while (cur < nb) {  // one round: up to four consecutive trials, one per warp
+            const int nspec = min(kSpecWarps, nb - cur);
+            const uint32_t pa = sb + F.pub + (uint32_t)(kPubBytes * kSpecWarps) * slot;
+            if (warp < nspec) {
+                // ---- evaluate trial cur + warp against the current state (this warp alone) ---------------------
+                const uint32_t ra = sb + F.rec + (uint32_t)kRecBytes * (uint32_t)(cur + warp);
+                double d0, d1, d2, thr;
+                int di0, di1, di2, i;
+                lds_f64x2(ra, d0, d1);
+                lds_f64x2(ra + 16, d2, thr);
+                lds_s32x4(ra + 32, di0, di1, di2, i);
+                const uint32_t xa = sb + F.x + 8u * (uint32_t)i;
+                double xo[3], xn[3];
+                xo[0] = lds_f64(xa);
+                xo[1] = lds_f64(xa + nb8);
+                xo[2] = (DIM == 3) ? lds_f64(xa + 2 * nb8) : 0.0;
+                const uint32_t si = lds_u8(sb + F.sp + (uint32_t)i);
+                const double t0 = xo[0] + d0, t1 = xo[1] + d1, t2 = xo[2] + d2;
+                xn[0] = wrap_once(t0, L);
+                xn[1] = wrap_once(t1, L);
+                xn[2] = (DIM == 3) ? wrap_once(t2, L) : 0.0;
+                const uint32_t uo0 = to_fixed32(xo[0], fscale), uo1 = to_fixed32(xo[1], fscale), uo2 = (DIM == 3) ? to_fixed32(xo[2], fscale) : 0u;
+                const uint32_t umq = pack8(uo0 + (uint32_t)(di0 >> 1), uo1 + (uint32_t)(di1 >> 1), uo2 + (uint32_t)(di2 >> 1));
+                const int fthr = (int)lds_u32(ra + 64 + 4u * si);
+                uint32_t m = 0;
+#pragma unroll
+                for (int k = 0; k < KC; k++) {  // survivor: bit KC-1-k
+                    const uint32_t t = __vabsdiffu4(umq, myq[k]);
+                    m = __funnelshift_l((uint32_t)__dp4a((int)t, (int)t, fthr), m, 1);
+                }
+                const int mine = __popc(m);
+                int incl = mine;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                    incl += (lane >= o) ? t : 0;
+                }
+                const int total = __shfl_sync(0xffffffffu, incl, 31);
+                const uint32_t prow = si * (uint32_t)ns;
+                double part = 0.0;
+                auto term = [&](uint32_t j) {
+                    if (j < (uint32_t)N && j != (uint32_t)i) {
+                        const uint32_t ja = sb + F.x + 8u * j;
+                        const double xj0 = lds_f64(ja), xj1 = lds_f64(ja + nb8);
+                        double r2o = mi_acc(xo[0], xj0, L, hL, 0.0), r2n = mi_acc(xn[0], xj0, L, hL, 0.0);
+                        r2o = mi_acc(xo[1], xj1, L, hL, r2o);
+                        r2n = mi_acc(xn[1], xj1, L, hL, r2n);
+                        if constexpr (DIM == 3) {
+                            const double xj2 = lds_f64(ja + 2 * nb8);
+                            r2o = mi_acc(xo[2], xj2, L, hL, r2o);
+                            r2n = mi_acc(xn[2], xj2, L, hL, r2n);
+                        }
+                        const uint32_t sj = lds_u8(sb + F.sp + j);
+                        if constexpr (MODEL == PMC_MODEL_LJ || MODEL == PMC_MODEL_KG) {
+                            double rc2, eps4, sig2, shift;
+                            const uint32_t pp = sb + F.cp + 32u * (prow + sj);
+                            lds_f64x2(pp, rc2, eps4);
+                            lds_f64x2(pp + 16, sig2, shift);
+                            const double uo = lj_core(r2o, eps4, sig2) - shift;
+                            const double un = lj_core(r2n, eps4, sig2) - shift;
+                            part += (r2n <= rc2 ? un : 0.0) - (r2o <= rc2 ? uo : 0.0);
+                        } else {
+                            const double *p = (const double *)(smem_raw + F.par) + (prow + sj) * PMC_NPAR;
+                            const double rc2 = p[PMC_P_RCUT2];
+                            if (r2o <= rc2) part -= pair_potential<MODEL>(p, r2o);
+                            if (r2n <= rc2) part += pair_potential<MODEL>(p, r2n);
+                        }
+                    }
+                };
+                if (total <= kSpecQCap) {
+                    // compaction: each lane appends its survivors (ascending candidate index) at its scan offset
+                    uint32_t wp = qa + 2u * (uint32_t)(incl - mine);
+                    uint32_t mm = m;
+                    while (mm) {
+                        const int b = 31 - __clz(mm);
+                        mm ^= 1u << b;
+                        sts_u16(wp, (uint32_t)((KC - 1 - b) * 32 + lane));
+                        wp += 2;
+                    }
+                    __syncwarp();
+                    for (int q = lane; q < total; q += 32) term(lds_u16(qa + 2u * (uint32_t)q));
+                    __syncwarp();
+                } else {  // tiny boxes where (nearly) every candidate survives: no queue, each lane its own survivors
+                    uint32_t mm = m;
+                    while (mm) {
+                        const int b = 31 - __clz(mm);
+                        mm ^= 1u << b;
+                        term((uint32_t)((KC - 1 - b) * 32 + lane));
+                    }
+                }
+                const double dE = warp_sum(part);
+                const bool acc = A.exact_exp ? accept_exact(dE, Tk, thr) : (dE < thr);
+                if (lane == 0) {
+                    const uint32_t pw = pa + (uint32_t)kPubBytes * (uint32_t)warp;
+                    const int w0 = (t0 >= L) - (t0 < 0.0), w1 = (t1 >= L) - (t1 < 0.0), w2 = (DIM == 3) ? (t2 >= L) - (t2 < 0.0) : 0;
+                    sts_f64x2(pw, dE, xn[0]);
+                    sts_f64x2(pw + 16, xn[1], xn[2]);
+                    sts_u32x4(pw + 32, (uint32_t)i, acc ? 1u : 0u, pack8(uo0, uo1, uo2),
+                              pack8(to_fixed32(xn[0], fscale), to_fixed32(xn[1], fscale), (DIM == 3) ? to_fixed32(xn[2], fscale) : 0u));
+                    sts_u32x4(pw + 48, umq, (uint32_t)fthr, (uint32_t)((w0 + 1) | ((w1 + 1) << 2) | ((w2 + 1) << 4)), 0u);
+                }
+            }
+            __syncthreads();
+            // ---- resolve the round in trial order; every thread does the same arithmetic ---------------------------
+            uint32_t cqo[kSpecWarps], cqn[kSpecWarps];  // packed old / new position of trials accepted in this round
+            uint32_t cmask = 0;
+            int ndone = 0;
+#pragma unroll
+            for (int w = 0; w < kSpecWarps; w++) {
+                if (w < nspec && ndone == w) {  // uniform
+                    const uint32_t pw = pa + (uint32_t)kPubBytes * (uint32_t)w;
+                    uint32_t iw, fl, qo, qn, umq, fthr, wr, pad_;
+                    lds_u32x4(pw + 32, iw, fl, qo, qn);
+                    lds_u32x4(pw + 48, umq, fthr, wr, pad_);
+                    int conflict = 0;
+#pragma unroll
+                    for (int v = 0; v < w; v++) {
+                        if (cmask & (1u << v)) {
+                            const uint32_t ta = __vabsdiffu4(umq, cqo[v]), tb_ = __vabsdiffu4(umq, cqn[v]);
+                            conflict |= __dp4a((int)ta, (int)ta, (int)fthr) | __dp4a((int)tb_, (int)tb_, (int)fthr);
+                        }
+                    }
+                    if (conflict >= 0) {  // stands: retire it
+                        ndone = w + 1;
+                        const bool acc = fl != 0u;
+                        cqo[w] = qo;
+                        cqn[w] = qn;
+                        double dE, x0, x1, x2;
+                        lds_f64x2(pw, dE, x0);
+                        if (acc) {
+                            cmask |= 1u << w;
+                            lds_f64x2(pw + 16, x1, x2);
+                            // every thread stores the (identical) committed position: its own later reads are
+                            // ordered after its own store
+                            const uint32_t xa = sb + F.x + 8u * iw;
+                            sts_f64(xa, x0);
+                            sts_f64(xa + nb8, x1);
+                            if constexpr (DIM == 3) sts_f64(xa + 2 * nb8, x2);
+                            E += dE;
+                            set_slot<KC>(myq, (int)(iw >> 5), qn, lane == (int)(iw & 31u));
+                            if (tid == kImgThread) {
+                                const int w0 = (int)(wr & 3u) - 1, w1 = (int)((wr >> 2) & 3u) - 1, w2 = (int)((wr >> 4) & 3u) - 1;
+                                if (w0) atomicAdd(&gimg[iw], w0);
+                                if (w1) atomicAdd(&gimg[gNpad + iw], w1);
+                                if (DIM == 3 && w2) atomicAdd(&gimg[2 * gNpad + iw], w2);
+                            }
+                        }
+                        if (tid == kCntThread) {
+                            unsigned long long *scnt = (unsigned long long *)(smem_raw + F.cnt);
+                            const int mv = (int)lds_u32(sb + F.rec + (uint32_t)kRecBytes * (uint32_t)(cur + w) + 48);
+                            scnt[mv] += 1ull;
+                            scnt[PMC_MAX_MOVES + mv] += acc ? 1ull : 0ull;
+                            if (A.acc_out) A.acc_out[(size_t)c * A.n_trials + tb + cur + w] = acc ? 1 : 0;
+                            if (A.dE_out) A.dE_out[(size_t)c * A.n_trials + tb + cur + w] = dE;
+                        }
+                    }
+                }
+            }
+            cur += ndone;
+            slot ^= 1u;
+        }
+    }
+    __syncthreads();
+    {
+        const double *sx = (const double *)(smem_raw + F.x);
+        for (int a = 0; a < DIM; a++)
+            for (int k = tid; k < gNpad; k += kSpecThreads) gx[a * gNpad + k] = sx[a * Npad + k];
+        const unsigned long long *scnt = (const unsigned long long *)(smem_raw + F.cnt);
+        if (tid == 0) A.energy[c] = E;
+        if (tid < A.n_moves) {
+            A.calls[(size_t)c * PMC_MAX_MOVES + tid] += scnt[tid];
+            A.accepted[(size_t)c * PMC_MAX_MOVES + tid] += scnt[PMC_MAX_MOVES + tid];
+        }
+    }
+}
+
+}  // namespace spec
+}  // namespace pmc
