@@ -47,7 +47,7 @@ __device__ __forceinline__ void sts_f64x2(uint32_t a, double v0, double v1) {
 }
 
 struct SpecLayout {
-    uint32_t x, sp, q, cp, rec, pub, cnt, par, rcs, total;
+    uint32_t x, sp, q, cp, rec, pub, cnt, cnt32, par, rcs, total;
 };
 __host__ __device__ inline SpecLayout spec_layout(int dim, int Npad, bool full_par) {
     SpecLayout f;
@@ -64,6 +64,7 @@ __host__ __device__ inline SpecLayout spec_layout(int dim, int Npad, bool full_p
     f.rec = take((uint32_t)kRecBytes * kSpecBatch);
     f.pub = take(2u * kPubBytes * kSpecWarps);  // two alternating sets
     f.cnt = take(8u * 2 * PMC_MAX_MOVES);
+    f.cnt32 = take(4u * 2 * PMC_MAX_MOVES);  // per-batch counters (native 32-bit shared atomics), folded into cnt
     f.par = take(full_par ? 8u * PMC_MAX_SPECIES * PMC_MAX_SPECIES * PMC_NPAR : 0u);
     f.rcs = take(8u * PMC_MAX_SPECIES);
     f.total = o;
@@ -110,6 +111,8 @@ __device__ __forceinline__ void set_slot(uint32_t (&myq)[KC], int ki, uint32_t v
     }
 }
 
+// 96 registers (32 of them the packed candidates): 5 CTAs = 20 warps per SM.  Capping at 80 registers for 6 CTAs
+// spills and measured 2 % slower.
 template <int DIM, int MODEL, int NPAD>
 __global__ void __launch_bounds__(kSpecThreads, 5) k_chain_sweep_spec(const __grid_constant__ ChainArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -148,7 +151,10 @@ __global__ void __launch_bounds__(kSpecThreads, 5) k_chain_sweep_spec(const __gr
             scp[4 * k + 3] = A.par[k * PMC_NPAR + PMC_P_SHIFT];
         }
         unsigned long long *scnt = (unsigned long long *)(smem_raw + F.cnt);
-        if (tid < 2 * PMC_MAX_MOVES) scnt[tid] = 0ull;
+        if (tid < 2 * PMC_MAX_MOVES) {
+            scnt[tid] = 0ull;
+            ((uint32_t *)(smem_raw + F.cnt32))[tid] = 0u;
+        }
         if (tid < PMC_MAX_SPECIES) {  // largest cutoff radius per species of the moved particle (filter sphere)
             double rc2 = 0.0;
             for (int b = 0; b < ns; b++) rc2 = fmax(rc2, A.par[((tid < ns ? tid : 0) * ns + b) * PMC_NPAR + PMC_P_RCUT2]);
@@ -171,10 +177,17 @@ __global__ void __launch_bounds__(kSpecThreads, 5) k_chain_sweep_spec(const __gr
     int32_t *gimg = A.img + (size_t)c * DIM * gNpad;
     const uint32_t qa = sb + F.q + (uint32_t)warp * (2u * kSpecQCap);
     uint32_t slot = 0;
+    const bool dbg_out = A.acc_out != nullptr || A.dE_out != nullptr;
 
     for (long long tb = 0; tb < A.n_trials; tb += kSpecBatch) {
         const int nb = (int)min((long long)kSpecBatch, A.n_trials - tb);
         __syncthreads();
+        if (tid >= kSpecThreads - 2 * PMC_MAX_MOVES) {  // fold the counters of the previous batch
+            const int k = tid - (kSpecThreads - 2 * PMC_MAX_MOVES);
+            uint32_t *c32 = (uint32_t *)(smem_raw + F.cnt32);
+            ((unsigned long long *)(smem_raw + F.cnt))[k] += c32[k];
+            c32[k] = 0u;
+        }
         // ---- proposals of trials tb .. tb+nb-1, parked in shared memory (same stream as every other kernel) ----
         if (tid < nb) {
             const long long q = tb + tid;
@@ -249,12 +262,23 @@ __global__ void __launch_bounds__(kSpecThreads, 5) k_chain_sweep_spec(const __gr
                 const uint32_t uo0 = to_fixed32(xo[0], fscale), uo1 = to_fixed32(xo[1], fscale), uo2 = (DIM == 3) ? to_fixed32(xo[2], fscale) : 0u;
                 const uint32_t umq = pack8(uo0 + (uint32_t)(di0 >> 1), uo1 + (uint32_t)(di1 >> 1), uo2 + (uint32_t)(di2 >> 1));
                 const int fthr = (int)lds_u32(ra + 64 + 4u * si);
-                uint32_t m = 0;
+                // survivor mask, candidate k -> bit KC-1-k; built as independent 8-bit shift chains (the funnel shifts of
+                // one chain depend on each other) and merged afterwards
+                constexpr int NCH = KC >= 8 ? KC / 8 : 1, CL = KC / NCH;
+                uint32_t mc[NCH];
 #pragma unroll
-                for (int k = 0; k < KC; k++) {  // survivor: bit KC-1-k
-                    const uint32_t t = __vabsdiffu4(umq, myq[k]);
-                    m = __funnelshift_l((uint32_t)__dp4a((int)t, (int)t, fthr), m, 1);
+                for (int h = 0; h < NCH; h++) mc[h] = 0;
+#pragma unroll
+                for (int kk = 0; kk < CL; kk++) {
+#pragma unroll
+                    for (int h = 0; h < NCH; h++) {
+                        const uint32_t t = __vabsdiffu4(umq, myq[h * CL + kk]);
+                        mc[h] = __funnelshift_l((uint32_t)__dp4a((int)t, (int)t, fthr), mc[h], 1);
+                    }
                 }
+                uint32_t m = mc[0];
+#pragma unroll
+                for (int h = 1; h < NCH; h++) m = (m << CL) | mc[h];
                 const int mine = __popc(m);
                 int incl = mine;
 #pragma unroll
@@ -265,34 +289,36 @@ __global__ void __launch_bounds__(kSpecThreads, 5) k_chain_sweep_spec(const __gr
                 const int total = __shfl_sync(0xffffffffu, incl, 31);
                 const uint32_t prow = si * (uint32_t)ns;
                 double part = 0.0;
-                auto term = [&](uint32_t j) {
-                    if (j < (uint32_t)N && j != (uint32_t)i) {
-                        const uint32_t ja = sb + F.x + 8u * j;
-                        const double xj0 = lds_f64(ja), xj1 = lds_f64(ja + nb8);
-                        double r2o = mi_acc(xo[0], xj0, L, hL, 0.0), r2n = mi_acc(xn[0], xj0, L, hL, 0.0);
-                        r2o = mi_acc(xo[1], xj1, L, hL, r2o);
-                        r2n = mi_acc(xn[1], xj1, L, hL, r2n);
-                        if constexpr (DIM == 3) {
-                            const double xj2 = lds_f64(ja + 2 * nb8);
-                            r2o = mi_acc(xo[2], xj2, L, hL, r2o);
-                            r2n = mi_acc(xn[2], xj2, L, hL, r2n);
-                        }
-                        const uint32_t sj = lds_u8(sb + F.sp + j);
-                        if constexpr (MODEL == PMC_MODEL_LJ || MODEL == PMC_MODEL_KG) {
-                            double rc2, eps4, sig2, shift;
-                            const uint32_t pp = sb + F.cp + 32u * (prow + sj);
-                            lds_f64x2(pp, rc2, eps4);
-                            lds_f64x2(pp + 16, sig2, shift);
-                            const double uo = lj_core(r2o, eps4, sig2) - shift;
-                            const double un = lj_core(r2n, eps4, sig2) - shift;
-                            part += (r2n <= rc2 ? un : 0.0) - (r2o <= rc2 ? uo : 0.0);
-                        } else {
-                            const double *p = (const double *)(smem_raw + F.par) + (prow + sj) * PMC_NPAR;
-                            const double rc2 = p[PMC_P_RCUT2];
-                            if (r2o <= rc2) part -= pair_potential<MODEL>(p, r2o);
-                            if (r2n <= rc2) part += pair_potential<MODEL>(p, r2n);
-                        }
+                // pair term of candidate j, branch-free (selects) so that two of them interleave in the unrolled loop
+                auto term = [&](uint32_t j) -> double {
+                    const bool valid = j < (uint32_t)N && j != (uint32_t)i;
+                    const uint32_t ja = sb + F.x + 8u * j;
+                    const double xj0 = lds_f64(ja), xj1 = lds_f64(ja + nb8);
+                    double r2o = mi_acc(xo[0], xj0, L, hL, 0.0), r2n = mi_acc(xn[0], xj0, L, hL, 0.0);
+                    r2o = mi_acc(xo[1], xj1, L, hL, r2o);
+                    r2n = mi_acc(xn[1], xj1, L, hL, r2n);
+                    if constexpr (DIM == 3) {
+                        const double xj2 = lds_f64(ja + 2 * nb8);
+                        r2o = mi_acc(xo[2], xj2, L, hL, r2o);
+                        r2n = mi_acc(xn[2], xj2, L, hL, r2n);
                     }
+                    const uint32_t sj = lds_u8(sb + F.sp + j);
+                    double uo, un, rc2;
+                    if constexpr (MODEL == PMC_MODEL_LJ || MODEL == PMC_MODEL_KG) {
+                        double eps4, sig2, shift;
+                        const uint32_t pp = sb + F.cp + 32u * (prow + sj);
+                        lds_f64x2(pp, rc2, eps4);
+                        lds_f64x2(pp + 16, sig2, shift);
+                        uo = lj_core(r2o, eps4, sig2) - shift;
+                        un = lj_core(r2n, eps4, sig2) - shift;
+                    } else {
+                        const double *p = (const double *)(smem_raw + F.par) + (prow + sj) * PMC_NPAR;
+                        rc2 = p[PMC_P_RCUT2];
+                        uo = pair_potential<MODEL>(p, r2o);
+                        un = pair_potential<MODEL>(p, r2n);
+                    }
+                    const double d = (r2n <= rc2 ? un : 0.0) - (r2o <= rc2 ? uo : 0.0);
+                    return valid ? d : 0.0;
                 };
                 if (total <= kSpecQCap) {
                     // compaction: each lane appends its survivors (ascending candidate index) at its scan offset
@@ -305,14 +331,24 @@ __global__ void __launch_bounds__(kSpecThreads, 5) k_chain_sweep_spec(const __gr
                         wp += 2;
                     }
                     __syncwarp();
-                    for (int q = lane; q < total; q += 32) term(lds_u16(qa + 2u * (uint32_t)q));
+                    // two survivors per lane and iteration while both exist (the dependent fp64 chains of one pair
+                    // term leave the pipe idle; two independent ones overlap), then the remainder one at a time
+                    const int nfull = total & ~63;
+                    int q = lane;
+                    for (; q < nfull; q += 64) {
+                        const uint32_t j0 = lds_u16(qa + 2u * (uint32_t)q), j1 = lds_u16(qa + 2u * (uint32_t)q + 64u);
+                        const double e0 = term(j0), e1 = term(j1);
+                        part += e0;
+                        part += e1;
+                    }
+                    for (; q < total; q += 32) part += term(lds_u16(qa + 2u * (uint32_t)q));
                     __syncwarp();
                 } else {  // tiny boxes where (nearly) every candidate survives: no queue, each lane its own survivors
                     uint32_t mm = m;
                     while (mm) {
                         const int b = 31 - __clz(mm);
                         mm ^= 1u << b;
-                        term((uint32_t)((KC - 1 - b) * 32 + lane));
+                        part += term((uint32_t)((KC - 1 - b) * 32 + lane));
                     }
                 }
                 const double dE = warp_sum(part);
@@ -322,9 +358,11 @@ __global__ void __launch_bounds__(kSpecThreads, 5) k_chain_sweep_spec(const __gr
                     const int w0 = (t0 >= L) - (t0 < 0.0), w1 = (t1 >= L) - (t1 < 0.0), w2 = (DIM == 3) ? (t2 >= L) - (t2 < 0.0) : 0;
                     sts_f64x2(pw, dE, xn[0]);
                     sts_f64x2(pw + 16, xn[1], xn[2]);
-                    sts_u32x4(pw + 32, (uint32_t)i, acc ? 1u : 0u, pack8(uo0, uo1, uo2),
+                    // +32: what the conflict test of LATER trials needs | +48: what retiring THIS trial needs
+                    sts_u32x4(pw + 32, umq, (uint32_t)fthr, pack8(uo0, uo1, uo2),
                               pack8(to_fixed32(xn[0], fscale), to_fixed32(xn[1], fscale), (DIM == 3) ? to_fixed32(xn[2], fscale) : 0u));
-                    sts_u32x4(pw + 48, umq, (uint32_t)fthr, (uint32_t)((w0 + 1) | ((w1 + 1) << 2) | ((w2 + 1) << 4)), 0u);
+                    sts_u32x4(pw + 48, (uint32_t)i, acc ? 1u : 0u, (uint32_t)((w0 + 1) | ((w1 + 1) << 2) | ((w2 + 1) << 4)),
+                              lds_u32(ra + 48));
                 }
             }
             __syncthreads();
@@ -336,26 +374,30 @@ __global__ void __launch_bounds__(kSpecThreads, 5) k_chain_sweep_spec(const __gr
             for (int w = 0; w < kSpecWarps; w++) {
                 if (w < nspec && ndone == w) {  // uniform
                     const uint32_t pw = pa + (uint32_t)kPubBytes * (uint32_t)w;
-                    uint32_t iw, fl, qo, qn, umq, fthr, wr, pad_;
-                    lds_u32x4(pw + 32, iw, fl, qo, qn);
-                    lds_u32x4(pw + 48, umq, fthr, wr, pad_);
+                    uint32_t umq, fthr, qo, qn;
                     int conflict = 0;
+                    if (w > 0 && cmask != 0u) {
+                        lds_u32x4(pw + 32, umq, fthr, qo, qn);
 #pragma unroll
-                    for (int v = 0; v < w; v++) {
-                        if (cmask & (1u << v)) {
-                            const uint32_t ta = __vabsdiffu4(umq, cqo[v]), tb_ = __vabsdiffu4(umq, cqn[v]);
-                            conflict |= __dp4a((int)ta, (int)ta, (int)fthr) | __dp4a((int)tb_, (int)tb_, (int)fthr);
+                        for (int v = 0; v < w; v++) {
+                            if (cmask & (1u << v)) {
+                                const uint32_t ta = __vabsdiffu4(umq, cqo[v]), tb_ = __vabsdiffu4(umq, cqn[v]);
+                                conflict |= __dp4a((int)ta, (int)ta, (int)fthr) | __dp4a((int)tb_, (int)tb_, (int)fthr);
+                            }
                         }
                     }
                     if (conflict >= 0) {  // stands: retire it
                         ndone = w + 1;
+                        uint32_t iw, fl, wr, mv;
+                        lds_u32x4(pw + 48, iw, fl, wr, mv);
                         const bool acc = fl != 0u;
-                        cqo[w] = qo;
-                        cqn[w] = qn;
-                        double dE, x0, x1, x2;
-                        lds_f64x2(pw, dE, x0);
                         if (acc) {
+                            if (w == 0 || cmask == 0u) lds_u32x4(pw + 32, umq, fthr, qo, qn);
                             cmask |= 1u << w;
+                            cqo[w] = qo;
+                            cqn[w] = qn;
+                            double dE, x0, x1, x2;
+                            lds_f64x2(pw, dE, x0);
                             lds_f64x2(pw + 16, x1, x2);
                             // every thread stores the (identical) committed position: its own later reads are
                             // ordered after its own store
@@ -365,7 +407,7 @@ __global__ void __launch_bounds__(kSpecThreads, 5) k_chain_sweep_spec(const __gr
                             if constexpr (DIM == 3) sts_f64(xa + 2 * nb8, x2);
                             E += dE;
                             set_slot<KC>(myq, (int)(iw >> 5), qn, lane == (int)(iw & 31u));
-                            if (tid == kImgThread) {
+                            if (tid == kImgThread && wr != 0x15u) {  // some coordinate wrapped around the box
                                 const int w0 = (int)(wr & 3u) - 1, w1 = (int)((wr >> 2) & 3u) - 1, w2 = (int)((wr >> 4) & 3u) - 1;
                                 if (w0) atomicAdd(&gimg[iw], w0);
                                 if (w1) atomicAdd(&gimg[gNpad + iw], w1);
@@ -373,12 +415,13 @@ __global__ void __launch_bounds__(kSpecThreads, 5) k_chain_sweep_spec(const __gr
                             }
                         }
                         if (tid == kCntThread) {
-                            unsigned long long *scnt = (unsigned long long *)(smem_raw + F.cnt);
-                            const int mv = (int)lds_u32(sb + F.rec + (uint32_t)kRecBytes * (uint32_t)(cur + w) + 48);
-                            scnt[mv] += 1ull;
-                            scnt[PMC_MAX_MOVES + mv] += acc ? 1ull : 0ull;
-                            if (A.acc_out) A.acc_out[(size_t)c * A.n_trials + tb + cur + w] = acc ? 1 : 0;
-                            if (A.dE_out) A.dE_out[(size_t)c * A.n_trials + tb + cur + w] = dE;
+                            uint32_t *c32 = (uint32_t *)(smem_raw + F.cnt32);
+                            atomicAdd(&c32[mv], 1u);
+                            if (acc) atomicAdd(&c32[PMC_MAX_MOVES + mv], 1u);
+                            if (dbg_out) {
+                                if (A.acc_out) A.acc_out[(size_t)c * A.n_trials + tb + cur + w] = acc ? 1 : 0;
+                                if (A.dE_out) A.dE_out[(size_t)c * A.n_trials + tb + cur + w] = lds_f64(pw);
+                            }
                         }
                     }
                 }
@@ -393,10 +436,11 @@ __global__ void __launch_bounds__(kSpecThreads, 5) k_chain_sweep_spec(const __gr
         for (int a = 0; a < DIM; a++)
             for (int k = tid; k < gNpad; k += kSpecThreads) gx[a * gNpad + k] = sx[a * Npad + k];
         const unsigned long long *scnt = (const unsigned long long *)(smem_raw + F.cnt);
+        const uint32_t *c32 = (const uint32_t *)(smem_raw + F.cnt32);
         if (tid == 0) A.energy[c] = E;
         if (tid < A.n_moves) {
-            A.calls[(size_t)c * PMC_MAX_MOVES + tid] += scnt[tid];
-            A.accepted[(size_t)c * PMC_MAX_MOVES + tid] += scnt[PMC_MAX_MOVES + tid];
+            A.calls[(size_t)c * PMC_MAX_MOVES + tid] += scnt[tid] + c32[tid];
+            A.accepted[(size_t)c * PMC_MAX_MOVES + tid] += scnt[PMC_MAX_MOVES + tid] + c32[PMC_MAX_MOVES + tid];
         }
     }
 }

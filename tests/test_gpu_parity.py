@@ -324,15 +324,54 @@ def test_sharded_chains_equal_unsharded():
         assert np.array_equal(sf[:2], s0) and np.array_equal(sf[2:], s1)
 
 
-@pytest.mark.parametrize("threads,prefilter", [(32, 0), (64, 0), (128, 0), (128, -1), (256, -1)])
+@pytest.mark.parametrize("threads,prefilter", [(32, 0), (64, 0), (128, 0), (128, 1), (128, -1), (256, -1)])
 def test_cta_size_and_prefilter_do_not_change_decisions(threads, prefilter):
     """The fixed-point prefilter only selects WHICH candidates get the fp64 evaluation (a superset of the pairs
-    inside the cutoff); decisions must equal the kernel that visits every candidate in fp64."""
+    inside the cutoff); decisions must equal the kernel that visits every candidate in fp64.  The default context
+    (128 threads, prefilter 0) runs the speculative kernel (four trials of a chain per round, chains_spec.cuh);
+    prefilter 1 the one-trial-at-a-time kernel; other CTA sizes and prefilter -1 the general kernel."""
     with _ka_ctx(2) as a, _ka_ctx(2, threads=threads, prefilter=prefilter) as b:
         _, acc_a, _ = a.run_traced(800)
         _, acc_b, _ = b.run_traced(800)
         assert np.array_equal(acc_a, acc_b)
         assert np.max(np.abs(a.download()[0] - b.download()[0])) < 1e-12
+
+
+def _ka_disp_ctx(n_chains, N, prefilter, T=1.0):
+    par = M.flatten_model_matrix(M.KobAndersen())
+    cfgs = [ka_config(N, s) for s in range(n_chains)]
+    ctx = DeviceContext(n_chains, N, 3, 2, M.MODEL_LJ, prefilter=prefilter)
+    ctx.set_model(par)
+    ctx.upload(np.stack([c[0] for c in cfgs]), np.stack([c[1] for c in cfgs]), cfgs[0][2], T)
+    ctx.init_energy()
+    ctx.set_moves([dict(kind="displacement", prob=0.7, sigma=0.05), dict(kind="displacement", prob=0.3, sigma=0.12)])
+    ctx.seed(7)
+    return ctx
+
+
+@pytest.mark.parametrize("N,sweeps", [(1000, 12), (512, 12), (216, 30)])
+def test_speculative_rounds_reproduce_the_sequential_chain(N, sweeps):
+    """Speculation must not change the Markov chain (chains_spec.cuh): every decision and every final coordinate
+    of 6 chains equal those of the kernel that evaluates one trial at a time (prefilter = 1).  Trials whose
+    neighbourhood was touched by an earlier accepted trial of the same round are re-evaluated, so nothing but the
+    schedule differs; dE agrees to rounding (same pairs, different summation order)."""
+    with _ka_disp_ctx(6, N, 0) as a, _ka_disp_ctx(6, N, 1) as b:
+        n = sweeps * N + 37  # not a multiple of the batch or of the round size
+        _, acc_a, dE_a = a.run_traced(n)
+        _, acc_b, dE_b = b.run_traced(n)
+        assert np.array_equal(acc_a, acc_b)
+        assert 0.2 < acc_a.mean() < 0.9
+        assert np.array_equal(a.download()[0], b.download()[0])
+        assert np.max(np.abs(dE_a - dE_b) / np.maximum(1.0, np.abs(dE_b))) < 1e-11
+        ca, aa = a.counters()
+        cb, ab = b.counters()
+        assert np.array_equal(ca, cb) and np.array_equal(aa, ab) and ca.sum() == 6 * n
+        assert np.allclose(a.energy(), b.energy(), rtol=1e-12, atol=0)
+        assert np.allclose(a.energy(), a.total_energy(), rtol=1e-11, atol=0)
+        # a second launch continues the same stream (trial counter, image counters, register copies reloaded)
+        a.run(3 * N)
+        b.run(3 * N)
+        assert np.array_equal(a.download()[0], b.download()[0])
 
 
 def test_noncubic_box_uses_direct_kernel_and_matches_oracle():
