@@ -47,7 +47,7 @@ __device__ __forceinline__ void sts_f64x2(uint32_t a, double v0, double v1) {
 }
 
 struct SpecLayout {
-    uint32_t x, sp, q, cp, rec, pub, cnt, cnt32, par, rcs, total;
+    uint32_t x, sp, pk, q, cp, rec, pub, cnt, cnt32, par, rcs, total;
 };
 __host__ __device__ inline SpecLayout spec_layout(int dim, int Npad, bool full_par) {
     SpecLayout f;
@@ -59,6 +59,7 @@ __host__ __device__ inline SpecLayout spec_layout(int dim, int Npad, bool full_p
     };
     f.x = take(8u * dim * Npad);
     f.sp = take(Npad);
+    f.pk = take(4u * Npad);  // packed 8-bit coordinates (common.cuh), word j = particle j
     f.q = take(2u * kSpecQCap * kSpecWarps);
     f.cp = take(32u * PMC_MAX_SPECIES * PMC_MAX_SPECIES);
     f.rec = take((uint32_t)kRecBytes * kSpecBatch);
@@ -71,53 +72,21 @@ __host__ __device__ inline SpecLayout spec_layout(int dim, int Npad, bool full_p
     return f;
 }
 
-// myq[ki] = v for a warp-uniform ki: one indirect branch instead of KC predicated selects
+// The packed candidates live in a shared-memory table that every warp streams through with LDS.128 (4 candidates per
+// load): keeping them in 32 registers per thread instead (96 registers, 5 CTAs per SM) measured slower than this
+// (6 CTAs = 24 warps per SM), and a commit is one store instead of a 32-way register select.
+// particle index of the candidate behind bit b of a survivor mask
 template <int KC>
-__device__ __forceinline__ void set_slot(uint32_t (&myq)[KC], int ki, uint32_t v, bool mine) {
-    switch (ki) {
-    case 0: if constexpr (KC > 0) { if (mine) myq[0 < KC ? 0 : 0] = v; } break;
-    case 1: if constexpr (KC > 1) { if (mine) myq[1 < KC ? 1 : 0] = v; } break;
-    case 2: if constexpr (KC > 2) { if (mine) myq[2 < KC ? 2 : 0] = v; } break;
-    case 3: if constexpr (KC > 3) { if (mine) myq[3 < KC ? 3 : 0] = v; } break;
-    case 4: if constexpr (KC > 4) { if (mine) myq[4 < KC ? 4 : 0] = v; } break;
-    case 5: if constexpr (KC > 5) { if (mine) myq[5 < KC ? 5 : 0] = v; } break;
-    case 6: if constexpr (KC > 6) { if (mine) myq[6 < KC ? 6 : 0] = v; } break;
-    case 7: if constexpr (KC > 7) { if (mine) myq[7 < KC ? 7 : 0] = v; } break;
-    case 8: if constexpr (KC > 8) { if (mine) myq[8 < KC ? 8 : 0] = v; } break;
-    case 9: if constexpr (KC > 9) { if (mine) myq[9 < KC ? 9 : 0] = v; } break;
-    case 10: if constexpr (KC > 10) { if (mine) myq[10 < KC ? 10 : 0] = v; } break;
-    case 11: if constexpr (KC > 11) { if (mine) myq[11 < KC ? 11 : 0] = v; } break;
-    case 12: if constexpr (KC > 12) { if (mine) myq[12 < KC ? 12 : 0] = v; } break;
-    case 13: if constexpr (KC > 13) { if (mine) myq[13 < KC ? 13 : 0] = v; } break;
-    case 14: if constexpr (KC > 14) { if (mine) myq[14 < KC ? 14 : 0] = v; } break;
-    case 15: if constexpr (KC > 15) { if (mine) myq[15 < KC ? 15 : 0] = v; } break;
-    case 16: if constexpr (KC > 16) { if (mine) myq[16 < KC ? 16 : 0] = v; } break;
-    case 17: if constexpr (KC > 17) { if (mine) myq[17 < KC ? 17 : 0] = v; } break;
-    case 18: if constexpr (KC > 18) { if (mine) myq[18 < KC ? 18 : 0] = v; } break;
-    case 19: if constexpr (KC > 19) { if (mine) myq[19 < KC ? 19 : 0] = v; } break;
-    case 20: if constexpr (KC > 20) { if (mine) myq[20 < KC ? 20 : 0] = v; } break;
-    case 21: if constexpr (KC > 21) { if (mine) myq[21 < KC ? 21 : 0] = v; } break;
-    case 22: if constexpr (KC > 22) { if (mine) myq[22 < KC ? 22 : 0] = v; } break;
-    case 23: if constexpr (KC > 23) { if (mine) myq[23 < KC ? 23 : 0] = v; } break;
-    case 24: if constexpr (KC > 24) { if (mine) myq[24 < KC ? 24 : 0] = v; } break;
-    case 25: if constexpr (KC > 25) { if (mine) myq[25 < KC ? 25 : 0] = v; } break;
-    case 26: if constexpr (KC > 26) { if (mine) myq[26 < KC ? 26 : 0] = v; } break;
-    case 27: if constexpr (KC > 27) { if (mine) myq[27 < KC ? 27 : 0] = v; } break;
-    case 28: if constexpr (KC > 28) { if (mine) myq[28 < KC ? 28 : 0] = v; } break;
-    case 29: if constexpr (KC > 29) { if (mine) myq[29 < KC ? 29 : 0] = v; } break;
-    case 30: if constexpr (KC > 30) { if (mine) myq[30 < KC ? 30 : 0] = v; } break;
-    case 31: if constexpr (KC > 31) { if (mine) myq[31 < KC ? 31 : 0] = v; } break;
-    default: break;
-    }
+__device__ __forceinline__ uint32_t cand_index(int b, int lane) {
+    const uint32_t k = (uint32_t)(KC - 1 - b);
+    return (k >> 2) * 128u + 4u * (uint32_t)lane + (k & 3u);
 }
 
-// 96 registers (32 of them the packed candidates): 5 CTAs = 20 warps per SM.  Capping at 80 registers for 6 CTAs
-// spills and measured 2 % slower.
 template <int DIM, int MODEL, int NPAD>
-__global__ void __launch_bounds__(kSpecThreads, 5) k_chain_sweep_spec(const __grid_constant__ ChainArgs A) {
+__global__ void __launch_bounds__(kSpecThreads, 6) k_chain_sweep_spec(const __grid_constant__ ChainArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int KC = NPAD / 32;  // candidates per lane: candidate j = k * 32 + lane, held by EVERY warp
-    static_assert(KC >= 1 && KC <= 32, "survivor masks are 32 bits");
+    constexpr int KC = NPAD / 32;  // candidates per lane: k = 4 * c + e  <->  particle j = 128 * c + 4 * lane + e
+    static_assert(KC >= 4 && KC <= 32 && KC % 4 == 0, "survivor masks are 32 bits, candidates come four per LDS.128");
     constexpr int Npad = NPAD;
     constexpr int kImgThread = 32, kCntThread = 64;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -161,15 +130,13 @@ __global__ void __launch_bounds__(kSpecThreads, 5) k_chain_sweep_spec(const __gr
             ((double *)(smem_raw + F.rcs))[tid] = sqrt(rc2);
         }
     }
-    uint32_t myq[KC];  // packed 8-bit coordinates (common.cuh) of candidates k * 32 + lane
-#pragma unroll
-    for (int k = 0; k < KC; k++) {
-        const int j = k * 32 + lane;
+    for (int j = tid; j < Npad; j += kSpecThreads) {
         uint32_t u[3] = {0u, 0u, 0u};
 #pragma unroll
         for (int a = 0; a < DIM; a++) u[a] = j < gNpad ? to_fixed32(gx[a * gNpad + j], fscale) : 0u;
-        myq[k] = pack8(u[0], u[1], u[2]);
+        ((uint32_t *)(smem_raw + F.pk))[j] = pack8(u[0], u[1], u[2]);
     }
+    const uint32_t pka = sb + F.pk + 16u * (uint32_t)lane;
     const double Tk = A.temp[c];
     double E = A.energy[c];
     const uint32_t k0 = (uint32_t)A.seed, k1 = (uint32_t)(A.seed >> 32);
@@ -262,23 +229,28 @@ __global__ void __launch_bounds__(kSpecThreads, 5) k_chain_sweep_spec(const __gr
                 const uint32_t uo0 = to_fixed32(xo[0], fscale), uo1 = to_fixed32(xo[1], fscale), uo2 = (DIM == 3) ? to_fixed32(xo[2], fscale) : 0u;
                 const uint32_t umq = pack8(uo0 + (uint32_t)(di0 >> 1), uo1 + (uint32_t)(di1 >> 1), uo2 + (uint32_t)(di2 >> 1));
                 const int fthr = (int)lds_u32(ra + 64 + 4u * si);
-                // survivor mask, candidate k -> bit KC-1-k; built as independent 8-bit shift chains (the funnel shifts of
-                // one chain depend on each other) and merged afterwards
-                constexpr int NCH = KC >= 8 ? KC / 8 : 1, CL = KC / NCH;
+                // survivor mask, candidate k -> bit KC-1-k; built as independent shift chains over groups of chunks
+                // (the funnel shifts of one chain depend on each other) and concatenated afterwards
+                constexpr int NCHUNK = KC / 4, NCH = NCHUNK >= 4 ? 4 : NCHUNK, CG = NCHUNK / NCH;
                 uint32_t mc[NCH];
 #pragma unroll
-                for (int h = 0; h < NCH; h++) mc[h] = 0;
+                for (int h = 0; h < NCH; h++) mc[h] = 0u;
 #pragma unroll
-                for (int kk = 0; kk < CL; kk++) {
+                for (int cc = 0; cc < CG; cc++) {
 #pragma unroll
                     for (int h = 0; h < NCH; h++) {
-                        const uint32_t t = __vabsdiffu4(umq, myq[h * CL + kk]);
-                        mc[h] = __funnelshift_l((uint32_t)__dp4a((int)t, (int)t, fthr), mc[h], 1);
+                        uint32_t w4[4];
+                        lds_u32x4(pka + 512u * (uint32_t)(h * CG + cc), w4[0], w4[1], w4[2], w4[3]);
+#pragma unroll
+                        for (int e = 0; e < 4; e++) {
+                            const uint32_t t = __vabsdiffu4(umq, w4[e]);
+                            mc[h] = __funnelshift_l((uint32_t)__dp4a((int)t, (int)t, fthr), mc[h], 1);
+                        }
                     }
                 }
                 uint32_t m = mc[0];
 #pragma unroll
-                for (int h = 1; h < NCH; h++) m = (m << CL) | mc[h];
+                for (int h = 1; h < NCH; h++) m = (m << (4 * CG)) | mc[h];
                 const int mine = __popc(m);
                 int incl = mine;
 #pragma unroll
@@ -327,7 +299,7 @@ __global__ void __launch_bounds__(kSpecThreads, 5) k_chain_sweep_spec(const __gr
                     while (mm) {
                         const int b = 31 - __clz(mm);
                         mm ^= 1u << b;
-                        sts_u16(wp, (uint32_t)((KC - 1 - b) * 32 + lane));
+                        sts_u16(wp, cand_index<KC>(b, lane));
                         wp += 2;
                     }
                     __syncwarp();
@@ -348,7 +320,7 @@ __global__ void __launch_bounds__(kSpecThreads, 5) k_chain_sweep_spec(const __gr
                     while (mm) {
                         const int b = 31 - __clz(mm);
                         mm ^= 1u << b;
-                        part += term((uint32_t)((KC - 1 - b) * 32 + lane));
+                        part += term(cand_index<KC>(b, lane));
                     }
                 }
                 const double dE = warp_sum(part);
@@ -406,7 +378,7 @@ __global__ void __launch_bounds__(kSpecThreads, 5) k_chain_sweep_spec(const __gr
                             sts_f64(xa + nb8, x1);
                             if constexpr (DIM == 3) sts_f64(xa + 2 * nb8, x2);
                             E += dE;
-                            set_slot<KC>(myq, (int)(iw >> 5), qn, lane == (int)(iw & 31u));
+                            sts_u32(sb + F.pk + 4u * iw, qn);
                             if (tid == kImgThread && wr != 0x15u) {  // some coordinate wrapped around the box
                                 const int w0 = (int)(wr & 3u) - 1, w1 = (int)((wr >> 2) & 3u) - 1, w2 = (int)((wr >> 4) & 3u) - 1;
                                 if (w0) atomicAdd(&gimg[iw], w0);
