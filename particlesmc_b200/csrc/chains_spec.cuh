@@ -5,7 +5,7 @@
 // candidates, but everything around the scan -- record and position loads, wrapping, the compaction scan, the block
 // reduction, the barrier, the commit -- is replicated in all four warps, and the fp64 pass runs with ~21 of 32 lanes.
 // Here warp w of the CTA evaluates trial t + w of the SAME chain against the current state, alone: it scans all
-// candidates (32 per lane, packed 8-bit coordinates in registers), compacts the survivors into its own queue, runs
+// candidates (32 per lane, packed 8-bit coordinates streamed from a shared-memory table), compacts the survivors into its own queue, runs
 // the fp64 pass at ~86 % lane utilisation and reduces with shuffles only.  After ONE barrier per round every thread
 // resolves the four results in trial order (identical arithmetic in every thread, so no second barrier):
 //
@@ -32,7 +32,7 @@ using namespace pmc::fast;
 
 constexpr int kSpecThreads = 128;
 constexpr int kSpecWarps = kSpecThreads / 32;  // speculation depth
-constexpr int kSpecBatch = 64;                 // parked proposals
+constexpr int kSpecBatch = 56;                 // parked proposals (56 x 80 B keeps the CTA under 1/6 of the SM shared memory)
 constexpr int kSpecQCap = 256;                 // survivor queue entries per warp (beyond: unqueued fallback)
 constexpr int kPubBytes = 64;                  // published result of one trial
 
@@ -72,9 +72,6 @@ __host__ __device__ inline SpecLayout spec_layout(int dim, int Npad, bool full_p
     return f;
 }
 
-// The packed candidates live in a shared-memory table that every warp streams through with LDS.128 (4 candidates per
-// load): keeping them in 32 registers per thread instead (96 registers, 5 CTAs per SM) measured slower than this
-// (6 CTAs = 24 warps per SM), and a commit is one store instead of a 32-way register select.
 // particle index of the candidate behind bit b of a survivor mask
 template <int KC>
 __device__ __forceinline__ uint32_t cand_index(int b, int lane) {
@@ -82,6 +79,10 @@ __device__ __forceinline__ uint32_t cand_index(int b, int lane) {
     return (k >> 2) * 128u + 4u * (uint32_t)lane + (k & 3u);
 }
 
+// The packed candidates live in a shared-memory table that every warp streams through with LDS.128 (4 candidates per
+// load): keeping them in 32 registers per thread instead (96 registers, 5 CTAs per SM) measured slower than this
+// (6 CTAs = 24 warps per SM), and a commit is one store instead of a 32-way register select.  Squeezing to 72 registers
+// and 32 KB for 7 CTAs (batch 32, queue 128) spills and measured 1 % slower again.
 template <int DIM, int MODEL, int NPAD>
 __global__ void __launch_bounds__(kSpecThreads, 6) k_chain_sweep_spec(const __grid_constant__ ChainArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
