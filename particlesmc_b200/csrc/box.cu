@@ -582,6 +582,9 @@ __global__ void __launch_bounds__(kBoxThreads) k_box_sweep(const __grid_constant
 // sphere test (midpoint of old/new, radius rc + |delta|/2; VABSDIFF4 + IDP.4A + funnel shift) per candidate, survivors
 // compacted with one warp prefix sum, fp64 only for survivors (no minimum image in the cell frame), explicit
 // 32-bit shared addressing.  Needs cubic cells (one fixed-point scale); otherwise k_box_sweep is used.
+// The one-warp-per-trial speculative scheme of chains_spec.cuh was tried here too and measured 17 % SLOWER
+// (5.3e8 vs 6.3e8 moves/s at N = 2^20): a cell holds only ~19 trials, so the rounds of four never fill up and
+// every warp has to stream the whole stencil.
 constexpr int kBfThreads = 128;
 constexpr int kBfWarps = kBfThreads / 32;
 // register candidates per thread offered (capacity = threads x KC): 512 / 640 / 768 / 1024 candidates
