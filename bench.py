@@ -43,6 +43,15 @@ WORK = {
 }
 
 
+# figures of ONE launch from the committed `ncu --set full` captures (profiles/README.md)
+NCU_CHAINS = {"source": "profiles/r01_final_k_chain_sweep_spec_ncu_full_summary.csv", "dram_read_bytes": 105.67e6,
+              "dram_write_bytes": 43.25e6, "warp_instructions_per_move": 884, "issue_active_pct": 70.4,
+              "fp64_pipe_pct": 29.7, "alu_pipe_pct": 50.4, "registers": 80, "ctas_per_sm": 6}
+NCU_BOX = {"source": "profiles/r01_final_k_box_sweep_fast_ncu_full_summary.csv", "dram_read_bytes": 35.76e6,
+           "dram_write_bytes": 0.21e6, "issue_active_pct": 66.6, "fp64_pipe_pct": 31.7, "alu_pipe_pct": 33.3,
+           "registers": 64, "ctas_per_sm": 8}
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -61,7 +70,7 @@ def parse_args():
     ap.add_argument("--prefilter", type=int, default=0, help="0 = fixed-point prefilter (default), -1 = visit all candidates in fp64")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--cpu-sweeps", type=int, default=40)
+    ap.add_argument("--cpu-sweeps", type=int, default=200)
     return ap.parse_args()
 
 
@@ -326,22 +335,33 @@ def run_ours(args):
         peak64 = measure_fma_peak(True, local)
         peak32 = measure_fma_peak(False, local)
         achieved = Mc * trials_per_step * work["P"] * work["F"] / (kms * 1e-3) / 1e12
-        # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from the committed ncu --set full captures
-        # (profiles/r01_final_k_chain_sweep_fast_ncu_full_summary.csv: 4096 chains x N=1000; profiles/
-        # r01_final_k_box_sweep_fast_ncu_full_summary.csv: one colour of N=2^20); null for any other shape
-        traffic = None
-        if args.workload == "chains" and Mc == 4096 and N == 1000 and args.precision == "fp64":
-            traffic = 105.820416e6 + 44.805632e6
-        elif args.workload == "box" and N == (1 << 20):
-            traffic = 35.759360e6 + 0.189952e6
-        roofline = {"bound": "fp64_pipe", "achieved": achieved, "peak": peak64, "unit": "TFLOP/s",
-                    "frac": achieved / peak64, "traffic": traffic,
-                    "kernel": "k_chain_sweep" if args.workload == "chains" else "k_box_sweep (8 colours + cell rebuild)",
+        # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch, and the issue-slot figures of that launch, from the
+        # committed ncu --set full captures (profiles/r01_final_*_ncu_full_summary.csv: 4096 chains x N=1000 x 1 sweep;
+        # one colour of N=2^20); null for any other shape
+        traffic, ncu = None, None
+        if args.workload == "chains" and Mc == 4096 and N == 1000 and args.precision == "fp64" and args.prefilter == 0:
+            traffic = NCU_CHAINS["dram_read_bytes"] + NCU_CHAINS["dram_write_bytes"]
+            ncu = NCU_CHAINS
+        elif args.workload == "box" and N == (1 << 20) and args.prefilter >= 0:
+            traffic = NCU_BOX["dram_read_bytes"] + NCU_BOX["dram_write_bytes"]
+            ncu = NCU_BOX
+        mixed = args.precision == "mixed"
+        peak = peak32 if mixed else peak64
+        kernel = ("k_chain_sweep_mixed" if mixed else "k_chain_sweep_spec" if args.prefilter == 0 else
+                  "k_chain_sweep_fast" if args.prefilter == 1 else "k_chain_sweep") if args.workload == "chains" \
+            else "k_box_sweep_fast (8 colours + cell rebuild)"
+        roofline = {"bound": "fp32_pipe" if mixed else "fp64_pipe", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                    "frac": achieved / peak, "traffic": traffic,
+                    "kernel": kernel,
                     "kernel_ms_per_launch": kms, "launches_per_step": launches / args.steps,
                     "work_model": f"reference-equivalent: P={work['P']:.0f} candidate pairs/move x F={work['F']:.2f} flop/pair (SURVEY.md 8d)",
-                    "peak_source": "DFMA burst micro-benchmark run in this process (pmc_measure_fma_peak); "
+                    "note": "achieved counts the REFERENCE's pair evaluations per move; the kernel rejects ~91 % of the candidates "
+                            "with a 3-instruction integer test and evaluates only the survivors in fp64, so frac can exceed the "
+                            "pipe utilisation (ncu: see `ncu`) -- the kernel is bound by instruction issue, not by the FMA pipe",
+                    "ncu": ncu,
+                    "peak_source": "FMA burst micro-benchmark run in this process (pmc_measure_fma_peak); "
                                    "MEASURED_PEAKS.json holds no FP64/FP32 CUDA-core figure",
-                    "fp32_fma_peak_tflops": peak32,
+                    "fp64_fma_peak_tflops": peak64, "fp32_fma_peak_tflops": peak32,
                     "hbm_algorithmic_gbs": 2.0 * Mc * N * 28 / (kms * 1e-3) / 1e9,
                     "hbm_peak_gbs": json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
                     if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0}
