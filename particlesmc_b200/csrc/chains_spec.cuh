@@ -6,8 +6,9 @@
 // reduction, the barrier, the commit -- is replicated in all four warps, and the fp64 pass runs with ~21 of 32 lanes.
 // Here warp w of the CTA evaluates trial t + w of the SAME chain against the current state, alone: it scans all
 // candidates (32 per lane, packed 8-bit coordinates streamed from a shared-memory table), compacts the survivors into its own queue, runs
-// the fp64 pass at ~86 % lane utilisation and reduces with shuffles only.  After ONE barrier per round every thread
-// resolves the four results in trial order (identical arithmetic in every thread, so no second barrier):
+// the fp64 pass at ~86 % lane utilisation and reduces with shuffles only.  After a barrier, warp 0 retires the four
+// results in trial order and publishes how many retired; a second barrier starts the next round (retiring in every
+// warp redundantly saves that barrier but costs 165 more instructions per move: measured 3 % slower):
 //
 //   trial t+w stands  <=>  no earlier trial of this round was ACCEPTED with its particle inside the filter sphere of
 //                          t+w, tested on the old AND the new position with the very 8-bit test the scan uses.
@@ -63,7 +64,7 @@ __host__ __device__ inline SpecLayout spec_layout(int dim, int Npad, bool full_p
     f.q = take(2u * kSpecQCap * kSpecWarps);
     f.cp = take(32u * PMC_MAX_SPECIES * PMC_MAX_SPECIES);
     f.rec = take((uint32_t)kRecBytes * kSpecBatch);
-    f.pub = take(2u * kPubBytes * kSpecWarps);  // two alternating sets
+    f.pub = take(2u * kPubBytes * kSpecWarps + 16u);  // two alternating sets + the retired count of the round
     f.cnt = take(8u * 2 * PMC_MAX_MOVES);
     f.cnt32 = take(4u * 2 * PMC_MAX_MOVES);  // per-batch counters (native 32-bit shared atomics), folded into cnt
     f.par = take(full_par ? 8u * PMC_MAX_SPECIES * PMC_MAX_SPECIES * PMC_NPAR : 0u);
@@ -89,7 +90,7 @@ __global__ void __launch_bounds__(kSpecThreads, 6) k_chain_sweep_spec(const __gr
     constexpr int KC = NPAD / 32;  // candidates per lane: k = 4 * c + e  <->  particle j = 128 * c + 4 * lane + e
     static_assert(KC >= 4 && KC <= 32 && KC % 4 == 0, "survivor masks are 32 bits, candidates come four per LDS.128");
     constexpr int Npad = NPAD;
-    constexpr int kImgThread = 32, kCntThread = 64;
+    constexpr int kImgThread = 1, kCntThread = 2;  // lanes of warp 0 (the retiring warp)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int c = blockIdx.x;
     const int N = A.N, gNpad = A.Npad, ns = A.ns;
@@ -339,7 +340,8 @@ __global__ void __launch_bounds__(kSpecThreads, 6) k_chain_sweep_spec(const __gr
                 }
             }
             __syncthreads();
-            // ---- resolve the round in trial order; every thread does the same arithmetic ---------------------------
+            // ---- retire the round in trial order: warp 0 alone, the others wait at the second barrier --------------
+            if (warp == 0) {
             uint32_t cqo[kSpecWarps], cqn[kSpecWarps];  // packed old / new position of trials accepted in this round
             uint32_t cmask = 0;
             int ndone = 0;
@@ -372,8 +374,6 @@ __global__ void __launch_bounds__(kSpecThreads, 6) k_chain_sweep_spec(const __gr
                             double dE, x0, x1, x2;
                             lds_f64x2(pw, dE, x0);
                             lds_f64x2(pw + 16, x1, x2);
-                            // every thread stores the (identical) committed position: its own later reads are
-                            // ordered after its own store
                             const uint32_t xa = sb + F.x + 8u * iw;
                             sts_f64(xa, x0);
                             sts_f64(xa + nb8, x1);
@@ -399,7 +399,10 @@ __global__ void __launch_bounds__(kSpecThreads, 6) k_chain_sweep_spec(const __gr
                     }
                 }
             }
-            cur += ndone;
+            if (lane == 0) sts_u32(sb + F.pub + 2u * kPubBytes * kSpecWarps, (uint32_t)ndone);
+            }
+            __syncthreads();
+            cur += (int)lds_u32(sb + F.pub + 2u * kPubBytes * kSpecWarps);
             slot ^= 1u;
         }
     }
