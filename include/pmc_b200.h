@@ -172,6 +172,15 @@ int pmc_download(pmc_ctx *ctx, int32_t first, int32_t count, double *position, i
  * (PMC_MODE_BOX: the cell side).  Multi-GPU: sum the histograms of the ranks (an all-reduce of nbins integers). */
 int pmc_pair_histogram(pmc_ctx *ctx, int32_t species_a, int32_t species_b, double rmax, int32_t nbins,
                        uint64_t *hist /*[nbins]*/);
+/* The `chain_correlation` callback (compute_chain_correlation, src/molecules.jl:224-246) of every chain, from the
+ * species field on the device: molecules of equal length (pmc_set_molecules), species 2 counted as -1, the squared
+ * cross terms of all site pairs summed.  Same error texts as the reference's assertions. */
+int pmc_chain_correlation(pmc_ctx *ctx, double *out /*[n_chains]*/);
+/* Histogram of the running energies energy[1] of all chains (per particle if per_particle != 0, i.e. the `energy`
+ * callback, src/utils.jl:51-53): nbins equal bins on [emin, emax), values outside are dropped.  The caller
+ * accumulates successive calls (and ranks) by adding the integer arrays. */
+int pmc_energy_histogram(pmc_ctx *ctx, double emin, double emax, int32_t nbins, int32_t per_particle,
+                         uint64_t *hist /*[nbins]*/);
 /* Move.total_calls / accepted_calls per chain and pool entry: [n_chains][n_moves]. */
 int pmc_counters(pmc_ctx *ctx, int64_t *calls, int64_t *accepted);
 /* Number of kernel launches issued by this context so far (bench.py's gpu_launches). */

@@ -230,3 +230,20 @@ def run_chains(systems: Sequence[OracleSystem], seed, t0, n_trials, pool, revert
     """Independent chains over host threads (the reference's `parallel=true`). Returns threads used."""
     hs = (C.c_void_p * len(systems))(*[s._h for s in systems])
     return lib().orc_run_chains(hs, len(systems), seed, t0, n_trials, pool, len(pool), revert_mode, n_threads)
+
+
+def chain_correlation(species, start_mol, length_mol) -> float:
+    """compute_chain_correlation (src/molecules.jl:224-243), numpy restatement; species 1-based labels,
+    start_mol 0-based first site of each molecule."""
+    species = np.asarray(species)
+    length_mol = np.asarray(length_mol)
+    n = int(length_mol[0])
+    assert np.all(length_mol == n), "All chains must have the same length"
+    assert n > 1, "Chains must have at least two particles"
+    nmol = len(start_mol)
+    arr = np.zeros((nmol, n))
+    for m, s0 in enumerate(start_mol):
+        arr[m, :] = species[s0:s0 + n]
+    arr[arr == 2] = -1
+    cross = [np.sum(arr[:, i] * arr[:, j]) / nmol for i in range(n - 1) for j in range(i + 1, n)]
+    return float(np.sum(np.square(cross)))

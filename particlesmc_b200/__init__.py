@@ -13,7 +13,8 @@ from .systems import (Atoms, CellList, EmptyList, LinkedList, Molecules, Neighbo
 from .simulation import (Metropolis, PrintTimeSteps, Simulation, StoreAcceptance, StoreCallbacks, StoreLastFrames,
                          StoreTrajectories, build_schedule, run)
 from .device import DeviceContext, measure_fma_peak
-from .observables import radial_distribution
+from .observables import EnergyHistogram, chain_correlation, radial_distribution
+from .io import EXYZ, LAMMPS, XYZ, load_chains, load_configuration, store_lastframe, store_trajectory
 from ._lib import PMCError
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -117,6 +117,48 @@ __global__ void k_egress(const double *__restrict__ x, const int32_t *__restrict
     for (int i = threadIdx.x; i < N; i += blockDim.x) raw_sp[(size_t)lc * N + i] = (long long)sp[(size_t)c * Npad + i] + 1;
 }
 
+// ---- observables of the species field --------------------------------------------------------------
+// compute_chain_correlation (src/molecules.jl:224-243): monodisperse molecules of `len` sites; species 2 counts as
+// -1, any other species as its label; for every site pair a < b the cross term sum_mol v_a v_b / Nmol, result =
+// sum of the squared cross terms.  The per-pair sums are integers (exact); one CTA per chain, thread p owns pair p.
+__global__ void k_chain_correlation(const uint8_t *__restrict__ sp, const int32_t *__restrict__ mol_start, int n_mol,
+                                    int len, int Npad, double *out) {
+    extern __shared__ double s_cross2[];
+    const int c = blockIdx.x, npairs = len * (len - 1) / 2;
+    const uint8_t *csp = sp + (size_t)c * Npad;
+    for (int p = threadIdx.x; p < npairs; p += blockDim.x) {
+        int a = 0, rem = p;  // pair index -> (a, b), pairs ordered (0,1), (0,2), ..., (1,2), ... as in the reference loop
+        while (rem >= len - 1 - a) {
+            rem -= len - 1 - a;
+            a++;
+        }
+        const int b = a + 1 + rem;
+        long long acc = 0;
+        for (int m = 0; m < n_mol; m++) {
+            const int s0 = mol_start[m];
+            const int la = (int)csp[s0 + a] + 1, lb = (int)csp[s0 + b] + 1;  // 1-based labels
+            acc += (long long)(la == 2 ? -1 : la) * (long long)(lb == 2 ? -1 : lb);
+        }
+        const double cross = (double)acc / (double)n_mol;
+        s_cross2[p] = cross * cross;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int p = 0; p < npairs; p++) t += s_cross2[p];
+        out[c] = t;
+    }
+}
+
+// histogram of the running energies of all chains (per particle if per_n), nbins equal bins on [emin, emax)
+__global__ void k_energy_histogram(const double *__restrict__ energy, int M, double inv_n, double emin, double inv_w, int nbins,
+                                   unsigned long long *hist) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= M) return;
+    const double t = (energy[c] * inv_n - emin) * inv_w;
+    if (t >= 0.0 && t < (double)nbins) atomicAdd(&hist[(int)t], 1ull);
+}
+
 // ---- FMA burst micro-benchmark (roofline denominator) ---------------------------------------------
 template <typename T>
 __global__ void k_fma_burst(T *out, int iters) {
@@ -150,6 +192,7 @@ struct pmc_ctx {
     uint16_t *bonds = nullptr;
     int32_t *mol_start = nullptr, *mol_len = nullptr;
     int n_mol = 0;
+    int mol_uniform_len = 0;  // > 0: every molecule has this many sites (pmc_chain_correlation)
     int *bad = nullptr;
     // staging
     double *raw_pos = nullptr;
@@ -472,6 +515,9 @@ int pmc_set_molecules(pmc_ctx *c, int32_t n_mol, const int32_t *start, const int
     CU(cudaMemcpyAsync(c->mol_len, length, sizeof(int32_t) * n_mol, cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     c->n_mol = n_mol;
+    c->mol_uniform_len = length[0];
+    for (int m = 1; m < n_mol; m++)
+        if (length[m] != length[0]) c->mol_uniform_len = 0;
     return PMC_OK;
 }
 
@@ -796,6 +842,62 @@ int pmc_pair_histogram(pmc_ctx *c, int32_t sa, int32_t sb, double rmax, int32_t 
     if (rc == PMC_ERR_INVALID) return fail(rc, "rmax must not exceed half the box length (minimum image)");
     if (rc) return fail(rc, "%s", pmc::box_error());
     if (e != cudaSuccess) return fail(PMC_ERR_CUDA, "pair histogram: %s", cudaGetErrorString(e));
+    return PMC_OK;
+}
+
+int pmc_chain_correlation(pmc_ctx *c, double *out) {
+    if (!c || !out) return fail(PMC_ERR_INVALID, "null argument");
+    if (c->cfg.mode != PMC_MODE_CHAINS) return fail(PMC_ERR_UNSUPPORTED, "chain_correlation is defined for PMC_MODE_CHAINS contexts");
+    if (!c->uploaded) return fail(PMC_ERR_STATE, "nothing uploaded yet");
+    if (c->n_mol < 1) return fail(PMC_ERR_STATE, "pmc_set_molecules first");
+    if (c->mol_uniform_len == 0) return fail(PMC_ERR_INVALID, "All chains must have the same length");
+    if (c->mol_uniform_len < 2) return fail(PMC_ERR_INVALID, "Chains must have at least two particles");
+    if (c->mol_uniform_len > 64) return fail(PMC_ERR_UNSUPPORTED, "molecules of more than 64 sites");
+    CU(cudaSetDevice(c->cfg.device));
+    const int M = c->cfg.n_chains, len = c->mol_uniform_len;
+    double *d_out = nullptr;
+    CU(cudaMalloc((void **)&d_out, sizeof(double) * M));
+    k_chain_correlation<<<M, 128, sizeof(double) * len * (len - 1) / 2, c->stream>>>(c->sp, c->mol_start, c->n_mol, len, c->Npad, d_out);
+    cudaError_t e = cudaGetLastError();
+    c->launches++;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, sizeof(double) * M, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return fail(PMC_ERR_CUDA, "chain correlation: %s", cudaGetErrorString(e));
+    return PMC_OK;
+}
+
+int pmc_energy_histogram(pmc_ctx *c, double emin, double emax, int32_t nbins, int32_t per_particle, uint64_t *hist) {
+    if (!c || !hist) return fail(PMC_ERR_INVALID, "null argument");
+    if (!c->energy_set) return fail(PMC_ERR_STATE, "pmc_init_energy has not been called");
+    if (nbins < 1 || nbins > (1 << 20) || !(emax > emin)) return fail(PMC_ERR_INVALID, "need 1 <= nbins <= 2^20 and emax > emin");
+    CU(cudaSetDevice(c->cfg.device));
+    const int M = c->cfg.mode == PMC_MODE_BOX ? 1 : c->cfg.n_chains;
+    std::vector<double> e_host;
+    const double *d_energy = c->energy;
+    double *d_tmp = nullptr;
+    if (c->cfg.mode == PMC_MODE_BOX) {  // the box keeps its running energy on the host side of the API
+        e_host.resize(1);
+        int rc = pmc_energy(c, e_host.data());
+        if (rc) return rc;
+        CU(cudaMalloc((void **)&d_tmp, sizeof(double)));
+        CU(cudaMemcpyAsync(d_tmp, e_host.data(), sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        d_energy = d_tmp;
+    }
+    unsigned long long *d_hist = nullptr;
+    CU(cudaMalloc((void **)&d_hist, sizeof(unsigned long long) * nbins));
+    cudaError_t e = cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * nbins, c->stream);
+    if (e == cudaSuccess) {
+        k_energy_histogram<<<(M + 255) / 256, 256, 0, c->stream>>>(d_energy, M, per_particle ? 1.0 / c->cfg.n_particles : 1.0, emin,
+                                                                  nbins / (emax - emin), nbins, d_hist);
+        e = cudaGetLastError();
+        c->launches++;
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(hist, d_hist, sizeof(unsigned long long) * nbins, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_hist);
+    if (d_tmp) cudaFree(d_tmp);
+    if (e != cudaSuccess) return fail(PMC_ERR_CUDA, "energy histogram: %s", cudaGetErrorString(e));
     return PMC_OK;
 }
 

@@ -190,6 +190,19 @@ class DeviceContext:
                                             h.ctypes.data_as(C.POINTER(C.c_uint64))))
         return h
 
+    def chain_correlation(self) -> np.ndarray:
+        """``chain_correlation`` callback of every chain (src/molecules.jl:224-246)."""
+        out = np.zeros(self.n_chains)
+        L.check(self.lib.pmc_chain_correlation(self._h, out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
+    def energy_histogram(self, emin: float, emax: float, nbins: int, per_particle: bool = True) -> np.ndarray:
+        """Counts of the chains' running energies (per particle by default) in nbins equal bins on [emin, emax)."""
+        h = np.zeros(nbins, dtype=np.uint64)
+        L.check(self.lib.pmc_energy_histogram(self._h, float(emin), float(emax), nbins, 1 if per_particle else 0,
+                                              h.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return h
+
     def counters(self):
         nm = max(self.n_moves, 1)
         calls = np.zeros((self.n_chains, nm), dtype=np.int64)

@@ -28,3 +28,31 @@ def radial_distribution(ctx, n_a: int, n_b: int, volume: float, species_a: int =
     ideal = n_pairs * shell / volume
     r = 0.5 * (edges[1:] + edges[:-1])
     return r, counts / (n_configs * ideal)
+
+
+def chain_correlation(ctx):
+    """The ``chain_correlation`` callback (src/molecules.jl:244-246) for every chain held by ``ctx``; computed on
+    the device from the species field (``pmc_chain_correlation``)."""
+    return ctx.chain_correlation()
+
+
+class EnergyHistogram:
+    """Accumulates ``pmc_energy_histogram`` calls over a run (the observable behind the energy-distribution checks
+    of test/gerhard_energy_distribution.jl); ``add`` at every schedule point, ``density`` at the end."""
+
+    def __init__(self, emin: float, emax: float, nbins: int, per_particle: bool = True):
+        self.emin, self.emax, self.nbins, self.per_particle = float(emin), float(emax), int(nbins), per_particle
+        self.counts = np.zeros(nbins, dtype=np.uint64)
+
+    def add(self, ctx, allreduce=None):
+        h = ctx.energy_histogram(self.emin, self.emax, self.nbins, self.per_particle)
+        self.counts += allreduce(h) if allreduce is not None else h
+
+    @property
+    def edges(self):
+        return np.linspace(self.emin, self.emax, self.nbins + 1)
+
+    def density(self):
+        w = (self.emax - self.emin) / self.nbins
+        tot = self.counts.sum()
+        return self.counts / (tot * w) if tot else self.counts.astype(np.float64)

@@ -113,14 +113,20 @@ def _append(path: str, line: str):
         f.write(line)
 
 
-def _write_xyz(path: str, s: Particles, t: int, mode: str):
-    """XYZ frame (header fields as in src/IO/xyz.jl:79-84), 6 decimals."""
+def _write_frame(path: str, s: Particles, t: int, mode: str, fmt, last: bool):
+    """One frame in the reference's grammar (``io.store_trajectory`` / ``io.store_lastframe``), 6 decimals."""
+    from . import io as IO
     os.makedirs(os.path.dirname(path), exist_ok=True)
-    cell = ",".join(repr(float(b)) for b in s.box)
     with open(path, mode) as f:
-        f.write(f"{s.N}\nstep:{t} columns:species,position dt:1 cell:{cell} rho:{s.density} T:{s.temperature}\n")
-        for sp, x in zip(s.species, s.position):
-            f.write(f"{int(sp)} " + " ".join(f"{v:.6f}" for v in x) + "\n")
+        (IO.store_lastframe if last else IO.store_trajectory)(f, s, t, fmt)
+
+
+def _output_format(entry: Dict):
+    """``fmt`` of a Store* entry: a Format instance or its name ("XYZ", "EXYZ", "LAMMPS"); default XYZ
+    (src/ParticlesMC.jl:277-291)."""
+    from . import io as IO
+    f = entry.get("fmt", "XYZ")
+    return getattr(IO, f)() if isinstance(f, str) else f
 
 
 def run(sim: Simulation):
@@ -157,11 +163,13 @@ def run(sim: Simulation):
                     rate = mv.accepted_calls / mv.total_calls if mv.total_calls else 0.0
                     _append(os.path.join(sim.path, "moves", str(m + 1), "acceptance.dat"), f"{t} {rate!r}\n")
             elif alg is StoreTrajectories:
+                fmt = _output_format(a)
                 for k, s in enumerate(sim.chains):
-                    _write_xyz(os.path.join(sim.path, "chains", str(k + 1), "trajectory.xyz"), s, t, "a")
+                    _write_frame(os.path.join(sim.path, "chains", str(k + 1), "trajectory" + fmt.extension), s, t, "a", fmt, False)
             elif alg is StoreLastFrames:
+                fmt = _output_format(a)
                 for k, s in enumerate(sim.chains):
-                    _write_xyz(os.path.join(sim.path, "chains", str(k + 1), "lastframe.xyz"), s, t, "w")
+                    _write_frame(os.path.join(sim.path, "chains", str(k + 1), "lastframe" + fmt.extension), s, t, "w", fmt, True)
             elif alg is PrintTimeSteps and sim.verbose:
                 print(f"t = {t}")
 

@@ -75,3 +75,67 @@ def test_box_pair_histogram_and_gr_normalisation():
     g_ref = ref / (nA * (nA - 1) / 2.0 * shell / float(np.prod(box)))
     assert np.allclose(g, g_ref, rtol=1e-12, atol=1e-12)
     assert g[:10].max() < 0.5 and abs((g * shell).sum() / shell.sum() - 1.0) < 0.1
+
+
+def test_chain_correlation_matches_reference_restatement(molecule):
+    """compute_chain_correlation (src/molecules.jl:224-246) on the reference's trimer fixture, before and after
+    MoleculeFlip moves have shuffled the species inside the molecules, against the numpy restatement."""
+    from oracle import oracle as O
+    zero_based = lambda bonds: [[j - 1 for j in b] for b in bonds]
+    par = M.flatten_model_matrix(M.Trimer())
+    starts, lens = np.arange(0, 3000, 3), np.full(1000, 3)
+    with DeviceContext(2, 3000, 3, 3, M.MODEL_KG, molecules=True) as ctx:
+        ctx.set_model(par)
+        ctx.set_bonds(zero_based(molecule["bonds"]))
+        ctx.upload(np.stack([molecule["position"]] * 2), np.stack([molecule["species"]] * 2), molecule["box"],
+                   [molecule["temperature"], 8.0])
+        with pytest.raises(L.PMCError, match="pmc_set_molecules"):
+            ctx.chain_correlation()
+        ctx.set_molecules(starts, lens)
+        cc0 = ctx.chain_correlation()
+        ref0 = O.chain_correlation(molecule["species"], starts, lens)
+        assert np.allclose(cc0, ref0, rtol=1e-13, atol=0)
+        ctx.init_energy()
+        ctx.set_moves([dict(kind="displacement", prob=0.5, sigma=0.05), dict(kind="flip", prob=0.5)])
+        ctx.seed(5)
+        ctx.run(4000)
+        cc1 = ctx.chain_correlation()
+        _, sp = ctx.download()
+        ref1 = [O.chain_correlation(sp[c], starts, lens) for c in range(2)]
+        assert np.allclose(cc1, ref1, rtol=1e-13, atol=0)
+        assert not np.allclose(cc1, cc0)  # flips were accepted, the order parameter moved
+        ctx.set_molecules(np.array([0, 3, 7]), np.array([3, 4, 2]))
+        with pytest.raises(L.PMCError, match="same length"):
+            ctx.chain_correlation()
+
+
+def test_energy_histogram_counts_chains():
+    from particlesmc_b200.observables import EnergyHistogram
+    N, nch = 216, 64
+    cfgs = []
+    for k in range(nch):
+        pos, sp, box = ka_lattice(N, 1.2, seed=k)
+        pos = pos + np.random.default_rng(k).normal(0, 0.05, pos.shape)
+        cfgs.append((pos - np.floor(pos / box) * box, sp, box))
+    with DeviceContext(nch, N, 3, 2, M.MODEL_LJ) as ctx:
+        ctx.set_model(M.flatten_model_matrix(M.KobAndersen()))
+        ctx.upload(np.stack([c[0] for c in cfgs]), np.stack([c[1] for c in cfgs]), cfgs[0][2], 1.0)
+        with pytest.raises(L.PMCError, match="pmc_init_energy"):
+            ctx.energy_histogram(-8.0, -2.0, 10)
+        ctx.init_energy()
+        ctx.set_moves([dict(kind="displacement", prob=1.0, sigma=0.05)])
+        ctx.seed(1)
+        lo, hi = -10.0, 5.0  # the chains relax from the jittered lattice (e/N ~ +1) towards the liquid (~ -5)
+        acc = EnergyHistogram(lo, hi, 40)
+        total = np.zeros(40, dtype=np.int64)
+        for _ in range(3):
+            ctx.run(5 * N)
+            e = ctx.energy() / N
+            acc.add(ctx)
+            total += np.histogram(e, bins=40, range=(lo, hi))[0]
+        # a value within rounding of a bin edge may land on either side: compare cumulative counts
+        assert int(acc.counts.sum()) == int(total.sum()) == 3 * nch
+        assert np.max(np.abs(np.cumsum(acc.counts.astype(np.int64)) - np.cumsum(total))) <= 1
+        assert abs(np.sum(acc.density()) * ((hi - lo) / 40) - 1.0) < 1e-12
+        h_tot = ctx.energy_histogram(lo * N, hi * N, 40, per_particle=False)
+        assert int(h_tot.sum()) == nch
