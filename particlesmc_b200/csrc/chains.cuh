@@ -79,9 +79,9 @@ cudaError_t configure_chain_fast(int dim, int model, int Npad, bool swaps, size_
 cudaError_t launch_chain_sweep_fast(int dim, int model, int M, size_t smem, const ChainArgs &a, cudaStream_t st);
 // speculative kernel, one warp per trial (chains_spec.cuh): Atoms + Displacement-only pools + cubic boxes + N <= 1024
 bool chain_spec_supported(int Npad, int threads);
-size_t chain_spec_smem_bytes(int dim, int Npad, int model);
-cudaError_t configure_chain_spec(int dim, int model, int Npad, size_t smem);
-cudaError_t launch_chain_sweep_spec(int dim, int model, int M, size_t smem, const ChainArgs &a, cudaStream_t st);
+size_t chain_spec_smem_bytes(int dim, int Npad, int model, bool mixed);
+cudaError_t configure_chain_spec(int dim, int model, int Npad, size_t smem, bool mixed);
+cudaError_t launch_chain_sweep_spec(int dim, int model, int M, size_t smem, const ChainArgs &a, cudaStream_t st, bool mixed);
 // PMC_MIXED variant of the fast kernel (fp32 pair terms on fixed-point coordinates, fp64 accumulation)
 size_t chain_mixed_smem_bytes(int dim, int Npad);
 cudaError_t launch_chain_sweep_mixed(int dim, int model, int M, size_t smem, const ChainArgs &a, cudaStream_t st);

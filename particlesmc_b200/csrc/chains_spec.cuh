@@ -50,7 +50,7 @@ __device__ __forceinline__ void sts_f64x2(uint32_t a, double v0, double v1) {
 struct SpecLayout {
     uint32_t x, sp, pk, q, cp, rec, pub, cnt, cnt32, par, rcs, total;
 };
-__host__ __device__ inline SpecLayout spec_layout(int dim, int Npad, bool full_par) {
+__host__ __device__ inline SpecLayout spec_layout(int dim, int Npad, bool full_par, bool mixed = false) {
     SpecLayout f;
     uint32_t o = 0;
     auto take = [&](uint32_t bytes) {
@@ -58,7 +58,7 @@ __host__ __device__ inline SpecLayout spec_layout(int dim, int Npad, bool full_p
         o += (bytes + 15u) & ~15u;
         return p;
     };
-    f.x = take(8u * dim * Npad);
+    f.x = take((mixed ? 4u : 8u) * dim * Npad);  // fp64 positions, or the 32-bit fixed-point state of PMC_MIXED
     f.sp = take(Npad);
     f.pk = take(4u * Npad);  // packed 8-bit coordinates (common.cuh), word j = particle j
     f.q = take(2u * kSpecQCap * kSpecWarps);
@@ -84,8 +84,11 @@ __device__ __forceinline__ uint32_t cand_index(int b, int lane) {
 // load): keeping them in 32 registers per thread instead (96 registers, 5 CTAs per SM) measured slower than this
 // (6 CTAs = 24 warps per SM), and a commit is one store instead of a 32-way register select.  Squeezing to 72 registers
 // and 32 KB for 7 CTAs (batch 32, queue 128) spills and measured 1 % slower again.
-template <int DIM, int MODEL, int NPAD>
-__global__ void __launch_bounds__(kSpecThreads, 6) k_chain_sweep_spec(const __grid_constant__ ChainArgs A) {
+// MIXED = true is the PMC_MIXED arithmetic of k_chain_sweep_mixed (chains_fast.cuh) in the same speculative schedule:
+// the chain state is the 32-bit fixed-point representation, pair terms are fp32 on wrapping integer distances,
+// accumulation across lanes and trials is fp64; 25 KB per chain, 8 CTAs per SM.
+template <int DIM, int MODEL, int NPAD, bool MIXED = false>
+__global__ void __launch_bounds__(kSpecThreads, MIXED ? 8 : 6) k_chain_sweep_spec(const __grid_constant__ ChainArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int KC = NPAD / 32;  // candidates per lane: k = 4 * c + e  <->  particle j = 128 * c + 4 * lane + e
     static_assert(KC >= 4 && KC <= 32 && KC % 4 == 0, "survivor masks are 32 bits, candidates come four per LDS.128");
@@ -94,19 +97,27 @@ __global__ void __launch_bounds__(kSpecThreads, 6) k_chain_sweep_spec(const __gr
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int c = blockIdx.x;
     const int N = A.N, gNpad = A.Npad, ns = A.ns;
-    constexpr bool kFullPar = !(MODEL == PMC_MODEL_LJ || MODEL == PMC_MODEL_KG);
-    const SpecLayout F = spec_layout(DIM, Npad, kFullPar);
+    constexpr bool kFullPar = !MIXED && !(MODEL == PMC_MODEL_LJ || MODEL == PMC_MODEL_KG);
+    const SpecLayout F = spec_layout(DIM, Npad, kFullPar, MIXED);
     const uint32_t sb = (uint32_t)__cvta_generic_to_shared(smem_raw);
-    const uint32_t nb8 = 8u * (uint32_t)Npad;
+    const uint32_t nb8 = 8u * (uint32_t)Npad;  // byte stride between coordinate planes (fp64)
+    constexpr uint32_t nb4 = 4u * (uint32_t)NPAD;  // ... of the fixed-point planes (MIXED)
 
     // ---- load chain state -----------------------------------------------------------------------------
     const double L = A.box[c * 3], hL = 0.5 * L;
     const double fscale = 4294967296.0 / L;
+    const float r2scale = (float)(L * L * 0x1p-32);  // MIXED: fixed-point r^2 units -> length^2
     double *gx = A.x + (size_t)c * DIM * gNpad;
     {
-        double *sx = (double *)(smem_raw + F.x);
-        for (int a = 0; a < DIM; a++)
-            for (int k = tid; k < Npad; k += kSpecThreads) sx[a * Npad + k] = k < gNpad ? gx[a * gNpad + k] : 0.0;
+        if constexpr (MIXED) {
+            uint32_t *su = (uint32_t *)(smem_raw + F.x);
+            for (int a = 0; a < DIM; a++)
+                for (int k = tid; k < Npad; k += kSpecThreads) su[a * Npad + k] = k < gNpad ? to_fixed32(gx[a * gNpad + k], fscale) : 0u;
+        } else {
+            double *sx = (double *)(smem_raw + F.x);
+            for (int a = 0; a < DIM; a++)
+                for (int k = tid; k < Npad; k += kSpecThreads) sx[a * Npad + k] = k < gNpad ? gx[a * gNpad + k] : 0.0;
+        }
         uint8_t *ssp = smem_raw + F.sp;
         const uint8_t *gsp = A.sp + (size_t)c * gNpad;
         for (int k = tid; k < Npad; k += kSpecThreads) ssp[k] = k < gNpad ? gsp[k] : 0;
@@ -116,10 +127,23 @@ __global__ void __launch_bounds__(kSpecThreads, 6) k_chain_sweep_spec(const __gr
             for (int k = tid; k < ns * ns * PMC_NPAR; k += kSpecThreads) spar[k] = A.par[k];
         }
         for (int k = tid; k < ns * ns; k += kSpecThreads) {
-            scp[4 * k + 0] = A.par[k * PMC_NPAR + PMC_P_RCUT2];
-            scp[4 * k + 1] = A.par[k * PMC_NPAR + PMC_P_EPS];
-            scp[4 * k + 2] = A.par[k * PMC_NPAR + PMC_P_SIG2];
-            scp[4 * k + 3] = A.par[k * PMC_NPAR + PMC_P_SHIFT];
+            if constexpr (MIXED) {  // float table {rc2, eps4|eps, sig2, shift, c0|ndiv2, c2, c4, -}
+                float *fcp = (float *)(smem_raw + F.cp);
+                const double *p = A.par + k * PMC_NPAR;
+                fcp[8 * k + 0] = (float)p[PMC_P_RCUT2];
+                fcp[8 * k + 1] = (float)p[PMC_P_EPS];
+                fcp[8 * k + 2] = (float)p[PMC_P_SIG2];
+                fcp[8 * k + 3] = (float)p[PMC_P_SHIFT];
+                fcp[8 * k + 4] = (float)p[5];
+                fcp[8 * k + 5] = (float)p[6];
+                fcp[8 * k + 6] = (float)p[7];
+                fcp[8 * k + 7] = 0.0f;
+            } else {
+                scp[4 * k + 0] = A.par[k * PMC_NPAR + PMC_P_RCUT2];
+                scp[4 * k + 1] = A.par[k * PMC_NPAR + PMC_P_EPS];
+                scp[4 * k + 2] = A.par[k * PMC_NPAR + PMC_P_SIG2];
+                scp[4 * k + 3] = A.par[k * PMC_NPAR + PMC_P_SHIFT];
+            }
         }
         unsigned long long *scnt = (unsigned long long *)(smem_raw + F.cnt);
         if (tid < 2 * PMC_MAX_MOVES) {
@@ -218,17 +242,37 @@ __global__ void __launch_bounds__(kSpecThreads, 6) k_chain_sweep_spec(const __gr
                 lds_f64x2(ra, d0, d1);
                 lds_f64x2(ra + 16, d2, thr);
                 lds_s32x4(ra + 32, di0, di1, di2, i);
-                const uint32_t xa = sb + F.x + 8u * (uint32_t)i;
-                double xo[3], xn[3];
-                xo[0] = lds_f64(xa);
-                xo[1] = lds_f64(xa + nb8);
-                xo[2] = (DIM == 3) ? lds_f64(xa + 2 * nb8) : 0.0;
                 const uint32_t si = lds_u8(sb + F.sp + (uint32_t)i);
-                const double t0 = xo[0] + d0, t1 = xo[1] + d1, t2 = xo[2] + d2;
-                xn[0] = wrap_once(t0, L);
-                xn[1] = wrap_once(t1, L);
-                xn[2] = (DIM == 3) ? wrap_once(t2, L) : 0.0;
-                const uint32_t uo0 = to_fixed32(xo[0], fscale), uo1 = to_fixed32(xo[1], fscale), uo2 = (DIM == 3) ? to_fixed32(xo[2], fscale) : 0u;
+                double xo[3] = {0.0, 0.0, 0.0}, xn[3] = {0.0, 0.0, 0.0};
+                uint32_t uo0, uo1, uo2, un0 = 0u, un1 = 0u, un2 = 0u;
+                int wr0, wr1, wr2;  // image-counter increments of the move
+                if constexpr (MIXED) {
+                    const uint32_t ua = sb + F.x + 4u * (uint32_t)i;
+                    uo0 = lds_u32(ua);
+                    uo1 = lds_u32(ua + nb4);
+                    uo2 = (DIM == 3) ? lds_u32(ua + 2 * nb4) : 0u;
+                    un0 = uo0 + (uint32_t)di0;  // wraps like the box does
+                    un1 = uo1 + (uint32_t)di1;
+                    un2 = uo2 + (uint32_t)di2;
+                    wr0 = (di0 > 0 && un0 < uo0) - (di0 < 0 && un0 > uo0);
+                    wr1 = (di1 > 0 && un1 < uo1) - (di1 < 0 && un1 > uo1);
+                    wr2 = (di2 > 0 && un2 < uo2) - (di2 < 0 && un2 > uo2);
+                } else {
+                    const uint32_t xa = sb + F.x + 8u * (uint32_t)i;
+                    xo[0] = lds_f64(xa);
+                    xo[1] = lds_f64(xa + nb8);
+                    xo[2] = (DIM == 3) ? lds_f64(xa + 2 * nb8) : 0.0;
+                    const double t0 = xo[0] + d0, t1 = xo[1] + d1, t2 = xo[2] + d2;
+                    xn[0] = wrap_once(t0, L);
+                    xn[1] = wrap_once(t1, L);
+                    xn[2] = (DIM == 3) ? wrap_once(t2, L) : 0.0;
+                    wr0 = (t0 >= L) - (t0 < 0.0);
+                    wr1 = (t1 >= L) - (t1 < 0.0);
+                    wr2 = (DIM == 3) ? (t2 >= L) - (t2 < 0.0) : 0;
+                    uo0 = to_fixed32(xo[0], fscale);
+                    uo1 = to_fixed32(xo[1], fscale);
+                    uo2 = (DIM == 3) ? to_fixed32(xo[2], fscale) : 0u;
+                }
                 const uint32_t umq = pack8(uo0 + (uint32_t)(di0 >> 1), uo1 + (uint32_t)(di1 >> 1), uo2 + (uint32_t)(di2 >> 1));
                 const int fthr = (int)lds_u32(ra + 64 + 4u * si);
                 // survivor mask, candidate k -> bit KC-1-k; built as independent shift chains over groups of chunks
@@ -266,6 +310,21 @@ __global__ void __launch_bounds__(kSpecThreads, 6) k_chain_sweep_spec(const __gr
                 // pair term of candidate j, branch-free (selects) so that two of them interleave in the unrolled loop
                 auto term = [&](uint32_t j) -> double {
                     const bool valid = j < (uint32_t)N && j != (uint32_t)i;
+                    if constexpr (MIXED) {  // fp32 pair terms on wrapping integer distances (minimum image for free)
+                        const uint32_t ja = sb + F.x + 4u * j;
+                        const uint32_t a0 = lds_u32(ja), a1 = lds_u32(ja + nb4), a2 = (DIM == 3) ? lds_u32(ja + 2 * nb4) : 0u;
+                        const float r2o = __uint2float_rn(dist2_u32<DIM>(uo0, uo1, uo2, a0, a1, a2)) * r2scale;
+                        const float r2n = __uint2float_rn(dist2_u32<DIM>(un0, un1, un2, a0, a1, a2)) * r2scale;
+                        const uint32_t sj = lds_u8(sb + F.sp + j);
+                        float rc2, eps, sig2, shift, c0, c2, c4, pad_;
+                        const uint32_t pp = sb + F.cp + 32u * (prow + sj);
+                        lds_f32x4(pp, rc2, eps, sig2, shift);
+                        lds_f32x4(pp + 16, c0, c2, c4, pad_);
+                        const float eo = pair_potential_f32<MODEL>(r2o, eps, sig2, shift, c0, c2, c4);
+                        const float en = pair_potential_f32<MODEL>(r2n, eps, sig2, shift, c0, c2, c4);
+                        const float d = (r2n <= rc2 ? en : 0.0f) - (r2o <= rc2 ? eo : 0.0f);
+                        return valid ? (double)d : 0.0;
+                    }
                     const uint32_t ja = sb + F.x + 8u * j;
                     const double xj0 = lds_f64(ja), xj1 = lds_f64(ja + nb8);
                     double r2o = mi_acc(xo[0], xj0, L, hL, 0.0), r2n = mi_acc(xn[0], xj0, L, hL, 0.0);
@@ -329,13 +388,19 @@ __global__ void __launch_bounds__(kSpecThreads, 6) k_chain_sweep_spec(const __gr
                 const bool acc = A.exact_exp ? accept_exact(dE, Tk, thr) : (dE < thr);
                 if (lane == 0) {
                     const uint32_t pw = pa + (uint32_t)kPubBytes * (uint32_t)warp;
-                    const int w0 = (t0 >= L) - (t0 < 0.0), w1 = (t1 >= L) - (t1 < 0.0), w2 = (DIM == 3) ? (t2 >= L) - (t2 < 0.0) : 0;
-                    sts_f64x2(pw, dE, xn[0]);
-                    sts_f64x2(pw + 16, xn[1], xn[2]);
+                    uint32_t qn;
+                    if constexpr (MIXED) {
+                        sts_f64(pw, dE);
+                        sts_u32x4(pw + 16, un0, un1, un2, 0u);
+                        qn = pack8(un0, un1, un2);
+                    } else {
+                        sts_f64x2(pw, dE, xn[0]);
+                        sts_f64x2(pw + 16, xn[1], xn[2]);
+                        qn = pack8(to_fixed32(xn[0], fscale), to_fixed32(xn[1], fscale), (DIM == 3) ? to_fixed32(xn[2], fscale) : 0u);
+                    }
                     // +32: what the conflict test of LATER trials needs | +48: what retiring THIS trial needs
-                    sts_u32x4(pw + 32, umq, (uint32_t)fthr, pack8(uo0, uo1, uo2),
-                              pack8(to_fixed32(xn[0], fscale), to_fixed32(xn[1], fscale), (DIM == 3) ? to_fixed32(xn[2], fscale) : 0u));
-                    sts_u32x4(pw + 48, (uint32_t)i, acc ? 1u : 0u, (uint32_t)((w0 + 1) | ((w1 + 1) << 2) | ((w2 + 1) << 4)),
+                    sts_u32x4(pw + 32, umq, (uint32_t)fthr, pack8(uo0, uo1, uo2), qn);
+                    sts_u32x4(pw + 48, (uint32_t)i, acc ? 1u : 0u, (uint32_t)((wr0 + 1) | ((wr1 + 1) << 2) | ((wr2 + 1) << 4)),
                               lds_u32(ra + 48));
                 }
             }
@@ -371,14 +436,24 @@ __global__ void __launch_bounds__(kSpecThreads, 6) k_chain_sweep_spec(const __gr
                             cmask |= 1u << w;
                             cqo[w] = qo;
                             cqn[w] = qn;
-                            double dE, x0, x1, x2;
-                            lds_f64x2(pw, dE, x0);
-                            lds_f64x2(pw + 16, x1, x2);
-                            const uint32_t xa = sb + F.x + 8u * iw;
-                            sts_f64(xa, x0);
-                            sts_f64(xa + nb8, x1);
-                            if constexpr (DIM == 3) sts_f64(xa + 2 * nb8, x2);
-                            E += dE;
+                            if constexpr (MIXED) {
+                                uint32_t n0, n1, n2, pad_;
+                                lds_u32x4(pw + 16, n0, n1, n2, pad_);
+                                const uint32_t ua = sb + F.x + 4u * iw;
+                                sts_u32(ua, n0);
+                                sts_u32(ua + nb4, n1);
+                                if constexpr (DIM == 3) sts_u32(ua + 2 * nb4, n2);
+                                E += lds_f64(pw);
+                            } else {
+                                double dE, x0, x1, x2;
+                                lds_f64x2(pw, dE, x0);
+                                lds_f64x2(pw + 16, x1, x2);
+                                const uint32_t xa = sb + F.x + 8u * iw;
+                                sts_f64(xa, x0);
+                                sts_f64(xa + nb8, x1);
+                                if constexpr (DIM == 3) sts_f64(xa + 2 * nb8, x2);
+                                E += dE;
+                            }
                             sts_u32(sb + F.pk + 4u * iw, qn);
                             if (tid == kImgThread && wr != 0x15u) {  // some coordinate wrapped around the box
                                 const int w0 = (int)(wr & 3u) - 1, w1 = (int)((wr >> 2) & 3u) - 1, w2 = (int)((wr >> 4) & 3u) - 1;
@@ -408,9 +483,17 @@ __global__ void __launch_bounds__(kSpecThreads, 6) k_chain_sweep_spec(const __gr
     }
     __syncthreads();
     {
-        const double *sx = (const double *)(smem_raw + F.x);
-        for (int a = 0; a < DIM; a++)
-            for (int k = tid; k < gNpad; k += kSpecThreads) gx[a * gNpad + k] = sx[a * Npad + k];
+        if constexpr (MIXED) {
+            // back to float64 at the centre of the fixed-point cell: re-quantising it gives the same integer again
+            const uint32_t *su = (const uint32_t *)(smem_raw + F.x);
+            const double inv = L * 0x1p-32;
+            for (int a = 0; a < DIM; a++)
+                for (int k = tid; k < gNpad; k += kSpecThreads) gx[a * gNpad + k] = ((double)su[a * Npad + k] + 0.5) * inv;
+        } else {
+            const double *sx = (const double *)(smem_raw + F.x);
+            for (int a = 0; a < DIM; a++)
+                for (int k = tid; k < gNpad; k += kSpecThreads) gx[a * gNpad + k] = sx[a * Npad + k];
+        }
         const unsigned long long *scnt = (const unsigned long long *)(smem_raw + F.cnt);
         const uint32_t *c32 = (const uint32_t *)(smem_raw + F.cnt32);
         if (tid == 0) A.energy[c] = E;
