@@ -316,8 +316,11 @@ int run_energy(pmc_ctx *c) {
     e.N = c->cfg.n_particles;
     e.Npad = c->Npad;
     e.ns = c->cfg.n_species;
-    CU(pmc::launch_chain_energy(c->cfg.dim, c->cfg.model_kind, c->cfg.molecules != 0, c->cfg.n_chains, c->energy_smem,
-                                e, c->stream));
+    if (c->cubic && c->cfg.prefilter >= 0 && !c->cfg.molecules && c->Npad <= 1024)
+        CU(pmc::launch_chain_energy_fast(c->cfg.dim, c->cfg.model_kind, c->cfg.n_chains, e, c->stream));
+    else
+        CU(pmc::launch_chain_energy(c->cfg.dim, c->cfg.model_kind, c->cfg.molecules != 0, c->cfg.n_chains, c->energy_smem,
+                                    e, c->stream));
     c->launches++;
     return PMC_OK;
 }

@@ -82,6 +82,8 @@ bool chain_spec_supported(int Npad, int threads);
 size_t chain_spec_smem_bytes(int dim, int Npad, int model, bool mixed);
 cudaError_t configure_chain_spec(int dim, int model, int Npad, size_t smem, bool mixed);
 cudaError_t launch_chain_sweep_spec(int dim, int model, int M, size_t smem, const ChainArgs &a, cudaStream_t st, bool mixed);
+// local energies through the 8-bit prefilter (Atoms, cubic box, N <= 1024)
+cudaError_t launch_chain_energy_fast(int dim, int model, int M, const EnergyArgs &a, cudaStream_t st);
 // PMC_MIXED variant of the fast kernel (fp32 pair terms on fixed-point coordinates, fp64 accumulation)
 size_t chain_mixed_smem_bytes(int dim, int Npad);
 cudaError_t launch_chain_sweep_mixed(int dim, int model, int M, size_t smem, const ChainArgs &a, cudaStream_t st);

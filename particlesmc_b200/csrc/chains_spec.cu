@@ -55,4 +55,37 @@ cudaError_t launch_chain_sweep_spec(int dim, int model, int M, size_t smem, cons
     return mixed ? spec_dispatch<true>(dim, model, a.Npad, go) : spec_dispatch<false>(dim, model, a.Npad, go);
 }
 
+// ---- local energies through the prefilter (k_chain_energy_fast) --------------------------------------------------
+template <typename F>
+static cudaError_t energy_dispatch(int dim, int model, int Npad, F &&f) {
+    const int np = spec_npad(Npad);
+#define PMC_CASE(D, MDL)                                                    \
+    if (dim == D && model == MDL) {                                         \
+        if (np == 256) return f(spec::k_chain_energy_fast<D, MDL, 256>);    \
+        if (np == 512) return f(spec::k_chain_energy_fast<D, MDL, 512>);    \
+        return f(spec::k_chain_energy_fast<D, MDL, 1024>);                  \
+    }
+    PMC_CASE(3, PMC_MODEL_LJ)
+    PMC_CASE(2, PMC_MODEL_LJ)
+    PMC_CASE(3, PMC_MODEL_SOFT)
+    PMC_CASE(2, PMC_MODEL_SOFT)
+    PMC_CASE(3, PMC_MODEL_SMOOTHLJ)
+    PMC_CASE(2, PMC_MODEL_SMOOTHLJ)
+    PMC_CASE(3, PMC_MODEL_KG)
+    PMC_CASE(2, PMC_MODEL_KG)
+#undef PMC_CASE
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_chain_energy_fast(int dim, int model, int M, const EnergyArgs &a, cudaStream_t st) {
+    const bool full_par = !(model == PMC_MODEL_LJ || model == PMC_MODEL_KG);
+    const size_t smem = spec::energy_layout(dim, spec_npad(a.Npad), full_par).total;
+    return energy_dispatch(dim, model, a.Npad, [&](auto kernel) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kernel<<<M, spec::kSpecThreads, smem, st>>>(a);
+        return cudaGetLastError();
+    });
+}
+
 }  // namespace pmc

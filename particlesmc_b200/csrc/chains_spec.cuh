@@ -504,5 +504,177 @@ __global__ void __launch_bounds__(kSpecThreads, MIXED ? 8 : 6) k_chain_sweep_spe
     }
 }
 
+// ==================================================================================================
+// Local energies + total through the same 8-bit prefilter (System(): src/atoms.jl:51-52, :81-88).  One CTA per
+// chain, one warp per particle i: scan all candidates against ONE sphere (x_i, rc_max(species i) + quantisation
+// margin), compact the survivors, fp64 pair terms for survivors only, shuffle reduction.  Same pairs inside the
+// cutoff as the direct kernel (k_chain_energy), a third of its instructions.  Atoms, cubic box, N <= 1024.
+// ==================================================================================================
+struct EnergyLayout {
+    uint32_t x, sp, pk, q, cp, par, thr, e, total;
+};
+__host__ __device__ inline EnergyLayout energy_layout(int dim, int Npad, bool full_par) {
+    EnergyLayout f;
+    uint32_t o = 0;
+    auto take = [&](uint32_t bytes) {
+        uint32_t p = o;
+        o += (bytes + 15u) & ~15u;
+        return p;
+    };
+    f.x = take(8u * dim * Npad);
+    f.sp = take(Npad);
+    f.pk = take(4u * Npad);
+    f.q = take(2u * kSpecQCap * kSpecWarps);
+    f.cp = take(32u * PMC_MAX_SPECIES * PMC_MAX_SPECIES);
+    f.par = take(full_par ? 8u * PMC_MAX_SPECIES * PMC_MAX_SPECIES * PMC_NPAR : 0u);
+    f.thr = take(4u * PMC_MAX_SPECIES);
+    f.e = take(8u * Npad);
+    f.total = o;
+    return f;
+}
+
+template <int DIM, int MODEL, int NPAD>
+__global__ void __launch_bounds__(kSpecThreads, 5) k_chain_energy_fast(const __grid_constant__ EnergyArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int KC = NPAD / 32, Npad = NPAD;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int c = blockIdx.x, N = A.N, gNpad = A.Npad, ns = A.ns;
+    constexpr bool kFullPar = !(MODEL == PMC_MODEL_LJ || MODEL == PMC_MODEL_KG);
+    const EnergyLayout F = energy_layout(DIM, Npad, kFullPar);
+    const uint32_t sb = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    const uint32_t nb8 = 8u * (uint32_t)Npad;
+    const double L = A.box[c * 3], hL = 0.5 * L;
+    const double fscale = 4294967296.0 / L;
+    const double *gx = A.x + (size_t)c * DIM * gNpad;
+    {
+        double *sx = (double *)(smem_raw + F.x);
+        for (int a = 0; a < DIM; a++)
+            for (int k = tid; k < Npad; k += kSpecThreads) sx[a * Npad + k] = k < gNpad ? gx[a * gNpad + k] : 0.0;
+        for (int k = tid; k < Npad; k += kSpecThreads) smem_raw[F.sp + k] = k < gNpad ? A.sp[(size_t)c * gNpad + k] : 0;
+        for (int j = tid; j < Npad; j += kSpecThreads) {
+            uint32_t u[3] = {0u, 0u, 0u};
+#pragma unroll
+            for (int a = 0; a < DIM; a++) u[a] = j < gNpad ? to_fixed32(gx[a * gNpad + j], fscale) : 0u;
+            ((uint32_t *)(smem_raw + F.pk))[j] = pack8(u[0], u[1], u[2]);
+        }
+        double *scp = (double *)(smem_raw + F.cp);
+        if constexpr (kFullPar) {
+            double *spar = (double *)(smem_raw + F.par);
+            for (int k = tid; k < ns * ns * PMC_NPAR; k += kSpecThreads) spar[k] = A.par[k];
+        }
+        for (int k = tid; k < ns * ns; k += kSpecThreads) {
+            scp[4 * k + 0] = A.par[k * PMC_NPAR + PMC_P_RCUT2];
+            scp[4 * k + 1] = A.par[k * PMC_NPAR + PMC_P_EPS];
+            scp[4 * k + 2] = A.par[k * PMC_NPAR + PMC_P_SIG2];
+            scp[4 * k + 3] = A.par[k * PMC_NPAR + PMC_P_SHIFT];
+        }
+        if (tid < PMC_MAX_SPECIES) {  // filter threshold per species of particle i
+            double rc2 = 0.0;
+            for (int b = 0; b < ns; b++) rc2 = fmax(rc2, A.par[((tid < ns ? tid : 0) * ns + b) * PMC_NPAR + PMC_P_RCUT2]);
+            ((uint32_t *)(smem_raw + F.thr))[tid] = neg_thr8(sqrt(rc2) * fscale * 0x1p-24);
+        }
+    }
+    __syncthreads();
+    const uint32_t pka = sb + F.pk + 16u * (uint32_t)lane;
+    const uint32_t qa = sb + F.q + (uint32_t)warp * (2u * kSpecQCap);
+    double *se = (double *)(smem_raw + F.e);
+    for (int i = warp; i < N; i += kSpecWarps) {
+        const uint32_t xa = sb + F.x + 8u * (uint32_t)i;
+        const double x0 = lds_f64(xa), x1 = lds_f64(xa + nb8), x2 = (DIM == 3) ? lds_f64(xa + 2 * nb8) : 0.0;
+        const uint32_t si = lds_u8(sb + F.sp + (uint32_t)i);
+        const uint32_t uq = lds_u32(sb + F.pk + 4u * (uint32_t)i);
+        const int fthr = (int)lds_u32(sb + F.thr + 4u * si);
+        constexpr int NCHUNK = KC / 4, NCH = NCHUNK >= 4 ? 4 : NCHUNK, CG = NCHUNK / NCH;
+        uint32_t mc[NCH];
+#pragma unroll
+        for (int h = 0; h < NCH; h++) mc[h] = 0u;
+#pragma unroll
+        for (int cc = 0; cc < CG; cc++) {
+#pragma unroll
+            for (int h = 0; h < NCH; h++) {
+                uint32_t w4[4];
+                lds_u32x4(pka + 512u * (uint32_t)(h * CG + cc), w4[0], w4[1], w4[2], w4[3]);
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    const uint32_t t = __vabsdiffu4(uq, w4[e]);
+                    mc[h] = __funnelshift_l((uint32_t)__dp4a((int)t, (int)t, fthr), mc[h], 1);
+                }
+            }
+        }
+        uint32_t m = mc[0];
+#pragma unroll
+        for (int h = 1; h < NCH; h++) m = (m << (4 * CG)) | mc[h];
+        const int mine = __popc(m);
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            incl += (lane >= o) ? t : 0;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        const uint32_t prow = si * (uint32_t)ns;
+        auto term = [&](uint32_t j) -> double {
+            const bool valid = j < (uint32_t)N && j != (uint32_t)i;
+            const uint32_t ja = sb + F.x + 8u * j;
+            double r2 = mi_acc(x0, lds_f64(ja), L, hL, 0.0);
+            r2 = mi_acc(x1, lds_f64(ja + nb8), L, hL, r2);
+            if constexpr (DIM == 3) r2 = mi_acc(x2, lds_f64(ja + 2 * nb8), L, hL, r2);
+            const uint32_t sj = lds_u8(sb + F.sp + j);
+            double u, rc2;
+            if constexpr (MODEL == PMC_MODEL_LJ || MODEL == PMC_MODEL_KG) {
+                double eps4, sig2, shift;
+                const uint32_t pp = sb + F.cp + 32u * (prow + sj);
+                lds_f64x2(pp, rc2, eps4);
+                lds_f64x2(pp + 16, sig2, shift);
+                u = lj_core(r2, eps4, sig2) - shift;
+            } else {
+                const double *p = (const double *)(smem_raw + F.par) + (prow + sj) * PMC_NPAR;
+                rc2 = p[PMC_P_RCUT2];
+                u = pair_potential<MODEL>(p, r2);
+            }
+            return (valid && r2 <= rc2) ? u : 0.0;
+        };
+        double part = 0.0;
+        if (total <= kSpecQCap) {
+            uint32_t wp = qa + 2u * (uint32_t)(incl - mine);
+            uint32_t mm = m;
+            while (mm) {
+                const int b = 31 - __clz(mm);
+                mm ^= 1u << b;
+                sts_u16(wp, cand_index<KC>(b, lane));
+                wp += 2;
+            }
+            __syncwarp();
+            for (int q = lane; q < total; q += 32) part += term(lds_u16(qa + 2u * (uint32_t)q));
+            __syncwarp();
+        } else {
+            uint32_t mm = m;
+            while (mm) {
+                const int b = 31 - __clz(mm);
+                mm ^= 1u << b;
+                part += term(cand_index<KC>(b, lane));
+            }
+        }
+        const double e = warp_sum(part);
+        if (lane == 0) {
+            se[i] = e;
+            A.eloc[(size_t)c * gNpad + i] = e;
+        }
+    }
+    __syncthreads();
+    // deterministic block reduction of se[0..N)
+    double s_ = 0.0;
+    for (int k = tid; k < N; k += kSpecThreads) s_ += se[k];
+    s_ = warp_sum(s_);
+    __syncthreads();
+    if (lane == 0) se[warp] = s_;
+    __syncthreads();
+    if (tid == 0) {
+        double tot = 0.0;
+        for (int w = 0; w < kSpecWarps; w++) tot += se[w];
+        A.etot[c] = tot / 2;
+    }
+}
+
 }  // namespace spec
 }  // namespace pmc

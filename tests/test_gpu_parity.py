@@ -170,6 +170,30 @@ def test_trace_parity_kob_andersen():
         assert calls[:, 0].tolist() == [3000] * M_ and accepted[:, 0].tolist() == acc.sum(axis=1).tolist()
 
 
+@pytest.mark.parametrize("name,d,prefilter", [("BHHP", 3, 0), ("BHHP", 2, 0), ("JBB", 2, 0), ("JBB", 2, 1), ("BHHP", 3, -1)])
+def test_trace_parity_models_displacement(name, d, prefilter):
+    """Every potential family and both dimensions through the sweep kernels the Displacement pool selects
+    (prefilter 0: speculative, 1: one trial at a time, -1: every candidate in fp64): decisions bit-exact against the
+    oracle replaying the same proposals, dE and final state to rounding."""
+    mm = M.NAMED_MODELS[name]()
+    ns = len(mm)
+    N = 512 if d == 3 else 400
+    par = M.flatten_model_matrix(mm)
+    pos, sp, box = lattice(N, d, 1.0 if d == 3 else 0.9, seed=7, fractions=[1.0 / ns] * ns)
+    cfgs = []
+    for k in range(2):
+        p = pos + np.random.default_rng(10 + k).normal(0, 0.04, pos.shape)
+        cfgs.append(p - np.floor(p / box) * box)
+    with DeviceContext(2, N, d, ns, M.model_kind(mm), prefilter=prefilter) as ctx:
+        ctx.set_model(par)
+        ctx.upload(np.stack(cfgs), np.stack([sp, sp]), box, [1.0, 0.4])
+        ctx.init_energy()
+        ctx.set_moves([dict(kind="displacement", prob=1.0, sigma=0.06)])
+        ctx.seed(21)
+        orcs = [O.OracleSystem(c, sp, box, T, M.model_kind(mm), par, O.LINKEDLIST) for c, T in zip(cfgs, (1.0, 0.4))]
+        check_trace(ctx, orcs, {0: (0, 0)}, 2500)
+
+
 def test_trace_parity_swaps(config0):
     """test/runtests.jl:93-129 pool on the reference's own ternary configuration."""
     par = M.flatten_model_matrix(M.JBB())
