@@ -142,6 +142,30 @@ end
 
 Arianna.finalise(alg::MetropolisB200, simulation::Arianna.Simulation) = sync_host!(simulation, alg)
 
-export MetropolisB200, sync_host!
+# ---- observables computed on the device (no download of the configurations) -----------------------------
+# chain_correlation callback (src/molecules.jl:224-246) of every chain
+function device_chain_correlation(alg::MetropolisB200, nchains::Integer)
+    out = Vector{Float64}(undef, nchains)
+    check(ccall((:pmc_chain_correlation, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), alg.ctx, out))
+    return out
+end
+
+# counts of energy[1]/N of all chains in nbins equal bins on [emin, emax)
+function device_energy_histogram(alg::MetropolisB200, emin, emax, nbins::Integer; per_particle::Bool = true)
+    h = zeros(UInt64, nbins)
+    check(ccall((:pmc_energy_histogram, LIB), Cint, (Ptr{Cvoid}, Float64, Float64, Int32, Int32, Ptr{UInt64}),
+                alg.ctx, emin, emax, nbins, per_particle, h))
+    return h
+end
+
+# raw pair-distance counts behind g(r); species labels 1-based, 0 = any
+function device_pair_histogram(alg::MetropolisB200, species_a::Integer, species_b::Integer, rmax, nbins::Integer)
+    h = zeros(UInt64, nbins)
+    check(ccall((:pmc_pair_histogram, LIB), Cint, (Ptr{Cvoid}, Int32, Int32, Float64, Int32, Ptr{UInt64}),
+                alg.ctx, species_a, species_b, rmax, nbins, h))
+    return h
+end
+
+export MetropolisB200, sync_host!, device_chain_correlation, device_energy_histogram, device_pair_histogram
 
 end # module
