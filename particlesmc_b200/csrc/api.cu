@@ -343,26 +343,21 @@ int sweep(pmc_ctx *c, int64_t n_trials, const pmc_trial *d_replay, pmc_trial *d_
     bool flips = false;  // MoleculeFlip stays in the general kernel (molecules are excluded here anyway)
     for (auto &m : c->pool) flips = flips || m.kind == PMC_MOVE_FLIP;
     const bool fastk = filter && !flips && !c->cfg.molecules && pmc::chain_fast_supported(c->cfg.dim, c->Npad, c->threads);
-    const bool speck = fastk && !any_swap && c->cfg.prefilter == 0 && pmc::chain_spec_supported(c->Npad, c->threads);
-    if (c->cfg.precision == PMC_MIXED && speck) {
-        const size_t ss = pmc::chain_spec_smem_bytes(c->cfg.dim, c->Npad, c->cfg.model_kind, true);
+    const bool mol = c->cfg.molecules != 0, mixed = c->cfg.precision == PMC_MIXED;
+    const bool speck = c->cubic && !flips && !any_swap && c->cfg.prefilter == 0 &&
+                       pmc::chain_spec_supported(c->cfg.dim, c->cfg.model_kind, c->Npad, c->threads, mol, mixed);
+    if (speck) {
+        const size_t ss = pmc::chain_spec_smem_bytes(c->cfg.dim, c->Npad, c->cfg.model_kind, mixed, mol);
         if (ss != c->spec_smem) {
-            CU(pmc::configure_chain_spec(c->cfg.dim, c->cfg.model_kind, c->Npad, ss, true));
+            CU(pmc::configure_chain_spec(c->cfg.dim, c->cfg.model_kind, c->Npad, ss, mixed, mol));
             c->spec_smem = ss;
         }
-        CU(pmc::launch_chain_sweep_spec(c->cfg.dim, c->cfg.model_kind, c->cfg.n_chains, ss, a, c->stream, true));
-    } else if (c->cfg.precision == PMC_MIXED) {
+        CU(pmc::launch_chain_sweep_spec(c->cfg.dim, c->cfg.model_kind, c->cfg.n_chains, ss, a, c->stream, mixed, mol));
+    } else if (mixed) {
         if (!fastk || any_swap)
             return fail(PMC_ERR_UNSUPPORTED, "PMC_MIXED needs a cubic box, a Displacement-only pool and %d threads per CTA", 128);
         CU(pmc::launch_chain_sweep_mixed(c->cfg.dim, c->cfg.model_kind, c->cfg.n_chains,
                                          pmc::chain_mixed_smem_bytes(c->cfg.dim, c->Npad), a, c->stream));
-    } else if (speck) {
-        const size_t ss = pmc::chain_spec_smem_bytes(c->cfg.dim, c->Npad, c->cfg.model_kind, false);
-        if (ss != c->spec_smem) {
-            CU(pmc::configure_chain_spec(c->cfg.dim, c->cfg.model_kind, c->Npad, ss, false));
-            c->spec_smem = ss;
-        }
-        CU(pmc::launch_chain_sweep_spec(c->cfg.dim, c->cfg.model_kind, c->cfg.n_chains, ss, a, c->stream, false));
     } else if (fastk) {
         const size_t fs = pmc::chain_fast_smem_bytes(c->cfg.dim, c->Npad, c->cfg.model_kind, any_swap);
         if (fs != c->fast_smem) {

@@ -9,16 +9,39 @@ namespace pmc {
 
 namespace {
 
-int spec_npad(int Npad) { return Npad <= 256 ? 256 : (Npad <= 512 ? 512 : 1024); }
+int spec_npad(int Npad) {
+    return Npad <= 256 ? 256 : (Npad <= 512 ? 512 : (Npad <= 1024 ? 1024 : (Npad <= 2048 ? 2048 : (Npad <= 3072 ? 3072 : 4096))));
+}
 
+// Shapes built: Atoms N <= 1024 (4 warps; + PMC_MIXED), Atoms N <= 2048 (2-D with 4 warps, 3-D with 8), Molecules
+// (GeneralKG, 3-D) N <= 1024 with 4 warps and N <= 4096 with 8.
 template <bool MIXED, typename F>
-cudaError_t spec_dispatch(int dim, int model, int Npad, F &&f) {
+cudaError_t spec_dispatch(int dim, int model, int Npad, bool mol, int threads, F &&f) {
     const int np = spec_npad(Npad);
-#define PMC_CASE(D, MDL)                                                              \
-    if (dim == D && model == MDL) {                                                   \
-        if (np == 256) return f(spec::k_chain_sweep_spec<D, MDL, 256, MIXED>);        \
-        if (np == 512) return f(spec::k_chain_sweep_spec<D, MDL, 512, MIXED>);        \
-        return f(spec::k_chain_sweep_spec<D, MDL, 1024, MIXED>);                      \
+    if (mol) {
+        if (MIXED || dim != 3 || model != PMC_MODEL_KG) return cudaErrorInvalidValue;
+        if constexpr (!MIXED) {
+            if (threads == 128) {
+                if (np == 256) return f(spec::k_chain_sweep_spec<3, PMC_MODEL_KG, 256, false, true, 4>);
+                if (np == 512) return f(spec::k_chain_sweep_spec<3, PMC_MODEL_KG, 512, false, true, 4>);
+                if (np == 1024) return f(spec::k_chain_sweep_spec<3, PMC_MODEL_KG, 1024, false, true, 4>);
+            } else {
+                if (np == 2048) return f(spec::k_chain_sweep_spec<3, PMC_MODEL_KG, 2048, false, true, 8>);
+                if (np == 3072) return f(spec::k_chain_sweep_spec<3, PMC_MODEL_KG, 3072, false, true, 8>);
+                if (np == 4096) return f(spec::k_chain_sweep_spec<3, PMC_MODEL_KG, 4096, false, true, 8>);
+            }
+        }
+        return cudaErrorInvalidValue;
+    }
+#define PMC_CASE(D, MDL)                                                                                     \
+    if (dim == D && model == MDL) {                                                                          \
+        if (np == 256) return f(spec::k_chain_sweep_spec<D, MDL, 256, MIXED>);                               \
+        if (np == 512) return f(spec::k_chain_sweep_spec<D, MDL, 512, MIXED>);                               \
+        if (np == 1024) return f(spec::k_chain_sweep_spec<D, MDL, 1024, MIXED>);                             \
+        if constexpr (!MIXED) {                                                                              \
+            if (np == 2048) return f(spec::k_chain_sweep_spec<D, MDL, 2048, false, false, D == 2 ? 4 : 8>);  \
+        }                                                                                                    \
+        return cudaErrorInvalidValue;                                                                        \
     }
     PMC_CASE(3, PMC_MODEL_LJ)
     PMC_CASE(2, PMC_MODEL_LJ)
@@ -32,27 +55,37 @@ cudaError_t spec_dispatch(int dim, int model, int Npad, F &&f) {
     return cudaErrorInvalidValue;
 }
 
+int spec_warps(int dim, int Npad, bool mol) { return spec_npad(Npad) <= 1024 || (dim == 2 && !mol) ? 4 : 8; }
+
 }  // namespace
 
-// 32 packed candidates per lane: N <= 1024, 128 threads (= four speculative trials per round)
-bool chain_spec_supported(int Npad, int threads) { return Npad <= 1024 && threads == spec::kSpecThreads; }
-
-size_t chain_spec_smem_bytes(int dim, int Npad, int model, bool mixed) {
-    const bool full_par = !mixed && !(model == PMC_MODEL_LJ || model == PMC_MODEL_KG);
-    return spec::spec_layout(dim, spec_npad(Npad), full_par, mixed).total;
+bool chain_spec_supported(int dim, int model, int Npad, int threads, bool mol, bool mixed) {
+    const int np = spec_npad(Npad);
+    if (Npad > np || threads != 32 * spec_warps(dim, Npad, mol)) return false;
+    if (mixed) return !mol && np <= 1024;
+    if (mol) return dim == 3 && model == PMC_MODEL_KG;
+    return np <= 2048;
 }
 
-cudaError_t configure_chain_spec(int dim, int model, int Npad, size_t smem, bool mixed) {
+size_t chain_spec_smem_bytes(int dim, int Npad, int model, bool mixed, bool mol) {
+    const bool full_par = !mixed && (mol || !(model == PMC_MODEL_LJ || model == PMC_MODEL_KG));
+    return spec::spec_layout(dim, spec_npad(Npad), full_par, mixed, spec_warps(dim, Npad, mol)).total;
+}
+
+cudaError_t configure_chain_spec(int dim, int model, int Npad, size_t smem, bool mixed, bool mol) {
     auto set = [&](auto kernel) { return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); };
-    return mixed ? spec_dispatch<true>(dim, model, Npad, set) : spec_dispatch<false>(dim, model, Npad, set);
+    const int th = 32 * spec_warps(dim, Npad, mol);
+    return mixed ? spec_dispatch<true>(dim, model, Npad, mol, th, set) : spec_dispatch<false>(dim, model, Npad, mol, th, set);
 }
 
-cudaError_t launch_chain_sweep_spec(int dim, int model, int M, size_t smem, const ChainArgs &a, cudaStream_t st, bool mixed) {
+cudaError_t launch_chain_sweep_spec(int dim, int model, int M, size_t smem, const ChainArgs &a, cudaStream_t st, bool mixed,
+                                    bool mol) {
+    const int th = 32 * spec_warps(dim, a.Npad, mol);
     auto go = [&](auto kernel) {
-        kernel<<<M, spec::kSpecThreads, smem, st>>>(a);
+        kernel<<<M, th, smem, st>>>(a);
         return cudaGetLastError();
     };
-    return mixed ? spec_dispatch<true>(dim, model, a.Npad, go) : spec_dispatch<false>(dim, model, a.Npad, go);
+    return mixed ? spec_dispatch<true>(dim, model, a.Npad, mol, th, go) : spec_dispatch<false>(dim, model, a.Npad, mol, th, go);
 }
 
 // ---- local energies through the prefilter (k_chain_energy_fast) --------------------------------------------------

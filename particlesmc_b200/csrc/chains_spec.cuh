@@ -50,7 +50,7 @@ __device__ __forceinline__ void sts_f64x2(uint32_t a, double v0, double v1) {
 struct SpecLayout {
     uint32_t x, sp, pk, q, cp, rec, pub, cnt, cnt32, par, rcs, total;
 };
-__host__ __device__ inline SpecLayout spec_layout(int dim, int Npad, bool full_par, bool mixed = false) {
+__host__ __device__ inline SpecLayout spec_layout(int dim, int Npad, bool full_par, bool mixed = false, int nw = kSpecWarps) {
     SpecLayout f;
     uint32_t o = 0;
     auto take = [&](uint32_t bytes) {
@@ -61,10 +61,10 @@ __host__ __device__ inline SpecLayout spec_layout(int dim, int Npad, bool full_p
     f.x = take((mixed ? 4u : 8u) * dim * Npad);  // fp64 positions, or the 32-bit fixed-point state of PMC_MIXED
     f.sp = take(Npad);
     f.pk = take(4u * Npad);  // packed 8-bit coordinates (common.cuh), word j = particle j
-    f.q = take(2u * kSpecQCap * kSpecWarps);
+    f.q = take(2u * kSpecQCap * nw);
     f.cp = take(32u * PMC_MAX_SPECIES * PMC_MAX_SPECIES);
     f.rec = take((uint32_t)kRecBytes * kSpecBatch);
-    f.pub = take(2u * kPubBytes * kSpecWarps + 16u);  // two alternating sets + the retired count of the round
+    f.pub = take(2u * kPubBytes * nw + 16u);  // two alternating sets + the retired count of the round
     f.cnt = take(8u * 2 * PMC_MAX_MOVES);
     f.cnt32 = take(4u * 2 * PMC_MAX_MOVES);  // per-batch counters (native 32-bit shared atomics), folded into cnt
     f.par = take(full_par ? 8u * PMC_MAX_SPECIES * PMC_MAX_SPECIES * PMC_NPAR : 0u);
@@ -87,18 +87,25 @@ __device__ __forceinline__ uint32_t cand_index(int b, int lane) {
 // MIXED = true is the PMC_MIXED arithmetic of k_chain_sweep_mixed (chains_fast.cuh) in the same speculative schedule:
 // the chain state is the 32-bit fixed-point representation, pair terms are fp32 on wrapping integer distances,
 // accumulation across lanes and trials is fp64; 25 KB per chain, 8 CTAs per SM.
-template <int DIM, int MODEL, int NPAD, bool MIXED = false>
-__global__ void __launch_bounds__(kSpecThreads, MIXED ? 8 : 6) k_chain_sweep_spec(const __grid_constant__ ChainArgs A) {
+// NW = warps per CTA = trials in flight per round (4 for N <= 1024; 8 for the larger shapes, whose chains are few per SM).
+// MOL = true: Molecules -- bonded partners (A.bonds, <= PMC_MAX_BONDS per site) are excluded from the pair pass and
+// contribute bond_potential (FENE + bonded LJ, src/models.jl:202-226) in a separate pass of the first lanes.
+// NPAD up to 4096: the survivor mask of a lane is NPAD / 1024 words.
+template <int DIM, int MODEL, int NPAD, bool MIXED = false, bool MOL = false, int NW = 4>
+__global__ void __launch_bounds__(32 * NW, NPAD <= 1024 ? (MIXED ? 8 : (MOL ? 5 : 6)) : 2) k_chain_sweep_spec(const __grid_constant__ ChainArgs A) {
+    constexpr int NT = 32 * NW;
+    static_assert(!(MIXED && MOL) && !(MIXED && NW != 4), "PMC_MIXED is implemented for Atoms, N <= 1024");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int KC = NPAD / 32;  // candidates per lane: k = 4 * c + e  <->  particle j = 128 * c + 4 * lane + e
-    static_assert(KC >= 4 && KC <= 32 && KC % 4 == 0, "survivor masks are 32 bits, candidates come four per LDS.128");
+    constexpr int NM = (KC + 31) / 32, KCW = KC < 32 ? KC : 32;  // mask words per lane, candidates per word
+    static_assert(KC >= 4 && KC % 4 == 0 && (KC <= 32 || KC % 32 == 0) && NM <= 4, "candidates come four per LDS.128, 32 per mask word");
     constexpr int Npad = NPAD;
     constexpr int kImgThread = 1, kCntThread = 2;  // lanes of warp 0 (the retiring warp)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int c = blockIdx.x;
     const int N = A.N, gNpad = A.Npad, ns = A.ns;
-    constexpr bool kFullPar = !MIXED && !(MODEL == PMC_MODEL_LJ || MODEL == PMC_MODEL_KG);
-    const SpecLayout F = spec_layout(DIM, Npad, kFullPar, MIXED);
+    constexpr bool kFullPar = !MIXED && (MOL || !(MODEL == PMC_MODEL_LJ || MODEL == PMC_MODEL_KG));
+    const SpecLayout F = spec_layout(DIM, Npad, kFullPar, MIXED, NW);
     const uint32_t sb = (uint32_t)__cvta_generic_to_shared(smem_raw);
     const uint32_t nb8 = 8u * (uint32_t)Npad;  // byte stride between coordinate planes (fp64)
     constexpr uint32_t nb4 = 4u * (uint32_t)NPAD;  // ... of the fixed-point planes (MIXED)
@@ -112,21 +119,21 @@ __global__ void __launch_bounds__(kSpecThreads, MIXED ? 8 : 6) k_chain_sweep_spe
         if constexpr (MIXED) {
             uint32_t *su = (uint32_t *)(smem_raw + F.x);
             for (int a = 0; a < DIM; a++)
-                for (int k = tid; k < Npad; k += kSpecThreads) su[a * Npad + k] = k < gNpad ? to_fixed32(gx[a * gNpad + k], fscale) : 0u;
+                for (int k = tid; k < Npad; k += NT) su[a * Npad + k] = k < gNpad ? to_fixed32(gx[a * gNpad + k], fscale) : 0u;
         } else {
             double *sx = (double *)(smem_raw + F.x);
             for (int a = 0; a < DIM; a++)
-                for (int k = tid; k < Npad; k += kSpecThreads) sx[a * Npad + k] = k < gNpad ? gx[a * gNpad + k] : 0.0;
+                for (int k = tid; k < Npad; k += NT) sx[a * Npad + k] = k < gNpad ? gx[a * gNpad + k] : 0.0;
         }
         uint8_t *ssp = smem_raw + F.sp;
         const uint8_t *gsp = A.sp + (size_t)c * gNpad;
-        for (int k = tid; k < Npad; k += kSpecThreads) ssp[k] = k < gNpad ? gsp[k] : 0;
+        for (int k = tid; k < Npad; k += NT) ssp[k] = k < gNpad ? gsp[k] : 0;
         double *scp = (double *)(smem_raw + F.cp);
         if constexpr (kFullPar) {
             double *spar = (double *)(smem_raw + F.par);
-            for (int k = tid; k < ns * ns * PMC_NPAR; k += kSpecThreads) spar[k] = A.par[k];
+            for (int k = tid; k < ns * ns * PMC_NPAR; k += NT) spar[k] = A.par[k];
         }
-        for (int k = tid; k < ns * ns; k += kSpecThreads) {
+        for (int k = tid; k < ns * ns; k += NT) {
             if constexpr (MIXED) {  // float table {rc2, eps4|eps, sig2, shift, c0|ndiv2, c2, c4, -}
                 float *fcp = (float *)(smem_raw + F.cp);
                 const double *p = A.par + k * PMC_NPAR;
@@ -156,7 +163,7 @@ __global__ void __launch_bounds__(kSpecThreads, MIXED ? 8 : 6) k_chain_sweep_spe
             ((double *)(smem_raw + F.rcs))[tid] = sqrt(rc2);
         }
     }
-    for (int j = tid; j < Npad; j += kSpecThreads) {
+    for (int j = tid; j < Npad; j += NT) {
         uint32_t u[3] = {0u, 0u, 0u};
 #pragma unroll
         for (int a = 0; a < DIM; a++) u[a] = j < gNpad ? to_fixed32(gx[a * gNpad + j], fscale) : 0u;
@@ -175,8 +182,8 @@ __global__ void __launch_bounds__(kSpecThreads, MIXED ? 8 : 6) k_chain_sweep_spe
     for (long long tb = 0; tb < A.n_trials; tb += kSpecBatch) {
         const int nb = (int)min((long long)kSpecBatch, A.n_trials - tb);
         __syncthreads();
-        if (tid >= kSpecThreads - 2 * PMC_MAX_MOVES) {  // fold the counters of the previous batch
-            const int k = tid - (kSpecThreads - 2 * PMC_MAX_MOVES);
+        if (tid >= NT - 2 * PMC_MAX_MOVES) {  // fold the counters of the previous batch
+            const int k = tid - (NT - 2 * PMC_MAX_MOVES);
             uint32_t *c32 = (uint32_t *)(smem_raw + F.cnt32);
             ((unsigned long long *)(smem_raw + F.cnt))[k] += c32[k];
             c32[k] = 0u;
@@ -232,8 +239,8 @@ __global__ void __launch_bounds__(kSpecThreads, MIXED ? 8 : 6) k_chain_sweep_spe
 
         int cur = 0;
         while (cur < nb) {  // one round: up to four consecutive trials, one per warp
-            const int nspec = min(kSpecWarps, nb - cur);
-            const uint32_t pa = sb + F.pub + (uint32_t)(kPubBytes * kSpecWarps) * slot;
+            const int nspec = min(NW, nb - cur);
+            const uint32_t pa = sb + F.pub + (uint32_t)(kPubBytes * NW) * slot;
             if (warp < nspec) {
                 // ---- evaluate trial cur + warp against the current state (this warp alone) ---------------------
                 const uint32_t ra = sb + F.rec + (uint32_t)kRecBytes * (uint32_t)(cur + warp);
@@ -275,29 +282,35 @@ __global__ void __launch_bounds__(kSpecThreads, MIXED ? 8 : 6) k_chain_sweep_spe
                 }
                 const uint32_t umq = pack8(uo0 + (uint32_t)(di0 >> 1), uo1 + (uint32_t)(di1 >> 1), uo2 + (uint32_t)(di2 >> 1));
                 const int fthr = (int)lds_u32(ra + 64 + 4u * si);
-                // survivor mask, candidate k -> bit KC-1-k; built as independent shift chains over groups of chunks
-                // (the funnel shifts of one chain depend on each other) and concatenated afterwards
-                constexpr int NCHUNK = KC / 4, NCH = NCHUNK >= 4 ? 4 : NCHUNK, CG = NCHUNK / NCH;
-                uint32_t mc[NCH];
+                // survivor masks: candidate k = 32 * word + k' -> bit KCW-1-k' of its word; every word is built as
+                // independent shift chains over groups of chunks (the funnel shifts of one chain depend on each other)
+                constexpr int NCHUNK = KCW / 4, NCH = NCHUNK >= 4 ? 4 : NCHUNK, CG = NCHUNK / NCH;
+                uint32_t m[NM];
+                int mine = 0;
 #pragma unroll
-                for (int h = 0; h < NCH; h++) mc[h] = 0u;
+                for (int mw = 0; mw < NM; mw++) {
+                    uint32_t mc[NCH];
 #pragma unroll
-                for (int cc = 0; cc < CG; cc++) {
+                    for (int h = 0; h < NCH; h++) mc[h] = 0u;
 #pragma unroll
-                    for (int h = 0; h < NCH; h++) {
-                        uint32_t w4[4];
-                        lds_u32x4(pka + 512u * (uint32_t)(h * CG + cc), w4[0], w4[1], w4[2], w4[3]);
+                    for (int cc = 0; cc < CG; cc++) {
 #pragma unroll
-                        for (int e = 0; e < 4; e++) {
-                            const uint32_t t = __vabsdiffu4(umq, w4[e]);
-                            mc[h] = __funnelshift_l((uint32_t)__dp4a((int)t, (int)t, fthr), mc[h], 1);
+                        for (int h = 0; h < NCH; h++) {
+                            uint32_t w4[4];
+                            lds_u32x4(pka + 512u * (uint32_t)(mw * 8 + h * CG + cc), w4[0], w4[1], w4[2], w4[3]);
+#pragma unroll
+                            for (int e = 0; e < 4; e++) {
+                                const uint32_t t = __vabsdiffu4(umq, w4[e]);
+                                mc[h] = __funnelshift_l((uint32_t)__dp4a((int)t, (int)t, fthr), mc[h], 1);
+                            }
                         }
                     }
-                }
-                uint32_t m = mc[0];
+                    uint32_t mm = mc[0];
 #pragma unroll
-                for (int h = 1; h < NCH; h++) m = (m << (4 * CG)) | mc[h];
-                const int mine = __popc(m);
+                    for (int h = 1; h < NCH; h++) mm = (mm << (4 * CG)) | mc[h];
+                    m[mw] = mm;
+                    mine += __popc(mm);
+                }
                 int incl = mine;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
@@ -307,9 +320,18 @@ __global__ void __launch_bounds__(kSpecThreads, MIXED ? 8 : 6) k_chain_sweep_spe
                 const int total = __shfl_sync(0xffffffffu, incl, 31);
                 const uint32_t prow = si * (uint32_t)ns;
                 double part = 0.0;
+                uint32_t bi[PMC_MAX_BONDS];  // MOL: bonded partners of i (0xFFFF = none)
+                if constexpr (MOL) {
+#pragma unroll
+                    for (int k = 0; k < PMC_MAX_BONDS; k++) bi[k] = (uint32_t)__ldg(A.bonds + (size_t)i * PMC_MAX_BONDS + k);
+                }
                 // pair term of candidate j, branch-free (selects) so that two of them interleave in the unrolled loop
                 auto term = [&](uint32_t j) -> double {
-                    const bool valid = j < (uint32_t)N && j != (uint32_t)i;
+                    bool valid = j < (uint32_t)N && j != (uint32_t)i;
+                    if constexpr (MOL) {  // bonded partners are handled by the bond pass below
+#pragma unroll
+                        for (int k = 0; k < PMC_MAX_BONDS; k++) valid = valid && j != bi[k];
+                    }
                     if constexpr (MIXED) {  // fp32 pair terms on wrapping integer distances (minimum image for free)
                         const uint32_t ja = sb + F.x + 4u * j;
                         const uint32_t a0 = lds_u32(ja), a1 = lds_u32(ja + nb4), a2 = (DIM == 3) ? lds_u32(ja + 2 * nb4) : 0u;
@@ -356,12 +378,15 @@ __global__ void __launch_bounds__(kSpecThreads, MIXED ? 8 : 6) k_chain_sweep_spe
                 if (total <= kSpecQCap) {
                     // compaction: each lane appends its survivors (ascending candidate index) at its scan offset
                     uint32_t wp = qa + 2u * (uint32_t)(incl - mine);
-                    uint32_t mm = m;
-                    while (mm) {
-                        const int b = 31 - __clz(mm);
-                        mm ^= 1u << b;
-                        sts_u16(wp, cand_index<KC>(b, lane));
-                        wp += 2;
+#pragma unroll
+                    for (int mw = 0; mw < NM; mw++) {
+                        uint32_t mm = m[mw];
+                        while (mm) {
+                            const int b = 31 - __clz(mm);
+                            mm ^= 1u << b;
+                            sts_u16(wp, cand_index<KCW>(b, lane) + 1024u * (uint32_t)mw);
+                            wp += 2;
+                        }
                     }
                     __syncwarp();
                     // two survivors per lane and iteration while both exist (the dependent fp64 chains of one pair
@@ -377,11 +402,31 @@ __global__ void __launch_bounds__(kSpecThreads, MIXED ? 8 : 6) k_chain_sweep_spe
                     for (; q < total; q += 32) part += term(lds_u16(qa + 2u * (uint32_t)q));
                     __syncwarp();
                 } else {  // tiny boxes where (nearly) every candidate survives: no queue, each lane its own survivors
-                    uint32_t mm = m;
-                    while (mm) {
-                        const int b = 31 - __clz(mm);
-                        mm ^= 1u << b;
-                        part += term(cand_index<KC>(b, lane));
+#pragma unroll
+                    for (int mw = 0; mw < NM; mw++) {
+                        uint32_t mm = m[mw];
+                        while (mm) {
+                            const int b = 31 - __clz(mm);
+                            mm ^= 1u << b;
+                            part += term(cand_index<KCW>(b, lane) + 1024u * (uint32_t)mw);
+                        }
+                    }
+                }
+                if constexpr (MOL) {  // bond pass: lane k owns bonded partner k of particle i
+                    const uint32_t b = lane < PMC_MAX_BONDS ? (uint32_t)__ldg(A.bonds + (size_t)i * PMC_MAX_BONDS + lane) : 0xFFFFu;
+                    if (b != 0xFFFFu) {
+                        const uint32_t ja = sb + F.x + 8u * b;
+                        const double xj0 = lds_f64(ja), xj1 = lds_f64(ja + nb8);
+                        double r2o = mi_acc(xo[0], xj0, L, hL, 0.0), r2n = mi_acc(xn[0], xj0, L, hL, 0.0);
+                        r2o = mi_acc(xo[1], xj1, L, hL, r2o);
+                        r2n = mi_acc(xn[1], xj1, L, hL, r2n);
+                        if constexpr (DIM == 3) {
+                            const double xj2 = lds_f64(ja + 2 * nb8);
+                            r2o = mi_acc(xo[2], xj2, L, hL, r2o);
+                            r2n = mi_acc(xn[2], xj2, L, hL, r2n);
+                        }
+                        const double *p = (const double *)(smem_raw + F.par) + (prow + lds_u8(sb + F.sp + b)) * PMC_NPAR;
+                        part += bond_potential(p, r2n) - bond_potential(p, r2o);
                     }
                 }
                 const double dE = warp_sum(part);
@@ -407,11 +452,12 @@ __global__ void __launch_bounds__(kSpecThreads, MIXED ? 8 : 6) k_chain_sweep_spe
             __syncthreads();
             // ---- retire the round in trial order: warp 0 alone, the others wait at the second barrier --------------
             if (warp == 0) {
-            uint32_t cqo[kSpecWarps], cqn[kSpecWarps];  // packed old / new position of trials accepted in this round
-            uint32_t cmask = 0;
             int ndone = 0;
+            if constexpr (NW == 4) {
+            uint32_t cqo[NW], cqn[NW];  // packed old / new position of trials accepted in this round
+            uint32_t cmask = 0;
 #pragma unroll
-            for (int w = 0; w < kSpecWarps; w++) {
+            for (int w = 0; w < NW; w++) {
                 if (w < nspec && ndone == w) {  // uniform
                     const uint32_t pw = pa + (uint32_t)kPubBytes * (uint32_t)w;
                     uint32_t umq, fthr, qo, qn;
@@ -474,10 +520,58 @@ __global__ void __launch_bounds__(kSpecThreads, MIXED ? 8 : 6) k_chain_sweep_spe
                     }
                 }
             }
-            if (lane == 0) sts_u32(sb + F.pub + 2u * kPubBytes * kSpecWarps, (uint32_t)ndone);
+            } else {
+                // the same retirement, rolled: the packed positions of the accepted trials are read back from the
+                // published entries instead of living in registers
+                uint32_t cmask = 0;
+                for (int w = 0; w < nspec; w++) {
+                    const uint32_t pw = pa + (uint32_t)kPubBytes * (uint32_t)w;
+                    uint32_t umq, fthr, qo, qn;
+                    lds_u32x4(pw + 32, umq, fthr, qo, qn);
+                    int conflict = 0;
+                    for (uint32_t mm = cmask; mm; mm &= mm - 1u) {
+                        const uint32_t pv = pa + (uint32_t)kPubBytes * (uint32_t)(__ffs((int)mm) - 1);
+                        const uint32_t ta = __vabsdiffu4(umq, lds_u32(pv + 40)), tb_ = __vabsdiffu4(umq, lds_u32(pv + 44));
+                        conflict |= __dp4a((int)ta, (int)ta, (int)fthr) | __dp4a((int)tb_, (int)tb_, (int)fthr);
+                    }
+                    if (conflict < 0) break;
+                    ndone = w + 1;
+                    uint32_t iw, fl, wr, mv;
+                    lds_u32x4(pw + 48, iw, fl, wr, mv);
+                    const bool acc = fl != 0u;
+                    if (acc) {
+                        cmask |= 1u << w;
+                        double dE, x0, x1, x2;
+                        lds_f64x2(pw, dE, x0);
+                        lds_f64x2(pw + 16, x1, x2);
+                        const uint32_t xa = sb + F.x + 8u * iw;
+                        sts_f64(xa, x0);
+                        sts_f64(xa + nb8, x1);
+                        if constexpr (DIM == 3) sts_f64(xa + 2 * nb8, x2);
+                        E += dE;
+                        sts_u32(sb + F.pk + 4u * iw, qn);
+                        if (tid == kImgThread && wr != 0x15u) {
+                            const int w0 = (int)(wr & 3u) - 1, w1 = (int)((wr >> 2) & 3u) - 1, w2 = (int)((wr >> 4) & 3u) - 1;
+                            if (w0) atomicAdd(&gimg[iw], w0);
+                            if (w1) atomicAdd(&gimg[gNpad + iw], w1);
+                            if (DIM == 3 && w2) atomicAdd(&gimg[2 * gNpad + iw], w2);
+                        }
+                    }
+                    if (tid == kCntThread) {
+                        uint32_t *c32 = (uint32_t *)(smem_raw + F.cnt32);
+                        atomicAdd(&c32[mv], 1u);
+                        if (acc) atomicAdd(&c32[PMC_MAX_MOVES + mv], 1u);
+                        if (dbg_out) {
+                            if (A.acc_out) A.acc_out[(size_t)c * A.n_trials + tb + cur + w] = acc ? 1 : 0;
+                            if (A.dE_out) A.dE_out[(size_t)c * A.n_trials + tb + cur + w] = lds_f64(pw);
+                        }
+                    }
+                }
+            }
+            if (lane == 0) sts_u32(sb + F.pub + 2u * kPubBytes * NW, (uint32_t)ndone);
             }
             __syncthreads();
-            cur += (int)lds_u32(sb + F.pub + 2u * kPubBytes * kSpecWarps);
+            cur += (int)lds_u32(sb + F.pub + 2u * kPubBytes * NW);
             slot ^= 1u;
         }
     }
@@ -488,11 +582,11 @@ __global__ void __launch_bounds__(kSpecThreads, MIXED ? 8 : 6) k_chain_sweep_spe
             const uint32_t *su = (const uint32_t *)(smem_raw + F.x);
             const double inv = L * 0x1p-32;
             for (int a = 0; a < DIM; a++)
-                for (int k = tid; k < gNpad; k += kSpecThreads) gx[a * gNpad + k] = ((double)su[a * Npad + k] + 0.5) * inv;
+                for (int k = tid; k < gNpad; k += NT) gx[a * gNpad + k] = ((double)su[a * Npad + k] + 0.5) * inv;
         } else {
             const double *sx = (const double *)(smem_raw + F.x);
             for (int a = 0; a < DIM; a++)
-                for (int k = tid; k < gNpad; k += kSpecThreads) gx[a * gNpad + k] = sx[a * Npad + k];
+                for (int k = tid; k < gNpad; k += NT) gx[a * gNpad + k] = sx[a * Npad + k];
         }
         const unsigned long long *scnt = (const unsigned long long *)(smem_raw + F.cnt);
         const uint32_t *c32 = (const uint32_t *)(smem_raw + F.cnt32);
