@@ -204,6 +204,7 @@ struct pmc_ctx {
     bool model_set = false, uploaded = false, energy_set = false, bonds_set = false;
     int64_t launches = 0;
     size_t sweep_smem = 0, sweep_smem_filter = 0, energy_smem = 0, fast_smem = 0, spec_smem = 0;
+    bool spec_swaps = false;
     bool sweep_swap_cfg = false;
     bool cubic = true;  // every uploaded chain has a cubic box (enables the fixed-point prefilter)
     pmc::BoxState *boxst = nullptr;
@@ -344,15 +345,16 @@ int sweep(pmc_ctx *c, int64_t n_trials, const pmc_trial *d_replay, pmc_trial *d_
     for (auto &m : c->pool) flips = flips || m.kind == PMC_MOVE_FLIP;
     const bool fastk = filter && !flips && !c->cfg.molecules && pmc::chain_fast_supported(c->cfg.dim, c->Npad, c->threads);
     const bool mol = c->cfg.molecules != 0, mixed = c->cfg.precision == PMC_MIXED;
-    const bool speck = c->cubic && !flips && !any_swap && c->cfg.prefilter == 0 &&
-                       pmc::chain_spec_supported(c->cfg.dim, c->cfg.model_kind, c->Npad, c->threads, mol, mixed);
+    const bool speck = c->cubic && !flips && c->cfg.prefilter == 0 &&
+                       pmc::chain_spec_supported(c->cfg.dim, c->cfg.model_kind, c->Npad, c->threads, mol, mixed, any_swap);
     if (speck) {
-        const size_t ss = pmc::chain_spec_smem_bytes(c->cfg.dim, c->Npad, c->cfg.model_kind, mixed, mol);
-        if (ss != c->spec_smem) {
-            CU(pmc::configure_chain_spec(c->cfg.dim, c->cfg.model_kind, c->Npad, ss, mixed, mol));
+        const size_t ss = pmc::chain_spec_smem_bytes(c->cfg.dim, c->Npad, c->cfg.model_kind, mixed, mol, any_swap);
+        if (ss != c->spec_smem || any_swap != c->spec_swaps) {
+            CU(pmc::configure_chain_spec(c->cfg.dim, c->cfg.model_kind, c->Npad, ss, mixed, mol, any_swap));
             c->spec_smem = ss;
+            c->spec_swaps = any_swap;
         }
-        CU(pmc::launch_chain_sweep_spec(c->cfg.dim, c->cfg.model_kind, c->cfg.n_chains, ss, a, c->stream, mixed, mol));
+        CU(pmc::launch_chain_sweep_spec(c->cfg.dim, c->cfg.model_kind, c->cfg.n_chains, ss, a, c->stream, mixed, mol, any_swap));
     } else if (mixed) {
         if (!fastk || any_swap)
             return fail(PMC_ERR_UNSUPPORTED, "PMC_MIXED needs a cubic box, a Displacement-only pool and %d threads per CTA", 128);

@@ -77,13 +77,13 @@ bool chain_fast_supported(int dim, int Npad, int threads);
 size_t chain_fast_smem_bytes(int dim, int Npad, int model, bool swaps);
 cudaError_t configure_chain_fast(int dim, int model, int Npad, bool swaps, size_t smem);
 cudaError_t launch_chain_sweep_fast(int dim, int model, int M, size_t smem, const ChainArgs &a, cudaStream_t st);
-// speculative kernel, one warp per trial (chains_spec.cuh): Displacement-only pools, cubic boxes; Atoms N <= 2048,
-// Molecules (GeneralKG, 3-D) N <= 4096, PMC_MIXED N <= 1024
-bool chain_spec_supported(int dim, int model, int Npad, int threads, bool mol, bool mixed);
-size_t chain_spec_smem_bytes(int dim, int Npad, int model, bool mixed, bool mol);
-cudaError_t configure_chain_spec(int dim, int model, int Npad, size_t smem, bool mixed, bool mol);
+// speculative kernel, one warp per trial (chains_spec.cuh), cubic boxes: Atoms N <= 2048 with Displacement and
+// DiscreteSwap pools, Molecules (GeneralKG, 3-D, Displacement) N <= 4096, PMC_MIXED (Displacement) N <= 1024
+bool chain_spec_supported(int dim, int model, int Npad, int threads, bool mol, bool mixed, bool swaps);
+size_t chain_spec_smem_bytes(int dim, int Npad, int model, bool mixed, bool mol, bool swaps);
+cudaError_t configure_chain_spec(int dim, int model, int Npad, size_t smem, bool mixed, bool mol, bool swaps);
 cudaError_t launch_chain_sweep_spec(int dim, int model, int M, size_t smem, const ChainArgs &a, cudaStream_t st, bool mixed,
-                                    bool mol);
+                                    bool mol, bool swaps);
 // local energies through the 8-bit prefilter (Atoms, cubic box, N <= 1024)
 cudaError_t launch_chain_energy_fast(int dim, int model, int M, const EnergyArgs &a, cudaStream_t st);
 // PMC_MIXED variant of the fast kernel (fp32 pair terms on fixed-point coordinates, fp64 accumulation)

@@ -15,12 +15,13 @@ int spec_npad(int Npad) {
 
 // Shapes built: Atoms N <= 1024 (4 warps; + PMC_MIXED), Atoms N <= 2048 (2-D with 4 warps, 3-D with 8), Molecules
 // (GeneralKG, 3-D) N <= 1024 with 4 warps and N <= 4096 with 8.
-template <bool MIXED, typename F>
+template <bool MIXED, bool SWAPS, typename F>
 cudaError_t spec_dispatch(int dim, int model, int Npad, bool mol, int threads, F &&f) {
     const int np = spec_npad(Npad);
+    if (SWAPS && (mol || MIXED || model == PMC_MODEL_KG)) return cudaErrorInvalidValue;
     if (mol) {
         if (MIXED || dim != 3 || model != PMC_MODEL_KG) return cudaErrorInvalidValue;
-        if constexpr (!MIXED) {
+        if constexpr (!MIXED && !SWAPS) {
             if (threads == 128) {
                 if (np == 256) return f(spec::k_chain_sweep_spec<3, PMC_MODEL_KG, 256, false, true, 4>);
                 if (np == 512) return f(spec::k_chain_sweep_spec<3, PMC_MODEL_KG, 512, false, true, 4>);
@@ -33,15 +34,17 @@ cudaError_t spec_dispatch(int dim, int model, int Npad, bool mol, int threads, F
         }
         return cudaErrorInvalidValue;
     }
-#define PMC_CASE(D, MDL)                                                                                     \
-    if (dim == D && model == MDL) {                                                                          \
-        if (np == 256) return f(spec::k_chain_sweep_spec<D, MDL, 256, MIXED>);                               \
-        if (np == 512) return f(spec::k_chain_sweep_spec<D, MDL, 512, MIXED>);                               \
-        if (np == 1024) return f(spec::k_chain_sweep_spec<D, MDL, 1024, MIXED>);                             \
-        if constexpr (!MIXED) {                                                                              \
-            if (np == 2048) return f(spec::k_chain_sweep_spec<D, MDL, 2048, false, false, D == 2 ? 4 : 8>);  \
-        }                                                                                                    \
-        return cudaErrorInvalidValue;                                                                        \
+#define PMC_CASE(D, MDL)                                                                                                \
+    if (dim == D && model == MDL) {                                                                                     \
+        if constexpr (!SWAPS || MDL != PMC_MODEL_KG) {                                                                  \
+            if (np == 256) return f(spec::k_chain_sweep_spec<D, MDL, 256, MIXED, false, 4, SWAPS>);                     \
+            if (np == 512) return f(spec::k_chain_sweep_spec<D, MDL, 512, MIXED, false, 4, SWAPS>);                     \
+            if (np == 1024) return f(spec::k_chain_sweep_spec<D, MDL, 1024, MIXED, false, 4, SWAPS>);                   \
+            if constexpr (!MIXED) {                                                                                     \
+                if (np == 2048) return f(spec::k_chain_sweep_spec<D, MDL, 2048, false, false, D == 2 ? 4 : 8, SWAPS>);  \
+            }                                                                                                           \
+        }                                                                                                               \
+        return cudaErrorInvalidValue;                                                                                   \
     }
     PMC_CASE(3, PMC_MODEL_LJ)
     PMC_CASE(2, PMC_MODEL_LJ)
@@ -59,33 +62,41 @@ int spec_warps(int dim, int Npad, bool mol) { return spec_npad(Npad) <= 1024 || 
 
 }  // namespace
 
-bool chain_spec_supported(int dim, int model, int Npad, int threads, bool mol, bool mixed) {
+bool chain_spec_supported(int dim, int model, int Npad, int threads, bool mol, bool mixed, bool swaps) {
     const int np = spec_npad(Npad);
     if (Npad > np || threads != 32 * spec_warps(dim, Npad, mol)) return false;
+    if (swaps && (mol || mixed || model == PMC_MODEL_KG)) return false;
     if (mixed) return !mol && np <= 1024;
     if (mol) return dim == 3 && model == PMC_MODEL_KG;
     return np <= 2048;
 }
 
-size_t chain_spec_smem_bytes(int dim, int Npad, int model, bool mixed, bool mol) {
+size_t chain_spec_smem_bytes(int dim, int Npad, int model, bool mixed, bool mol, bool swaps) {
     const bool full_par = !mixed && (mol || !(model == PMC_MODEL_LJ || model == PMC_MODEL_KG));
-    return spec::spec_layout(dim, spec_npad(Npad), full_par, mixed, spec_warps(dim, Npad, mol)).total;
+    return spec::spec_layout(dim, spec_npad(Npad), full_par, mixed, spec_warps(dim, Npad, mol), swaps).total;
 }
 
-cudaError_t configure_chain_spec(int dim, int model, int Npad, size_t smem, bool mixed, bool mol) {
-    auto set = [&](auto kernel) { return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); };
+template <typename F>
+static cudaError_t spec_dispatch_rt(int dim, int model, int Npad, bool mixed, bool mol, bool swaps, F &&f) {
     const int th = 32 * spec_warps(dim, Npad, mol);
-    return mixed ? spec_dispatch<true>(dim, model, Npad, mol, th, set) : spec_dispatch<false>(dim, model, Npad, mol, th, set);
+    if (mixed) return spec_dispatch<true, false>(dim, model, Npad, mol, th, f);
+    if (swaps) return spec_dispatch<false, true>(dim, model, Npad, mol, th, f);
+    return spec_dispatch<false, false>(dim, model, Npad, mol, th, f);
+}
+
+cudaError_t configure_chain_spec(int dim, int model, int Npad, size_t smem, bool mixed, bool mol, bool swaps) {
+    return spec_dispatch_rt(dim, model, Npad, mixed, mol, swaps, [&](auto kernel) {
+        return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    });
 }
 
 cudaError_t launch_chain_sweep_spec(int dim, int model, int M, size_t smem, const ChainArgs &a, cudaStream_t st, bool mixed,
-                                    bool mol) {
+                                    bool mol, bool swaps) {
     const int th = 32 * spec_warps(dim, a.Npad, mol);
-    auto go = [&](auto kernel) {
+    return spec_dispatch_rt(dim, model, a.Npad, mixed, mol, swaps, [&](auto kernel) {
         kernel<<<M, th, smem, st>>>(a);
         return cudaGetLastError();
-    };
-    return mixed ? spec_dispatch<true>(dim, model, a.Npad, mol, th, go) : spec_dispatch<false>(dim, model, a.Npad, mol, th, go);
+    });
 }
 
 // ---- local energies through the prefilter (k_chain_energy_fast) --------------------------------------------------

@@ -48,9 +48,10 @@ __device__ __forceinline__ void sts_f64x2(uint32_t a, double v0, double v1) {
 }
 
 struct SpecLayout {
-    uint32_t x, sp, pk, q, cp, rec, pub, cnt, cnt32, par, rcs, total;
+    uint32_t x, sp, pk, q, cp, rec, pub, cnt, cnt32, par, rcs, spids, heads, spoff, total;
 };
-__host__ __device__ inline SpecLayout spec_layout(int dim, int Npad, bool full_par, bool mixed = false, int nw = kSpecWarps) {
+__host__ __device__ inline SpecLayout spec_layout(int dim, int Npad, bool full_par, bool mixed = false, int nw = kSpecWarps,
+                                                  bool swaps = false) {
     SpecLayout f;
     uint32_t o = 0;
     auto take = [&](uint32_t bytes) {
@@ -69,6 +70,9 @@ __host__ __device__ inline SpecLayout spec_layout(int dim, int Npad, bool full_p
     f.cnt32 = take(4u * 2 * PMC_MAX_MOVES);  // per-batch counters (native 32-bit shared atomics), folded into cnt
     f.par = take(full_par ? 8u * PMC_MAX_SPECIES * PMC_MAX_SPECIES * PMC_NPAR : 0u);
     f.rcs = take(8u * PMC_MAX_SPECIES);
+    f.spids = take(swaps ? 2u * (uint32_t)Npad : 0u);  // SpeciesList (src/utils.jl:31-49), DiscreteSwap pools only
+    f.heads = take(swaps ? 2u * (uint32_t)Npad : 0u);
+    f.spoff = take(swaps ? 32u : 0u);                   // species offsets [5] + ~threshold of the swap filter [1]
     f.total = o;
     return f;
 }
@@ -91,10 +95,13 @@ __device__ __forceinline__ uint32_t cand_index(int b, int lane) {
 // MOL = true: Molecules -- bonded partners (A.bonds, <= PMC_MAX_BONDS per site) are excluded from the pair pass and
 // contribute bond_potential (FENE + bonded LJ, src/models.jl:202-226) in a separate pass of the first lanes.
 // NPAD up to 4096: the survivor mask of a lane is NPAD / 1024 words.
-template <int DIM, int MODEL, int NPAD, bool MIXED = false, bool MOL = false, int NW = 4>
+// SWAPS = true adds DiscreteSwap trials (src/moves.jl:137-214): positions fixed, four local energies in one pass over
+// the survivors of two spheres; an accepted swap ends the round for later swaps (the species lists changed).
+template <int DIM, int MODEL, int NPAD, bool MIXED = false, bool MOL = false, int NW = 4, bool SWAPS = false>
 __global__ void __launch_bounds__(32 * NW, NPAD <= 1024 ? (MIXED ? 8 : (MOL ? 5 : 6)) : 2) k_chain_sweep_spec(const __grid_constant__ ChainArgs A) {
     constexpr int NT = 32 * NW;
     static_assert(!(MIXED && MOL) && !(MIXED && NW != 4), "PMC_MIXED is implemented for Atoms, N <= 1024");
+    static_assert(!(SWAPS && (MIXED || MOL)), "DiscreteSwap pools: Atoms, fp64");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int KC = NPAD / 32;  // candidates per lane: k = 4 * c + e  <->  particle j = 128 * c + 4 * lane + e
     constexpr int NM = (KC + 31) / 32, KCW = KC < 32 ? KC : 32;  // mask words per lane, candidates per word
@@ -105,7 +112,7 @@ __global__ void __launch_bounds__(32 * NW, NPAD <= 1024 ? (MIXED ? 8 : (MOL ? 5 
     const int c = blockIdx.x;
     const int N = A.N, gNpad = A.Npad, ns = A.ns;
     constexpr bool kFullPar = !MIXED && (MOL || !(MODEL == PMC_MODEL_LJ || MODEL == PMC_MODEL_KG));
-    const SpecLayout F = spec_layout(DIM, Npad, kFullPar, MIXED, NW);
+    const SpecLayout F = spec_layout(DIM, Npad, kFullPar, MIXED, NW, SWAPS);
     const uint32_t sb = (uint32_t)__cvta_generic_to_shared(smem_raw);
     const uint32_t nb8 = 8u * (uint32_t)Npad;  // byte stride between coordinate planes (fp64)
     constexpr uint32_t nb4 = 4u * (uint32_t)NPAD;  // ... of the fixed-point planes (MIXED)
@@ -157,6 +164,21 @@ __global__ void __launch_bounds__(32 * NW, NPAD <= 1024 ? (MIXED ? 8 : (MOL ? 5 
             scnt[tid] = 0ull;
             ((uint32_t *)(smem_raw + F.cnt32))[tid] = 0u;
         }
+        if constexpr (SWAPS) {
+            uint16_t *si_ = (uint16_t *)(smem_raw + F.spids), *sh_ = (uint16_t *)(smem_raw + F.heads);
+            const uint16_t *gi = A.spids + (size_t)c * gNpad, *gh = A.heads + (size_t)c * gNpad;
+            for (int k = tid; k < Npad; k += NT) {
+                si_[k] = k < gNpad ? gi[k] : 0;
+                sh_[k] = k < gNpad ? gh[k] : 0;
+            }
+            int *sso = (int *)(smem_raw + F.spoff);
+            if (tid <= PMC_MAX_SPECIES) sso[tid] = A.spoff[c * (PMC_MAX_SPECIES + 1) + tid];
+            if (tid == 0) {  // one conservative threshold over all species pairs (swap filter: no displacement)
+                double rc2 = 0.0;
+                for (int k = 0; k < ns * ns; k++) rc2 = fmax(rc2, A.par[k * PMC_NPAR + PMC_P_RCUT2]);
+                ((uint32_t *)sso)[PMC_MAX_SPECIES + 1] = neg_thr8(sqrt(rc2) * fscale * 0x1p-24);
+            }
+        }
         if (tid < PMC_MAX_SPECIES) {  // largest cutoff radius per species of the moved particle (filter sphere)
             double rc2 = 0.0;
             for (int b = 0; b < ns; b++) rc2 = fmax(rc2, A.par[((tid < ns ? tid : 0) * ns + b) * PMC_NPAR + PMC_P_RCUT2]);
@@ -202,18 +224,27 @@ __global__ void __launch_bounds__(32 * NW, NPAD <= 1024 ? (MIXED ? 8 : (MOL ? 5 
                 int m = A.n_moves - 1;
                 for (int k = A.n_moves - 2; k >= 0; k--)
                     if (um < A.mv_cum[k]) m = k;
-                float z0, z1, z2, z3;
-                box_muller(b.v[0], b.v[1], z0, z1);
-                box_muller(b.v[2], b.v[3], z2, z3);
-                const float sg = A.mv_sigma[m];
                 tr.u = uniform53(a.v[2], a.v[3]);
                 tr.move = m;
-                tr.kind = PMC_MOVE_DISPLACEMENT;
-                tr.i = (int)bounded(a.v[1], (uint32_t)N);
-                tr.j = -1;
-                tr.delta[0] = (double)(sg * z0);
-                tr.delta[1] = (double)(sg * z1);
-                tr.delta[2] = (DIM == 3) ? (double)(sg * z2) : 0.0;
+                tr.kind = A.mv_kind[m];
+                if (!SWAPS || tr.kind == PMC_MOVE_DISPLACEMENT) {
+                    float z0, z1, z2, z3;
+                    box_muller(b.v[0], b.v[1], z0, z1);
+                    box_muller(b.v[2], b.v[3], z2, z3);
+                    const float sg = A.mv_sigma[m];
+                    tr.kind = PMC_MOVE_DISPLACEMENT;
+                    tr.i = (int)bounded(a.v[1], (uint32_t)N);
+                    tr.j = -1;
+                    tr.delta[0] = (double)(sg * z0);
+                    tr.delta[1] = (double)(sg * z1);
+                    tr.delta[2] = (DIM == 3) ? (double)(sg * z2) : 0.0;
+                } else {  // slots in the species lists; resolved to particles when the trial is evaluated
+                    const int *sso = (const int *)(smem_raw + F.spoff);
+                    const int nA = sso[A.mv_a[m] + 1] - sso[A.mv_a[m]], nB = sso[A.mv_b[m] + 1] - sso[A.mv_b[m]];
+                    tr.i = (nA > 0 && nB > 0) ? (int)bounded(a.v[1], (uint32_t)nA) : -1;
+                    tr.j = (nA > 0 && nB > 0) ? (int)bounded(b.v[0], (uint32_t)nB) : -1;
+                    tr.delta[0] = tr.delta[1] = tr.delta[2] = 0.0;
+                }
                 if (A.trace) A.trace[(size_t)c * A.n_trials + q] = tr;
             }
             // record: f64 delta[3], f64 thr | s32 dint[3], s32 i | s32 m, pad[3] | u32 ~thr8[4]
@@ -230,6 +261,9 @@ __global__ void __launch_bounds__(32 * NW, NPAD <= 1024 ? (MIXED ? 8 : (MOL ? 5 
             ri[2] = (int)__double2ll_rn(tr.delta[2] * fscale);
             ri[3] = tr.i;
             ri[4] = tr.move;
+            ri[5] = tr.kind;
+            ri[6] = tr.j;
+            ri[7] = (tr.kind == PMC_MOVE_SWAP && !A.replay) ? (A.mv_a[tr.move] | (A.mv_b[tr.move] << 8)) : 0;
             const double hd = 0.5 * sqrt(tr.delta[0] * tr.delta[0] + tr.delta[1] * tr.delta[1] + tr.delta[2] * tr.delta[2]);
             const double *rcs = (const double *)(smem_raw + F.rcs);
 #pragma unroll
@@ -249,6 +283,140 @@ __global__ void __launch_bounds__(32 * NW, NPAD <= 1024 ? (MIXED ? 8 : (MOL ? 5 
                 lds_f64x2(ra, d0, d1);
                 lds_f64x2(ra + 16, d2, thr);
                 lds_s32x4(ra + 32, di0, di1, di2, i);
+                bool is_swap = false;
+                if constexpr (SWAPS) {
+                    int mv, kind, j, sab;
+                    lds_s32x4(ra + 48, mv, kind, j, sab);
+                    if (kind == PMC_MOVE_SWAP) {
+                        is_swap = true;
+                        // ---- DiscreteSwap: positions fixed, four local energies in one pass (src/moves.jl:159-167) ----
+                        const uint32_t soa = sb + F.spoff;
+                        if (!A.replay && i >= 0) {  // slots -> particles through the species lists (current state)
+                            const uint32_t oa = lds_u32(soa + 4u * (uint32_t)(sab & 0xFF)), ob = lds_u32(soa + 4u * (uint32_t)(sab >> 8));
+                            i = (int)lds_u16(sb + F.spids + 2u * (oa + (uint32_t)i));
+                            j = (int)lds_u16(sb + F.spids + 2u * (ob + (uint32_t)j));
+                        }
+                        const bool valid = i >= 0 && j >= 0;
+                        const uint32_t iu = valid ? (uint32_t)i : 0u, ju = valid ? (uint32_t)j : 0u;
+                        const uint32_t xia = sb + F.x + 8u * iu, xja = sb + F.x + 8u * ju;
+                        const double xi0 = lds_f64(xia), xi1 = lds_f64(xia + nb8), xi2 = DIM == 3 ? lds_f64(xia + 2 * nb8) : 0.0;
+                        const double xj0 = lds_f64(xja), xj1 = lds_f64(xja + nb8), xj2 = DIM == 3 ? lds_f64(xja + 2 * nb8) : 0.0;
+                        const uint32_t si = lds_u8(sb + F.sp + iu), sj = lds_u8(sb + F.sp + ju);
+                        const uint32_t qi = lds_u32(sb + F.pk + 4u * iu), qj = lds_u32(sb + F.pk + 4u * ju);
+                        const int gthr = (int)lds_u32(soa + 4u * (PMC_MAX_SPECIES + 1));
+                        constexpr int NCHUNK = KCW / 4, NCH = NCHUNK >= 4 ? 4 : NCHUNK, CG = NCHUNK / NCH;
+                        uint32_t m[NM];
+                        int mine = 0;
+#pragma unroll
+                        for (int mw = 0; mw < NM; mw++) {
+                            uint32_t mc[NCH];
+#pragma unroll
+                            for (int h = 0; h < NCH; h++) mc[h] = 0u;
+#pragma unroll
+                            for (int cc = 0; cc < CG; cc++) {
+#pragma unroll
+                                for (int h = 0; h < NCH; h++) {
+                                    uint32_t w4[4];
+                                    lds_u32x4(pka + 512u * (uint32_t)(mw * 8 + h * CG + cc), w4[0], w4[1], w4[2], w4[3]);
+#pragma unroll
+                                    for (int e = 0; e < 4; e++) {  // survivor of either sphere
+                                        const uint32_t t1 = __vabsdiffu4(qi, w4[e]), t2 = __vabsdiffu4(qj, w4[e]);
+                                        const int v = __dp4a((int)t1, (int)t1, gthr) | __dp4a((int)t2, (int)t2, gthr);
+                                        mc[h] = __funnelshift_l((uint32_t)v, mc[h], 1);
+                                    }
+                                }
+                            }
+                            uint32_t mm = mc[0];
+#pragma unroll
+                            for (int h = 1; h < NCH; h++) mm = (mm << (4 * CG)) | mc[h];
+                            m[mw] = valid ? mm : 0u;
+                            mine += __popc(m[mw]);
+                        }
+                        int incl = mine;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                            incl += (lane >= o) ? t : 0;
+                        }
+                        const int total = __shfl_sync(0xffffffffu, incl, 31);
+                        auto pair_e = [&](uint32_t sa, uint32_t sb_, double r2) -> double {
+                            if constexpr (MODEL == PMC_MODEL_LJ || MODEL == PMC_MODEL_KG) {
+                                double rc2, eps4, sig2, shift;
+                                const uint32_t pp = sb + F.cp + 32u * (sa * (uint32_t)ns + sb_);
+                                lds_f64x2(pp, rc2, eps4);
+                                lds_f64x2(pp + 16, sig2, shift);
+                                return r2 <= rc2 ? lj_core(r2, eps4, sig2) - shift : 0.0;
+                            } else {
+                                const double *p = (const double *)(smem_raw + F.par) + (sa * (uint32_t)ns + sb_) * PMC_NPAR;
+                                return r2 <= p[PMC_P_RCUT2] ? pair_potential<MODEL>(p, r2) : 0.0;
+                            }
+                        };
+                        auto sterm = [&](uint32_t k) -> double {
+                            double t = 0.0;
+                            if (k < (uint32_t)N) {
+                                const uint32_t ka = sb + F.x + 8u * k;
+                                const double xk0 = lds_f64(ka), xk1 = lds_f64(ka + nb8), xk2 = DIM == 3 ? lds_f64(ka + 2 * nb8) : 0.0;
+                                const uint32_t sk = lds_u8(sb + F.sp + k);
+                                const uint32_t skn = k == iu ? sj : (k == ju ? si : sk);  // species of k after the exchange
+                                if (k != iu) {  // k-term of particle i's local energy: (si, sk) -> (sj, sk')
+                                    double r2 = mi_acc(xi0, xk0, L, hL, 0.0);
+                                    r2 = mi_acc(xi1, xk1, L, hL, r2);
+                                    if constexpr (DIM == 3) r2 = mi_acc(xi2, xk2, L, hL, r2);
+                                    t += pair_e(sj, skn, r2) - pair_e(si, sk, r2);
+                                }
+                                if (k != ju) {  // k-term of particle j's local energy: (sj, sk) -> (si, sk')
+                                    double r2 = mi_acc(xj0, xk0, L, hL, 0.0);
+                                    r2 = mi_acc(xj1, xk1, L, hL, r2);
+                                    if constexpr (DIM == 3) r2 = mi_acc(xj2, xk2, L, hL, r2);
+                                    t += pair_e(si, skn, r2) - pair_e(sj, sk, r2);
+                                }
+                            }
+                            return t;
+                        };
+                        double part = 0.0;
+                        if (total <= kSpecQCap) {
+                            uint32_t wp = qa + 2u * (uint32_t)(incl - mine);
+#pragma unroll
+                            for (int mw = 0; mw < NM; mw++) {
+                                uint32_t mm = m[mw];
+                                while (mm) {
+                                    const int b = 31 - __clz(mm);
+                                    mm ^= 1u << b;
+                                    sts_u16(wp, cand_index<KCW>(b, lane) + 1024u * (uint32_t)mw);
+                                    wp += 2;
+                                }
+                            }
+                            __syncwarp();
+                            for (int q = lane; q < total; q += 32) part += sterm(lds_u16(qa + 2u * (uint32_t)q));
+                            __syncwarp();
+                        } else {
+#pragma unroll
+                            for (int mw = 0; mw < NM; mw++) {
+                                uint32_t mm = m[mw];
+                                while (mm) {
+                                    const int b = 31 - __clz(mm);
+                                    mm ^= 1u << b;
+                                    part += sterm(cand_index<KCW>(b, lane) + 1024u * (uint32_t)mw);
+                                }
+                            }
+                        }
+                        const double dE = warp_sum(part);
+                        const bool acc = valid && (A.exact_exp ? accept_exact(dE, Tk, thr) : (dE < thr));
+                        if (lane == 0) {
+                            const uint32_t pw = pa + (uint32_t)kPubBytes * (uint32_t)warp;
+                            sts_f64(pw, dE);
+                            // spheres of a swap = its two particles; an invalid trial (empty species list) touches nothing
+                            sts_u32x4(pw + 32, qi, valid ? (uint32_t)gthr : 0xFFFFFFFFu, qi, qj);
+                            sts_u32x4(pw + 48, iu, (acc ? 1u : 0u) | 2u, ju, (uint32_t)mv);
+                            if (A.trace) {
+                                pmc_trial *tr = A.trace + (size_t)c * A.n_trials + tb + cur + warp;
+                                tr->i = i;
+                                tr->j = j;
+                            }
+                        }
+                    }
+                }
+                if (!is_swap) {
                 const uint32_t si = lds_u8(sb + F.sp + (uint32_t)i);
                 double xo[3] = {0.0, 0.0, 0.0}, xn[3] = {0.0, 0.0, 0.0};
                 uint32_t uo0, uo1, uo2, un0 = 0u, un1 = 0u, un2 = 0u;
@@ -448,11 +616,26 @@ __global__ void __launch_bounds__(32 * NW, NPAD <= 1024 ? (MIXED ? 8 : (MOL ? 5 
                     sts_u32x4(pw + 48, (uint32_t)i, acc ? 1u : 0u, (uint32_t)((wr0 + 1) | ((wr1 + 1) << 2) | ((wr2 + 1) << 4)),
                               lds_u32(ra + 48));
                 }
+                }  // !is_swap
             }
             __syncthreads();
             // ---- retire the round in trial order: warp 0 alone, the others wait at the second barrier --------------
             if (warp == 0) {
             int ndone = 0;
+            bool swap_committed = false;  // SWAPS: an accepted swap changed the species lists -> later swaps of the round wait
+            auto commit_swap = [&](uint32_t pw, uint32_t iw, uint32_t jw) {  // update_species_list! (src/moves.jl:175-179)
+                const uint32_t si = lds_u8(sb + F.sp + iw), sj = lds_u8(sb + F.sp + jw);
+                const uint32_t hi = lds_u16(sb + F.heads + 2u * iw), hj = lds_u16(sb + F.heads + 2u * jw);
+                const uint32_t oi = lds_u32(sb + F.spoff + 4u * si), oj = lds_u32(sb + F.spoff + 4u * sj);
+                asm volatile("st.shared.u8 [%0], %1;" ::"r"(sb + F.sp + iw), "r"(sj) : "memory");
+                asm volatile("st.shared.u8 [%0], %1;" ::"r"(sb + F.sp + jw), "r"(si) : "memory");
+                sts_u16(sb + F.spids + 2u * (oi + hi), jw);
+                sts_u16(sb + F.spids + 2u * (oj + hj), iw);
+                sts_u16(sb + F.heads + 2u * iw, hj);
+                sts_u16(sb + F.heads + 2u * jw, hi);
+                E += lds_f64(pw);
+                swap_committed = true;
+            };
             if constexpr (NW == 4) {
             uint32_t cqo[NW], cqn[NW];  // packed old / new position of trials accepted in this round
             uint32_t cmask = 0;
@@ -461,6 +644,9 @@ __global__ void __launch_bounds__(32 * NW, NPAD <= 1024 ? (MIXED ? 8 : (MOL ? 5 
                 if (w < nspec && ndone == w) {  // uniform
                     const uint32_t pw = pa + (uint32_t)kPubBytes * (uint32_t)w;
                     uint32_t umq, fthr, qo, qn;
+                    uint32_t iw, fl, wr, mv;
+                    lds_u32x4(pw + 48, iw, fl, wr, mv);
+                    const bool wswap = SWAPS && (fl & 2u) != 0u;
                     int conflict = 0;
                     if (w > 0 && cmask != 0u) {
                         lds_u32x4(pw + 32, umq, fthr, qo, qn);
@@ -469,19 +655,26 @@ __global__ void __launch_bounds__(32 * NW, NPAD <= 1024 ? (MIXED ? 8 : (MOL ? 5 
                             if (cmask & (1u << v)) {
                                 const uint32_t ta = __vabsdiffu4(umq, cqo[v]), tb_ = __vabsdiffu4(umq, cqn[v]);
                                 conflict |= __dp4a((int)ta, (int)ta, (int)fthr) | __dp4a((int)tb_, (int)tb_, (int)fthr);
+                                if (wswap) {  // second sphere of a swap: around its particle j
+                                    const uint32_t tc = __vabsdiffu4(qn, cqo[v]), td = __vabsdiffu4(qn, cqn[v]);
+                                    conflict |= __dp4a((int)tc, (int)tc, (int)fthr) | __dp4a((int)td, (int)td, (int)fthr);
+                                }
                             }
                         }
+                        if (wswap && swap_committed) conflict = -1;
                     }
                     if (conflict >= 0) {  // stands: retire it
                         ndone = w + 1;
-                        uint32_t iw, fl, wr, mv;
-                        lds_u32x4(pw + 48, iw, fl, wr, mv);
-                        const bool acc = fl != 0u;
+                        const bool acc = (fl & 1u) != 0u;
                         if (acc) {
                             if (w == 0 || cmask == 0u) lds_u32x4(pw + 32, umq, fthr, qo, qn);
                             cmask |= 1u << w;
                             cqo[w] = qo;
                             cqn[w] = qn;
+                            if (wswap) {
+                                commit_swap(pw, iw, wr);
+                            } else
+                            {
                             if constexpr (MIXED) {
                                 uint32_t n0, n1, n2, pad_;
                                 lds_u32x4(pw + 16, n0, n1, n2, pad_);
@@ -507,6 +700,7 @@ __global__ void __launch_bounds__(32 * NW, NPAD <= 1024 ? (MIXED ? 8 : (MOL ? 5 
                                 if (w1) atomicAdd(&gimg[gNpad + iw], w1);
                                 if (DIM == 3 && w2) atomicAdd(&gimg[2 * gNpad + iw], w2);
                             }
+                                                    }
                         }
                         if (tid == kCntThread) {
                             uint32_t *c32 = (uint32_t *)(smem_raw + F.cnt32);
@@ -528,18 +722,28 @@ __global__ void __launch_bounds__(32 * NW, NPAD <= 1024 ? (MIXED ? 8 : (MOL ? 5 
                     const uint32_t pw = pa + (uint32_t)kPubBytes * (uint32_t)w;
                     uint32_t umq, fthr, qo, qn;
                     lds_u32x4(pw + 32, umq, fthr, qo, qn);
+                    uint32_t iw, fl, wr, mv;
+                    lds_u32x4(pw + 48, iw, fl, wr, mv);
+                    const bool wswap = SWAPS && (fl & 2u) != 0u;
                     int conflict = 0;
                     for (uint32_t mm = cmask; mm; mm &= mm - 1u) {
                         const uint32_t pv = pa + (uint32_t)kPubBytes * (uint32_t)(__ffs((int)mm) - 1);
-                        const uint32_t ta = __vabsdiffu4(umq, lds_u32(pv + 40)), tb_ = __vabsdiffu4(umq, lds_u32(pv + 44));
+                        const uint32_t p0 = lds_u32(pv + 40), p1 = lds_u32(pv + 44);
+                        const uint32_t ta = __vabsdiffu4(umq, p0), tb_ = __vabsdiffu4(umq, p1);
                         conflict |= __dp4a((int)ta, (int)ta, (int)fthr) | __dp4a((int)tb_, (int)tb_, (int)fthr);
+                        if (wswap) {
+                            const uint32_t tc = __vabsdiffu4(qn, p0), td = __vabsdiffu4(qn, p1);
+                            conflict |= __dp4a((int)tc, (int)tc, (int)fthr) | __dp4a((int)td, (int)td, (int)fthr);
+                        }
                     }
+                    if (wswap && swap_committed) conflict = -1;
                     if (conflict < 0) break;
                     ndone = w + 1;
-                    uint32_t iw, fl, wr, mv;
-                    lds_u32x4(pw + 48, iw, fl, wr, mv);
-                    const bool acc = fl != 0u;
-                    if (acc) {
+                    const bool acc = (fl & 1u) != 0u;
+                    if (acc && wswap) {
+                        cmask |= 1u << w;
+                        commit_swap(pw, iw, wr);
+                    } else if (acc) {
                         cmask |= 1u << w;
                         double dE, x0, x1, x2;
                         lds_f64x2(pw, dE, x0);
@@ -587,6 +791,16 @@ __global__ void __launch_bounds__(32 * NW, NPAD <= 1024 ? (MIXED ? 8 : (MOL ? 5 
             const double *sx = (const double *)(smem_raw + F.x);
             for (int a = 0; a < DIM; a++)
                 for (int k = tid; k < gNpad; k += NT) gx[a * gNpad + k] = sx[a * Npad + k];
+        }
+        if constexpr (SWAPS) {
+            uint8_t *gsp = A.sp + (size_t)c * gNpad;
+            uint16_t *gi = A.spids + (size_t)c * gNpad, *gh = A.heads + (size_t)c * gNpad;
+            const uint16_t *si_ = (const uint16_t *)(smem_raw + F.spids), *sh_ = (const uint16_t *)(smem_raw + F.heads);
+            for (int k = tid; k < gNpad; k += NT) {
+                gsp[k] = smem_raw[F.sp + k];
+                gi[k] = si_[k];
+                gh[k] = sh_[k];
+            }
         }
         const unsigned long long *scnt = (const unsigned long long *)(smem_raw + F.cnt);
         const uint32_t *c32 = (const uint32_t *)(smem_raw + F.cnt32);
