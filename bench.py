@@ -44,9 +44,9 @@ WORK = {
 
 
 # figures of ONE launch from the committed `ncu --set full` captures (profiles/README.md)
-NCU_CHAINS = {"source": "profiles/r01_final_k_chain_sweep_spec_ncu_full_summary.csv", "dram_read_bytes": 105.67e6,
-              "dram_write_bytes": 43.25e6, "warp_instructions_per_move": 884, "issue_active_pct": 70.4,
-              "fp64_pipe_pct": 29.7, "alu_pipe_pct": 50.4, "registers": 80, "ctas_per_sm": 6}
+NCU_CHAINS = {"source": "profiles/r01_final_k_chain_sweep_spec_ncu_full_summary.csv", "dram_read_bytes": 105.62e6,
+              "dram_write_bytes": 42.96e6, "warp_instructions_per_move": 778, "issue_active_pct": 64.9,
+              "fp64_pipe_pct": 30.6, "alu_pipe_pct": 47.5, "registers": 80, "ctas_per_sm": 6}
 NCU_BOX = {"source": "profiles/r01_final_k_box_sweep_fast_ncu_full_summary.csv", "dram_read_bytes": 35.76e6,
            "dram_write_bytes": 0.21e6, "issue_active_pct": 66.6, "fp64_pipe_pct": 31.7, "alu_pipe_pct": 33.3,
            "registers": 64, "ctas_per_sm": 8}
@@ -347,7 +347,8 @@ def run_ours(args):
             ncu = NCU_BOX
         mixed = args.precision == "mixed"
         peak = peak32 if mixed else peak64
-        kernel = ("k_chain_sweep_mixed" if mixed else "k_chain_sweep_spec" if args.prefilter == 0 else
+        kernel = (("k_chain_sweep_spec<MIXED>" if args.prefilter == 0 else "k_chain_sweep_mixed") if mixed else
+                  "k_chain_sweep_spec" if args.prefilter == 0 else
                   "k_chain_sweep_fast" if args.prefilter == 1 else "k_chain_sweep") if args.workload == "chains" \
             else "k_box_sweep_fast (8 colours + cell rebuild)"
         roofline = {"bound": "fp32_pipe" if mixed else "fp64_pipe", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
