@@ -268,6 +268,18 @@ def run_ours(args):
     while world == 1 and rank == 0 and sampler.proc and not sampler.rows and time.perf_counter() - t_wait < 1.0:
         ctx.run(trials_per_step, sync=True)
         extra += 1
+    n_load = 0
+    if world > 1:
+        # several ranks (and, for the box, the device barriers between them) must issue identical launch sequences: the
+        # number of untimed load steps is derived from an all-reduced step time, the same on every rank
+        t_s = time.perf_counter()
+        ctx.run(trials_per_step, sync=True)
+        tt = torch.tensor([time.perf_counter() - t_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        n_load = int(min(400, np.ceil(0.35 / max(float(tt.item()), 1e-4))))
+        for _ in range(n_load):
+            ctx.run(trials_per_step, sync=False)
+        ctx.sync()
     n_pre = len(sampler.rows)
     launches0 = ctx.launch_count()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
@@ -285,6 +297,10 @@ def run_ours(args):
         t_wait = time.perf_counter()                                                # extend the load until one more sample
         while len(sampler.rows) == n_pre and time.perf_counter() - t_wait < 0.5:
             ctx.run(trials_per_step, sync=True)
+    if world > 1:  # keep the same load up until the sampler has seen it (same count on every rank)
+        for _ in range(max(1, n_load // 2)):
+            ctx.run(trials_per_step, sync=False)
+        ctx.sync()
     clocks = sampler.stop() if rank == 0 else None
     if clocks is not None:
         clocks["note"] = "sampled every 50 ms from the last warm-up step through the timed region (same load)"
