@@ -232,6 +232,45 @@ def test_trace_parity_molecules(molecule):
         check_trace(ctx, [orc], {0: (0, 0)}, 2000)
 
 
+def test_trace_parity_small_molecules(molecule):
+    """The first 300 trimers of the fixture in a smaller box (N = 900 <= 1024: the four-warp speculative kernel
+    with the bond pass) -- decisions bit-exact against the oracle, as for the full fixture."""
+    par = M.flatten_model_matrix(M.Trimer())
+    n = 900
+    pos = molecule["position"][:n].copy()
+    sp = molecule["species"][:n]
+    bonds = [[j for j in b if j <= n] for b in molecule["bonds"][:n]]
+    box = molecule["box"]  # same box: a dilute system, every bond intact
+    with DeviceContext(2, n, 3, 3, M.MODEL_KG, molecules=True) as ctx:
+        ctx.set_model(par)
+        ctx.set_bonds(zero_based(bonds))
+        ctx.upload(np.stack([pos, pos]), np.stack([sp, sp]), box, [2.0, 0.7])
+        ctx.init_energy()
+        ctx.set_moves([dict(kind="displacement", prob=1.0, sigma=0.06)])
+        ctx.seed(77)
+        orcs = [O.OracleSystem(pos - np.floor(pos / box) * box, sp, box, T, M.MODEL_KG, par, O.LINKEDLIST,
+                               bonds=zero_based(bonds)) for T in (2.0, 0.7)]
+        for c in range(2):
+            assert rel(ctx.energy()[c], orcs[c].energy) < RTOL_E
+        check_trace(ctx, orcs, {0: (0, 0)}, 3000)
+
+
+def test_trace_parity_2d_displacement_two_mask_words(config0):
+    """test/config_0 (2-D ternary JBB, N = 1290 -> 2048 padded candidates: two survivor-mask words per lane) with a
+    Displacement-only pool: the speculative kernel against the oracle."""
+    par = M.flatten_model_matrix(M.JBB())
+    with DeviceContext(2, 1290, 2, 3, M.MODEL_SMOOTHLJ) as ctx:
+        ctx.set_model(par)
+        ctx.upload(np.stack([config0["position"]] * 2), np.stack([config0["species"]] * 2), config0["box"],
+                   [config0["temperature"], 1.0])
+        ctx.init_energy()
+        ctx.set_moves([dict(kind="displacement", prob=1.0, sigma=0.08)])
+        ctx.seed(5)
+        orcs = [O.OracleSystem(config0["position"], config0["species"], config0["box"], T, M.MODEL_SMOOTHLJ, par,
+                               O.LINKEDLIST) for T in (config0["temperature"], 1.0)]
+        check_trace(ctx, orcs, {0: (0, 0)}, 3000)
+
+
 def test_trace_parity_molecule_flip(molecule):
     """examples/ortho-terphenyl pool: Displacement 0.8 + MoleculeFlip 0.2 (params-template.toml:59-68)."""
     par = M.flatten_model_matrix(M.Trimer())
