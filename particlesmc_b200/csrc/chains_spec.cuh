@@ -71,7 +71,7 @@ __host__ __device__ inline SpecLayout spec_layout(int dim, int Npad, bool full_p
     f.par = take(full_par ? 8u * PMC_MAX_SPECIES * PMC_MAX_SPECIES * PMC_NPAR : 0u);
     f.rcs = take(8u * PMC_MAX_SPECIES);
     f.spids = take(swaps ? 2u * (uint32_t)Npad : 0u);  // SpeciesList (src/utils.jl:31-49), DiscreteSwap pools only
-    f.heads = take(swaps ? 2u * (uint32_t)Npad : 0u);
+    f.heads = take(0u);  // positions inside the lists are searched for when a swap commits (rare), not stored
     f.spoff = take(swaps ? 32u : 0u);                   // species offsets [5] + ~threshold of the swap filter [1]
     f.total = o;
     return f;
@@ -98,7 +98,7 @@ __device__ __forceinline__ uint32_t cand_index(int b, int lane) {
 // SWAPS = true adds DiscreteSwap trials (src/moves.jl:137-214): positions fixed, four local energies in one pass over
 // the survivors of two spheres; an accepted swap ends the round for later swaps (the species lists changed).
 template <int DIM, int MODEL, int NPAD, bool MIXED = false, bool MOL = false, int NW = 4, bool SWAPS = false>
-__global__ void __launch_bounds__(32 * NW, NPAD <= 1024 ? (MIXED ? 8 : (MOL ? 5 : 6)) : 2) k_chain_sweep_spec(const __grid_constant__ ChainArgs A) {
+__global__ void __launch_bounds__(32 * NW, NPAD <= 1024 ? (MIXED ? 8 : (MOL ? 5 : 6)) : (NW == 4 ? 4 : 2)) k_chain_sweep_spec(const __grid_constant__ ChainArgs A) {
     constexpr int NT = 32 * NW;
     static_assert(!(MIXED && MOL) && !(MIXED && NW != 4), "PMC_MIXED is implemented for Atoms, N <= 1024");
     static_assert(!(SWAPS && (MIXED || MOL)), "DiscreteSwap pools: Atoms, fp64");
@@ -165,12 +165,9 @@ __global__ void __launch_bounds__(32 * NW, NPAD <= 1024 ? (MIXED ? 8 : (MOL ? 5 
             ((uint32_t *)(smem_raw + F.cnt32))[tid] = 0u;
         }
         if constexpr (SWAPS) {
-            uint16_t *si_ = (uint16_t *)(smem_raw + F.spids), *sh_ = (uint16_t *)(smem_raw + F.heads);
-            const uint16_t *gi = A.spids + (size_t)c * gNpad, *gh = A.heads + (size_t)c * gNpad;
-            for (int k = tid; k < Npad; k += NT) {
-                si_[k] = k < gNpad ? gi[k] : 0;
-                sh_[k] = k < gNpad ? gh[k] : 0;
-            }
+            uint16_t *si_ = (uint16_t *)(smem_raw + F.spids);
+            const uint16_t *gi = A.spids + (size_t)c * gNpad;
+            for (int k = tid; k < Npad; k += NT) si_[k] = k < gNpad ? gi[k] : 0;
             int *sso = (int *)(smem_raw + F.spoff);
             if (tid <= PMC_MAX_SPECIES) sso[tid] = A.spoff[c * (PMC_MAX_SPECIES + 1) + tid];
             if (tid == 0) {  // one conservative threshold over all species pairs (swap filter: no displacement)
@@ -625,14 +622,26 @@ __global__ void __launch_bounds__(32 * NW, NPAD <= 1024 ? (MIXED ? 8 : (MOL ? 5 
             bool swap_committed = false;  // SWAPS: an accepted swap changed the species lists -> later swaps of the round wait
             auto commit_swap = [&](uint32_t pw, uint32_t iw, uint32_t jw) {  // update_species_list! (src/moves.jl:175-179)
                 const uint32_t si = lds_u8(sb + F.sp + iw), sj = lds_u8(sb + F.sp + jw);
-                const uint32_t hi = lds_u16(sb + F.heads + 2u * iw), hj = lds_u16(sb + F.heads + 2u * jw);
                 const uint32_t oi = lds_u32(sb + F.spoff + 4u * si), oj = lds_u32(sb + F.spoff + 4u * sj);
+                const uint32_t ni = lds_u32(sb + F.spoff + 4u * si + 4u) - oi, nj = lds_u32(sb + F.spoff + 4u * sj + 4u) - oj;
+                // where i and j sit in their species lists: a warp search, paid only by accepted swaps
+                auto find = [&](uint32_t off, uint32_t n, uint32_t who) -> uint32_t {
+                    uint32_t pos = 0;
+                    for (uint32_t b0 = 0; b0 < n; b0 += 32) {
+                        const uint32_t k = b0 + (uint32_t)lane;
+                        const bool hit = k < n && lds_u16(sb + F.spids + 2u * (off + k)) == who;
+                        const unsigned bal = __ballot_sync(0xffffffffu, hit);
+                        if (bal) pos = b0 + (uint32_t)__ffs((int)bal) - 1u;
+                    }
+                    return pos;
+                };
+                const uint32_t hi = find(oi, ni, iw), hj = find(oj, nj, jw);
+                __syncwarp();
                 asm volatile("st.shared.u8 [%0], %1;" ::"r"(sb + F.sp + iw), "r"(sj) : "memory");
                 asm volatile("st.shared.u8 [%0], %1;" ::"r"(sb + F.sp + jw), "r"(si) : "memory");
                 sts_u16(sb + F.spids + 2u * (oi + hi), jw);
                 sts_u16(sb + F.spids + 2u * (oj + hj), iw);
-                sts_u16(sb + F.heads + 2u * iw, hj);
-                sts_u16(sb + F.heads + 2u * jw, hi);
+                __syncwarp();
                 E += lds_f64(pw);
                 swap_committed = true;
             };
@@ -795,11 +804,15 @@ __global__ void __launch_bounds__(32 * NW, NPAD <= 1024 ? (MIXED ? 8 : (MOL ? 5 
         if constexpr (SWAPS) {
             uint8_t *gsp = A.sp + (size_t)c * gNpad;
             uint16_t *gi = A.spids + (size_t)c * gNpad, *gh = A.heads + (size_t)c * gNpad;
-            const uint16_t *si_ = (const uint16_t *)(smem_raw + F.spids), *sh_ = (const uint16_t *)(smem_raw + F.heads);
+            const uint16_t *si_ = (const uint16_t *)(smem_raw + F.spids);
+            const int *sso = (const int *)(smem_raw + F.spoff);
             for (int k = tid; k < gNpad; k += NT) {
                 gsp[k] = smem_raw[F.sp + k];
                 gi[k] = si_[k];
-                gh[k] = sh_[k];
+            }
+            for (int k = tid; k < N; k += NT) {  // heads[particle] = its position inside its species list
+                const int who = si_[k];
+                gh[who] = (uint16_t)(k - sso[smem_raw[F.sp + who]]);
             }
         }
         const unsigned long long *scnt = (const unsigned long long *)(smem_raw + F.cnt);
