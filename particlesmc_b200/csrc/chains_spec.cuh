@@ -8,7 +8,8 @@
 // candidates (32 per lane, packed 8-bit coordinates streamed from a shared-memory table), compacts the survivors into its own queue, runs
 // the fp64 pass at ~86 % lane utilisation and reduces with shuffles only.  After a barrier, warp 0 retires the four
 // results in trial order and publishes how many retired; a second barrier starts the next round (retiring in every
-// warp redundantly saves that barrier but costs 165 more instructions per move: measured 3 % slower):
+// warp redundantly saves that barrier but costs 165 more instructions per move: measured 3 % slower; letting the warp
+// that arrives last retire the round behind a shared-memory arrival counter instead of the first barrier: 4 % slower):
 //
 //   trial t+w stands  <=>  no earlier trial of this round was ACCEPTED with its particle inside the filter sphere of
 //                          t+w, tested on the old AND the new position with the very 8-bit test the scan uses.
