@@ -89,14 +89,6 @@ struct BoxArgs {
     int32_t *peer_img[PMC_MAX_PEERS];
     double *peer_cellE[PMC_MAX_PEERS];
     uint32_t *peer_cacc[PMC_MAX_PEERS];
-    // inter-GPU barrier fused into the colour kernels (k_box_sweep_fast): a kernel first waits until every rank has
-    // signalled `wait_epoch` (0 = nothing to wait for) and its last CTA to finish signals `signal_epoch` to every rank
-    uint32_t wait_epoch, signal_epoch;
-    int rank, world;
-    volatile uint32_t *bar_flags;    // [world] local flags
-    uint32_t *const *peer_flags;     // [world] flag arrays of all ranks (self included)
-    unsigned int *done_count;        // CTAs of the running colour kernel that have finished
-    int *error;
 };
 
 // Cell coordinate and in-cell coordinate of a wrapped position under grid origin s.
@@ -670,37 +662,6 @@ __global__ void __launch_bounds__(kBfThreads, kBfThreads == 64 ? 12 : 8) k_box_s
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double *sr = (double *)(smem_raw + F.r);
     uint8_t *ssp = smem_raw + F.sp;
-    if (A.wait_epoch) {  // fused inter-GPU barrier: the peers' pushes of the previous colour must have landed
-        if (tid < A.world) {
-            unsigned long long spins = 0;
-            while ((int32_t)(A.bar_flags[tid] - A.wait_epoch) < 0) {
-                if (++spins > 50000000ull) {  // a peer that never arrives raises an error instead of hanging the GPU
-                    atomicExch(A.error, 3);
-                    break;
-                }
-            }
-            __threadfence();
-        }
-        __syncthreads();
-    }
-    // last CTA of this rank's colour kernel to finish tells every rank (system-scope fences order the pushes first)
-    auto signal_done = [&]() {
-        if (A.signal_epoch == 0u) return;
-        __syncthreads();
-        if (tid == 0) {
-            __threadfence_system();
-            const unsigned prev = atomicAdd(A.done_count, 1u);
-            if (prev == gridDim.x - 1) {
-                atomicExch(A.done_count, 0u);
-                __threadfence_system();
-                for (int t = 0; t < A.world; t++) {
-                    volatile uint32_t *dst = A.peer_flags[t] + A.rank;
-                    *dst = A.signal_epoch;
-                }
-                __threadfence_system();
-            }
-        }
-    };
     {
         double *spar = (double *)(smem_raw + F.par), *scp = (double *)(smem_raw + F.cp);
         for (int k = tid; k < A.ns * A.ns * PMC_NPAR; k += kBfThreads) spar[k] = A.par[k];
@@ -724,10 +685,7 @@ __global__ void __launch_bounds__(kBfThreads, kBfThreads == 64 ? 12 : 8) k_box_s
         cc[0] = 2 * (l / (A.g.nc[1] / 2)) + (colour & 1);
     }
     const int ncand = load_stencil_flat<DIM, kBfThreads>(A, cc, &st, sr, ssp);  // A.cap == CAP on this path
-    if (ncand < 0) {
-        signal_done();
-        return;
-    }
+    if (ncand < 0) return;
     const int cell = st.cell[0], ncen = st.off[1], bstart = A.start[cell];
     for (int k = tid; k < ncen; k += kBfThreads) smem_raw[F.mv + k] = 0;
     const double cs = A.g.cs[0];
@@ -916,7 +874,6 @@ __global__ void __launch_bounds__(kBfThreads, kBfThreads == 64 ? 12 : 8) k_box_s
         }
     }
     if (A.n_peers) __threadfence_system();
-    signal_done();
 }
 
 // (Fusing this barrier into the colour kernels -- last CTA signals, every CTA of the next colour waits -- was tried and
@@ -1053,7 +1010,6 @@ struct BoxState {
     // multi-GPU replicas (box_peer_attach)
     int rank = 0, world = 1;
     uint32_t *bar_flags = nullptr;      // [8] local barrier flags
-    unsigned int *done_count = nullptr; // finished CTAs of the running colour kernel (fused barrier)
     uint32_t **d_peer_flags = nullptr;  // device array [world] of flag arrays (self included)
     uint32_t epoch = 0;
     unsigned char *shared_block = nullptr;  // ONE allocation [x | xs | img | cellE | cell_acc | flags]: one IPC handle
@@ -1134,13 +1090,6 @@ void fill_args(BoxState *b, BoxArgs &a) {
     a.overflow = b->flags + 1;
     a.cta_offset = 0;
     a.n_peers = 0;
-    a.wait_epoch = a.signal_epoch = 0;
-    a.rank = b->rank;
-    a.world = b->world;
-    a.bar_flags = b->bar_flags;
-    a.peer_flags = b->d_peer_flags;
-    a.done_count = b->done_count;
-    a.error = b->flags;
     if (b->world > 1) {
         const BlockLayout bl = block_layout(b->N, b->dim, b->g.ncell);
         for (int r = 0; r < b->world; r++) {
@@ -1392,8 +1341,6 @@ int box_create(BoxState **out, const pmc_config &cfg) {
     if (e == cudaSuccess) e = balloc(&b->etmp, 1);
     if (e == cudaSuccess) e = balloc(&b->acc_total, 1);
     if (e == cudaSuccess) e = balloc(&b->flags, 2);
-    if (e == cudaSuccess) e = balloc(&b->done_count, 1);
-    if (e == cudaSuccess) e = cudaMemset(b->done_count, 0, sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMalloc((void **)&b->raw, sizeof(double) * d * N);
     if (e == cudaSuccess) e = cudaMalloc((void **)&b->rsp, sizeof(long long) * N);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();  // zero-fills ran on the legacy default stream
@@ -1410,7 +1357,7 @@ void box_destroy(BoxState *b) {
     for (int r = 0; r < b->world; r++)
         if (r != b->rank && b->peer_block[r]) cudaIpcCloseMemHandle(b->peer_block[r]);
     void *bufs[] = {b->shared_block, b->ids, b->cid, b->sp, b->sps, b->eloc, b->par, b->energy, b->etmp, b->acc_total,
-                    b->flags, b->raw, b->rsp, b->count, b->cursor, b->start, b->d_peer_flags, b->cid_blocksum, b->done_count};
+                    b->flags, b->raw, b->rsp, b->count, b->cursor, b->start, b->d_peer_flags, b->cid_blocksum};
     for (void *p : bufs)
         if (p) cudaFree(p);
     delete b;
@@ -1525,15 +1472,8 @@ int box_run(BoxState *b, int64_t n_trials) {
         }
         rc = bdispatch(b->dim, b->cfg.model_kind, [&](auto D, auto MDL) {
             constexpr int d = decltype(D)::value, mdl = decltype(MDL)::value;
-            // with the fast kernel the barriers between colours are fused into the kernels (wait at the start of
-            // colour k + 1, signal from the last CTA of colour k): 7 of the 9 barrier launches of a sweep disappear
-            const bool fused = b->world > 1 && b->fast_kc != 0 && hi > lo;
-            uint32_t prev_signal = 0;
             for (int k = 0; k < ncol; k++) {
                 if (hi > lo) {
-                    A.wait_epoch = fused ? prev_signal : 0u;
-                    A.signal_epoch = (fused && k < ncol - 1) ? ++b->epoch : 0u;
-                    prev_signal = A.signal_epoch;
                     if (b->fast_kc == kBfKc0)
                         k_box_sweep_fast<d, mdl, kBfKc0><<<hi - lo, kBfThreads, b->fast_smem, b->stream>>>(A, order[k]);
                     else if (b->fast_kc == kBfKc1)
@@ -1546,7 +1486,7 @@ int box_run(BoxState *b, int64_t n_trials) {
                         k_box_sweep<d, mdl><<<hi - lo, kBoxThreads, b->smem, b->stream>>>(A, order[k]);
                 }
                 BCU(cudaGetLastError());
-                if (b->world > 1 && !(fused && k < ncol - 1)) {
+                if (b->world > 1) {
                     const int brc = peer_barrier(b);
                     if (brc) return brc;
                 }
