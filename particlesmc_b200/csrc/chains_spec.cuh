@@ -415,173 +415,105 @@ __global__ void __launch_bounds__(32 * NW, NPAD <= 1024 ? (MIXED ? 8 : (MOL ? 5 
                     }
                 }
                 if (!is_swap) {
-                const uint32_t si = lds_u8(sb + F.sp + (uint32_t)i);
-                double xo[3] = {0.0, 0.0, 0.0}, xn[3] = {0.0, 0.0, 0.0};
-                uint32_t uo0, uo1, uo2, un0 = 0u, un1 = 0u, un2 = 0u;
-                int wr0, wr1, wr2;  // image-counter increments of the move
-                if constexpr (MIXED) {
-                    const uint32_t ua = sb + F.x + 4u * (uint32_t)i;
-                    uo0 = lds_u32(ua);
-                    uo1 = lds_u32(ua + nb4);
-                    uo2 = (DIM == 3) ? lds_u32(ua + 2 * nb4) : 0u;
-                    un0 = uo0 + (uint32_t)di0;  // wraps like the box does
-                    un1 = uo1 + (uint32_t)di1;
-                    un2 = uo2 + (uint32_t)di2;
-                    wr0 = (di0 > 0 && un0 < uo0) - (di0 < 0 && un0 > uo0);
-                    wr1 = (di1 > 0 && un1 < uo1) - (di1 < 0 && un1 > uo1);
-                    wr2 = (di2 > 0 && un2 < uo2) - (di2 < 0 && un2 > uo2);
-                } else {
-                    const uint32_t xa = sb + F.x + 8u * (uint32_t)i;
-                    xo[0] = lds_f64(xa);
-                    xo[1] = lds_f64(xa + nb8);
-                    xo[2] = (DIM == 3) ? lds_f64(xa + 2 * nb8) : 0.0;
-                    const double t0 = xo[0] + d0, t1 = xo[1] + d1, t2 = xo[2] + d2;
-                    xn[0] = wrap_once(t0, L);
-                    xn[1] = wrap_once(t1, L);
-                    xn[2] = (DIM == 3) ? wrap_once(t2, L) : 0.0;
-                    wr0 = (t0 >= L) - (t0 < 0.0);
-                    wr1 = (t1 >= L) - (t1 < 0.0);
-                    wr2 = (DIM == 3) ? (t2 >= L) - (t2 < 0.0) : 0;
-                    uo0 = to_fixed32(xo[0], fscale);
-                    uo1 = to_fixed32(xo[1], fscale);
-                    uo2 = (DIM == 3) ? to_fixed32(xo[2], fscale) : 0u;
-                }
-                const uint32_t umq = pack8(uo0 + (uint32_t)(di0 >> 1), uo1 + (uint32_t)(di1 >> 1), uo2 + (uint32_t)(di2 >> 1));
-                const int fthr = (int)lds_u32(ra + 64 + 4u * si);
-                // survivor masks: candidate k = 32 * word + k' -> bit KCW-1-k' of its word; every word is built as
-                // independent shift chains over groups of chunks (the funnel shifts of one chain depend on each other)
-                constexpr int NCHUNK = KCW / 4, NCH = NCHUNK >= 4 ? 4 : NCHUNK, CG = NCHUNK / NCH;
-                uint32_t m[NM];
-                int mine = 0;
+                    const uint32_t si = lds_u8(sb + F.sp + (uint32_t)i);
+                    double xo[3] = {0.0, 0.0, 0.0}, xn[3] = {0.0, 0.0, 0.0};
+                    uint32_t uo0, uo1, uo2, un0 = 0u, un1 = 0u, un2 = 0u;
+                    int wr0, wr1, wr2;  // image-counter increments of the move
+                    if constexpr (MIXED) {
+                        const uint32_t ua = sb + F.x + 4u * (uint32_t)i;
+                        uo0 = lds_u32(ua);
+                        uo1 = lds_u32(ua + nb4);
+                        uo2 = (DIM == 3) ? lds_u32(ua + 2 * nb4) : 0u;
+                        un0 = uo0 + (uint32_t)di0;  // wraps like the box does
+                        un1 = uo1 + (uint32_t)di1;
+                        un2 = uo2 + (uint32_t)di2;
+                        wr0 = (di0 > 0 && un0 < uo0) - (di0 < 0 && un0 > uo0);
+                        wr1 = (di1 > 0 && un1 < uo1) - (di1 < 0 && un1 > uo1);
+                        wr2 = (di2 > 0 && un2 < uo2) - (di2 < 0 && un2 > uo2);
+                    } else {
+                        const uint32_t xa = sb + F.x + 8u * (uint32_t)i;
+                        xo[0] = lds_f64(xa);
+                        xo[1] = lds_f64(xa + nb8);
+                        xo[2] = (DIM == 3) ? lds_f64(xa + 2 * nb8) : 0.0;
+                        const double t0 = xo[0] + d0, t1 = xo[1] + d1, t2 = xo[2] + d2;
+                        xn[0] = wrap_once(t0, L);
+                        xn[1] = wrap_once(t1, L);
+                        xn[2] = (DIM == 3) ? wrap_once(t2, L) : 0.0;
+                        wr0 = (t0 >= L) - (t0 < 0.0);
+                        wr1 = (t1 >= L) - (t1 < 0.0);
+                        wr2 = (DIM == 3) ? (t2 >= L) - (t2 < 0.0) : 0;
+                        uo0 = to_fixed32(xo[0], fscale);
+                        uo1 = to_fixed32(xo[1], fscale);
+                        uo2 = (DIM == 3) ? to_fixed32(xo[2], fscale) : 0u;
+                    }
+                    const uint32_t umq = pack8(uo0 + (uint32_t)(di0 >> 1), uo1 + (uint32_t)(di1 >> 1), uo2 + (uint32_t)(di2 >> 1));
+                    const int fthr = (int)lds_u32(ra + 64 + 4u * si);
+                    // survivor masks: candidate k = 32 * word + k' -> bit KCW-1-k' of its word; every word is built as
+                    // independent shift chains over groups of chunks (the funnel shifts of one chain depend on each other)
+                    constexpr int NCHUNK = KCW / 4, NCH = NCHUNK >= 4 ? 4 : NCHUNK, CG = NCHUNK / NCH;
+                    uint32_t m[NM];
+                    int mine = 0;
 #pragma unroll
-                for (int mw = 0; mw < NM; mw++) {
-                    uint32_t mc[NCH];
+                    for (int mw = 0; mw < NM; mw++) {
+                        uint32_t mc[NCH];
 #pragma unroll
-                    for (int h = 0; h < NCH; h++) mc[h] = 0u;
+                        for (int h = 0; h < NCH; h++) mc[h] = 0u;
 #pragma unroll
-                    for (int cc = 0; cc < CG; cc++) {
+                        for (int cc = 0; cc < CG; cc++) {
 #pragma unroll
-                        for (int h = 0; h < NCH; h++) {
-                            uint32_t w4[4];
-                            lds_u32x4(pka + 512u * (uint32_t)(mw * 8 + h * CG + cc), w4[0], w4[1], w4[2], w4[3]);
+                            for (int h = 0; h < NCH; h++) {
+                                uint32_t w4[4];
+                                lds_u32x4(pka + 512u * (uint32_t)(mw * 8 + h * CG + cc), w4[0], w4[1], w4[2], w4[3]);
 #pragma unroll
-                            for (int e = 0; e < 4; e++) {
-                                const uint32_t t = __vabsdiffu4(umq, w4[e]);
-                                mc[h] = __funnelshift_l((uint32_t)__dp4a((int)t, (int)t, fthr), mc[h], 1);
+                                for (int e = 0; e < 4; e++) {
+                                    const uint32_t t = __vabsdiffu4(umq, w4[e]);
+                                    mc[h] = __funnelshift_l((uint32_t)__dp4a((int)t, (int)t, fthr), mc[h], 1);
+                                }
                             }
                         }
-                    }
-                    uint32_t mm = mc[0];
+                        uint32_t mm = mc[0];
 #pragma unroll
-                    for (int h = 1; h < NCH; h++) mm = (mm << (4 * CG)) | mc[h];
-                    m[mw] = mm;
-                    mine += __popc(mm);
-                }
-                int incl = mine;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int t = __shfl_up_sync(0xffffffffu, incl, o);
-                    incl += (lane >= o) ? t : 0;
-                }
-                const int total = __shfl_sync(0xffffffffu, incl, 31);
-                const uint32_t prow = si * (uint32_t)ns;
-                double part = 0.0;
-                uint32_t bi[PMC_MAX_BONDS];  // MOL: bonded partners of i (0xFFFF = none)
-                if constexpr (MOL) {
-#pragma unroll
-                    for (int k = 0; k < PMC_MAX_BONDS; k++) bi[k] = (uint32_t)__ldg(A.bonds + (size_t)i * PMC_MAX_BONDS + k);
-                }
-                // pair term of candidate j, branch-free (selects) so that two of them interleave in the unrolled loop
-                auto term = [&](uint32_t j) -> double {
-                    bool valid = j < (uint32_t)N && j != (uint32_t)i;
-                    if constexpr (MOL) {  // bonded partners are handled by the bond pass below
-#pragma unroll
-                        for (int k = 0; k < PMC_MAX_BONDS; k++) valid = valid && j != bi[k];
+                        for (int h = 1; h < NCH; h++) mm = (mm << (4 * CG)) | mc[h];
+                        m[mw] = mm;
+                        mine += __popc(mm);
                     }
-                    if constexpr (MIXED) {  // fp32 pair terms on wrapping integer distances (minimum image for free)
-                        const uint32_t ja = sb + F.x + 4u * j;
-                        const uint32_t a0 = lds_u32(ja), a1 = lds_u32(ja + nb4), a2 = (DIM == 3) ? lds_u32(ja + 2 * nb4) : 0u;
-                        const float r2o = __uint2float_rn(dist2_u32<DIM>(uo0, uo1, uo2, a0, a1, a2)) * r2scale;
-                        const float r2n = __uint2float_rn(dist2_u32<DIM>(un0, un1, un2, a0, a1, a2)) * r2scale;
-                        const uint32_t sj = lds_u8(sb + F.sp + j);
-                        float rc2, eps, sig2, shift, c0, c2, c4, pad_;
-                        const uint32_t pp = sb + F.cp + 32u * (prow + sj);
-                        lds_f32x4(pp, rc2, eps, sig2, shift);
-                        lds_f32x4(pp + 16, c0, c2, c4, pad_);
-                        const float eo = pair_potential_f32<MODEL>(r2o, eps, sig2, shift, c0, c2, c4);
-                        const float en = pair_potential_f32<MODEL>(r2n, eps, sig2, shift, c0, c2, c4);
-                        const float d = (r2n <= rc2 ? en : 0.0f) - (r2o <= rc2 ? eo : 0.0f);
-                        return valid ? (double)d : 0.0;
-                    }
-                    const uint32_t ja = sb + F.x + 8u * j;
-                    const double xj0 = lds_f64(ja), xj1 = lds_f64(ja + nb8);
-                    double r2o = mi_acc(xo[0], xj0, L, hL, 0.0), r2n = mi_acc(xn[0], xj0, L, hL, 0.0);
-                    r2o = mi_acc(xo[1], xj1, L, hL, r2o);
-                    r2n = mi_acc(xn[1], xj1, L, hL, r2n);
-                    if constexpr (DIM == 3) {
-                        const double xj2 = lds_f64(ja + 2 * nb8);
-                        r2o = mi_acc(xo[2], xj2, L, hL, r2o);
-                        r2n = mi_acc(xn[2], xj2, L, hL, r2n);
-                    }
-                    const uint32_t sj = lds_u8(sb + F.sp + j);
-                    double uo, un, rc2;
-                    if constexpr (MODEL == PMC_MODEL_LJ || MODEL == PMC_MODEL_KG) {
-                        double eps4, sig2, shift;
-                        const uint32_t pp = sb + F.cp + 32u * (prow + sj);
-                        lds_f64x2(pp, rc2, eps4);
-                        lds_f64x2(pp + 16, sig2, shift);
-                        uo = lj_core(r2o, eps4, sig2) - shift;
-                        un = lj_core(r2n, eps4, sig2) - shift;
-                    } else {
-                        const double *p = (const double *)(smem_raw + F.par) + (prow + sj) * PMC_NPAR;
-                        rc2 = p[PMC_P_RCUT2];
-                        uo = pair_potential<MODEL>(p, r2o);
-                        un = pair_potential<MODEL>(p, r2n);
-                    }
-                    const double d = (r2n <= rc2 ? un : 0.0) - (r2o <= rc2 ? uo : 0.0);
-                    return valid ? d : 0.0;
-                };
-                if (total <= kSpecQCap) {
-                    // compaction: each lane appends its survivors (ascending candidate index) at its scan offset
-                    uint32_t wp = qa + 2u * (uint32_t)(incl - mine);
+                    int incl = mine;
 #pragma unroll
-                    for (int mw = 0; mw < NM; mw++) {
-                        uint32_t mm = m[mw];
-                        while (mm) {
-                            const int b = 31 - __clz(mm);
-                            mm ^= 1u << b;
-                            sts_u16(wp, cand_index<KCW>(b, lane) + 1024u * (uint32_t)mw);
-                            wp += 2;
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                        incl += (lane >= o) ? t : 0;
+                    }
+                    const int total = __shfl_sync(0xffffffffu, incl, 31);
+                    const uint32_t prow = si * (uint32_t)ns;
+                    double part = 0.0;
+                    uint32_t bi[PMC_MAX_BONDS];  // MOL: bonded partners of i (0xFFFF = none)
+                    if constexpr (MOL) {
+#pragma unroll
+                        for (int k = 0; k < PMC_MAX_BONDS; k++) bi[k] = (uint32_t)__ldg(A.bonds + (size_t)i * PMC_MAX_BONDS + k);
+                    }
+                    // pair term of candidate j, branch-free (selects) so that two of them interleave in the unrolled loop
+                    auto term = [&](uint32_t j) -> double {
+                        bool valid = j < (uint32_t)N && j != (uint32_t)i;
+                        if constexpr (MOL) {  // bonded partners are handled by the bond pass below
+#pragma unroll
+                            for (int k = 0; k < PMC_MAX_BONDS; k++) valid = valid && j != bi[k];
                         }
-                    }
-                    __syncwarp();
-                    // two survivors per lane and iteration while both exist (the dependent fp64 chains of one pair
-                    // term leave the pipe idle; two independent ones overlap), then the remainder one at a time
-                    const int nfull = total & ~63;
-                    int q = lane;
-                    for (; q < nfull; q += 64) {
-                        const uint32_t j0 = lds_u16(qa + 2u * (uint32_t)q), j1 = lds_u16(qa + 2u * (uint32_t)q + 64u);
-                        const double e0 = term(j0), e1 = term(j1);
-                        part += e0;
-                        part += e1;
-                    }
-                    for (; q < total; q += 32) part += term(lds_u16(qa + 2u * (uint32_t)q));
-                    __syncwarp();
-                } else {  // tiny boxes where (nearly) every candidate survives: no queue, each lane its own survivors
-#pragma unroll
-                    for (int mw = 0; mw < NM; mw++) {
-                        uint32_t mm = m[mw];
-                        while (mm) {
-                            const int b = 31 - __clz(mm);
-                            mm ^= 1u << b;
-                            part += term(cand_index<KCW>(b, lane) + 1024u * (uint32_t)mw);
+                        if constexpr (MIXED) {  // fp32 pair terms on wrapping integer distances (minimum image for free)
+                            const uint32_t ja = sb + F.x + 4u * j;
+                            const uint32_t a0 = lds_u32(ja), a1 = lds_u32(ja + nb4), a2 = (DIM == 3) ? lds_u32(ja + 2 * nb4) : 0u;
+                            const float r2o = __uint2float_rn(dist2_u32<DIM>(uo0, uo1, uo2, a0, a1, a2)) * r2scale;
+                            const float r2n = __uint2float_rn(dist2_u32<DIM>(un0, un1, un2, a0, a1, a2)) * r2scale;
+                            const uint32_t sj = lds_u8(sb + F.sp + j);
+                            float rc2, eps, sig2, shift, c0, c2, c4, pad_;
+                            const uint32_t pp = sb + F.cp + 32u * (prow + sj);
+                            lds_f32x4(pp, rc2, eps, sig2, shift);
+                            lds_f32x4(pp + 16, c0, c2, c4, pad_);
+                            const float eo = pair_potential_f32<MODEL>(r2o, eps, sig2, shift, c0, c2, c4);
+                            const float en = pair_potential_f32<MODEL>(r2n, eps, sig2, shift, c0, c2, c4);
+                            const float d = (r2n <= rc2 ? en : 0.0f) - (r2o <= rc2 ? eo : 0.0f);
+                            return valid ? (double)d : 0.0;
                         }
-                    }
-                }
-                if constexpr (MOL) {  // bond pass: lane k owns bonded partner k of particle i
-                    const uint32_t b = lane < PMC_MAX_BONDS ? (uint32_t)__ldg(A.bonds + (size_t)i * PMC_MAX_BONDS + lane) : 0xFFFFu;
-                    if (b != 0xFFFFu) {
-                        const uint32_t ja = sb + F.x + 8u * b;
+                        const uint32_t ja = sb + F.x + 8u * j;
                         const double xj0 = lds_f64(ja), xj1 = lds_f64(ja + nb8);
                         double r2o = mi_acc(xo[0], xj0, L, hL, 0.0), r2n = mi_acc(xn[0], xj0, L, hL, 0.0);
                         r2o = mi_acc(xo[1], xj1, L, hL, r2o);
@@ -591,126 +523,252 @@ __global__ void __launch_bounds__(32 * NW, NPAD <= 1024 ? (MIXED ? 8 : (MOL ? 5 
                             r2o = mi_acc(xo[2], xj2, L, hL, r2o);
                             r2n = mi_acc(xn[2], xj2, L, hL, r2n);
                         }
-                        const double *p = (const double *)(smem_raw + F.par) + (prow + lds_u8(sb + F.sp + b)) * PMC_NPAR;
-                        part += bond_potential(p, r2n) - bond_potential(p, r2o);
+                        const uint32_t sj = lds_u8(sb + F.sp + j);
+                        double uo, un, rc2;
+                        if constexpr (MODEL == PMC_MODEL_LJ || MODEL == PMC_MODEL_KG) {
+                            double eps4, sig2, shift;
+                            const uint32_t pp = sb + F.cp + 32u * (prow + sj);
+                            lds_f64x2(pp, rc2, eps4);
+                            lds_f64x2(pp + 16, sig2, shift);
+                            uo = lj_core(r2o, eps4, sig2) - shift;
+                            un = lj_core(r2n, eps4, sig2) - shift;
+                        } else {
+                            const double *p = (const double *)(smem_raw + F.par) + (prow + sj) * PMC_NPAR;
+                            rc2 = p[PMC_P_RCUT2];
+                            uo = pair_potential<MODEL>(p, r2o);
+                            un = pair_potential<MODEL>(p, r2n);
+                        }
+                        const double d = (r2n <= rc2 ? un : 0.0) - (r2o <= rc2 ? uo : 0.0);
+                        return valid ? d : 0.0;
+                    };
+                    if (total <= kSpecQCap) {
+                        // compaction: each lane appends its survivors (ascending candidate index) at its scan offset
+                        uint32_t wp = qa + 2u * (uint32_t)(incl - mine);
+#pragma unroll
+                        for (int mw = 0; mw < NM; mw++) {
+                            uint32_t mm = m[mw];
+                            while (mm) {
+                                const int b = 31 - __clz(mm);
+                                mm ^= 1u << b;
+                                sts_u16(wp, cand_index<KCW>(b, lane) + 1024u * (uint32_t)mw);
+                                wp += 2;
+                            }
+                        }
+                        __syncwarp();
+                        // two survivors per lane and iteration while both exist (the dependent fp64 chains of one pair
+                        // term leave the pipe idle; two independent ones overlap), then the remainder one at a time
+                        const int nfull = total & ~63;
+                        int q = lane;
+                        for (; q < nfull; q += 64) {
+                            const uint32_t j0 = lds_u16(qa + 2u * (uint32_t)q), j1 = lds_u16(qa + 2u * (uint32_t)q + 64u);
+                            const double e0 = term(j0), e1 = term(j1);
+                            part += e0;
+                            part += e1;
+                        }
+                        for (; q < total; q += 32) part += term(lds_u16(qa + 2u * (uint32_t)q));
+                        __syncwarp();
+                    } else {  // tiny boxes where (nearly) every candidate survives: no queue, each lane its own survivors
+#pragma unroll
+                        for (int mw = 0; mw < NM; mw++) {
+                            uint32_t mm = m[mw];
+                            while (mm) {
+                                const int b = 31 - __clz(mm);
+                                mm ^= 1u << b;
+                                part += term(cand_index<KCW>(b, lane) + 1024u * (uint32_t)mw);
+                            }
+                        }
                     }
-                }
-                const double dE = warp_sum(part);
-                const bool acc = A.exact_exp ? accept_exact(dE, Tk, thr) : (dE < thr);
-                if (lane == 0) {
-                    const uint32_t pw = pa + (uint32_t)kPubBytes * (uint32_t)warp;
-                    uint32_t qn;
-                    if constexpr (MIXED) {
-                        sts_f64(pw, dE);
-                        sts_u32x4(pw + 16, un0, un1, un2, 0u);
-                        qn = pack8(un0, un1, un2);
-                    } else {
-                        sts_f64x2(pw, dE, xn[0]);
-                        sts_f64x2(pw + 16, xn[1], xn[2]);
-                        qn = pack8(to_fixed32(xn[0], fscale), to_fixed32(xn[1], fscale), (DIM == 3) ? to_fixed32(xn[2], fscale) : 0u);
+                    if constexpr (MOL) {  // bond pass: lane k owns bonded partner k of particle i
+                        const uint32_t b = lane < PMC_MAX_BONDS ? (uint32_t)__ldg(A.bonds + (size_t)i * PMC_MAX_BONDS + lane) : 0xFFFFu;
+                        if (b != 0xFFFFu) {
+                            const uint32_t ja = sb + F.x + 8u * b;
+                            const double xj0 = lds_f64(ja), xj1 = lds_f64(ja + nb8);
+                            double r2o = mi_acc(xo[0], xj0, L, hL, 0.0), r2n = mi_acc(xn[0], xj0, L, hL, 0.0);
+                            r2o = mi_acc(xo[1], xj1, L, hL, r2o);
+                            r2n = mi_acc(xn[1], xj1, L, hL, r2n);
+                            if constexpr (DIM == 3) {
+                                const double xj2 = lds_f64(ja + 2 * nb8);
+                                r2o = mi_acc(xo[2], xj2, L, hL, r2o);
+                                r2n = mi_acc(xn[2], xj2, L, hL, r2n);
+                            }
+                            const double *p = (const double *)(smem_raw + F.par) + (prow + lds_u8(sb + F.sp + b)) * PMC_NPAR;
+                            part += bond_potential(p, r2n) - bond_potential(p, r2o);
+                        }
                     }
-                    // +32: what the conflict test of LATER trials needs | +48: what retiring THIS trial needs
-                    sts_u32x4(pw + 32, umq, (uint32_t)fthr, pack8(uo0, uo1, uo2), qn);
-                    sts_u32x4(pw + 48, (uint32_t)i, acc ? 1u : 0u, (uint32_t)((wr0 + 1) | ((wr1 + 1) << 2) | ((wr2 + 1) << 4)),
-                              lds_u32(ra + 48));
-                }
+                    const double dE = warp_sum(part);
+                    const bool acc = A.exact_exp ? accept_exact(dE, Tk, thr) : (dE < thr);
+                    if (lane == 0) {
+                        const uint32_t pw = pa + (uint32_t)kPubBytes * (uint32_t)warp;
+                        uint32_t qn;
+                        if constexpr (MIXED) {
+                            sts_f64(pw, dE);
+                            sts_u32x4(pw + 16, un0, un1, un2, 0u);
+                            qn = pack8(un0, un1, un2);
+                        } else {
+                            sts_f64x2(pw, dE, xn[0]);
+                            sts_f64x2(pw + 16, xn[1], xn[2]);
+                            qn = pack8(to_fixed32(xn[0], fscale), to_fixed32(xn[1], fscale), (DIM == 3) ? to_fixed32(xn[2], fscale) : 0u);
+                        }
+                        // +32: what the conflict test of LATER trials needs | +48: what retiring THIS trial needs
+                        sts_u32x4(pw + 32, umq, (uint32_t)fthr, pack8(uo0, uo1, uo2), qn);
+                        sts_u32x4(pw + 48, (uint32_t)i, acc ? 1u : 0u, (uint32_t)((wr0 + 1) | ((wr1 + 1) << 2) | ((wr2 + 1) << 4)),
+                                  lds_u32(ra + 48));
+                    }
                 }  // !is_swap
             }
             __syncthreads();
             // ---- retire the round in trial order: warp 0 alone, the others wait at the second barrier --------------
             if (warp == 0) {
-            int ndone = 0;
-            bool swap_committed = false;  // SWAPS: an accepted swap changed the species lists -> later swaps of the round wait
-            auto commit_swap = [&](uint32_t pw, uint32_t iw, uint32_t jw) {  // update_species_list! (src/moves.jl:175-179)
-                const uint32_t si = lds_u8(sb + F.sp + iw), sj = lds_u8(sb + F.sp + jw);
-                const uint32_t oi = lds_u32(sb + F.spoff + 4u * si), oj = lds_u32(sb + F.spoff + 4u * sj);
-                const uint32_t ni = lds_u32(sb + F.spoff + 4u * si + 4u) - oi, nj = lds_u32(sb + F.spoff + 4u * sj + 4u) - oj;
-                // where i and j sit in their species lists: a warp search, paid only by accepted swaps
-                auto find = [&](uint32_t off, uint32_t n, uint32_t who) -> uint32_t {
-                    uint32_t pos = 0;
-                    for (uint32_t b0 = 0; b0 < n; b0 += 32) {
-                        const uint32_t k = b0 + (uint32_t)lane;
-                        const bool hit = k < n && lds_u16(sb + F.spids + 2u * (off + k)) == who;
-                        const unsigned bal = __ballot_sync(0xffffffffu, hit);
-                        if (bal) pos = b0 + (uint32_t)__ffs((int)bal) - 1u;
-                    }
-                    return pos;
+                int ndone = 0;
+                bool swap_committed = false;  // SWAPS: an accepted swap changed the species lists -> later swaps of the round wait
+                auto commit_swap = [&](uint32_t pw, uint32_t iw, uint32_t jw) {  // update_species_list! (src/moves.jl:175-179)
+                    const uint32_t si = lds_u8(sb + F.sp + iw), sj = lds_u8(sb + F.sp + jw);
+                    const uint32_t oi = lds_u32(sb + F.spoff + 4u * si), oj = lds_u32(sb + F.spoff + 4u * sj);
+                    const uint32_t ni = lds_u32(sb + F.spoff + 4u * si + 4u) - oi, nj = lds_u32(sb + F.spoff + 4u * sj + 4u) - oj;
+                    // where i and j sit in their species lists: a warp search, paid only by accepted swaps
+                    auto find = [&](uint32_t off, uint32_t n, uint32_t who) -> uint32_t {
+                        uint32_t pos = 0;
+                        for (uint32_t b0 = 0; b0 < n; b0 += 32) {
+                            const uint32_t k = b0 + (uint32_t)lane;
+                            const bool hit = k < n && lds_u16(sb + F.spids + 2u * (off + k)) == who;
+                            const unsigned bal = __ballot_sync(0xffffffffu, hit);
+                            if (bal) pos = b0 + (uint32_t)__ffs((int)bal) - 1u;
+                        }
+                        return pos;
+                    };
+                    const uint32_t hi = find(oi, ni, iw), hj = find(oj, nj, jw);
+                    __syncwarp();
+                    asm volatile("st.shared.u8 [%0], %1;" ::"r"(sb + F.sp + iw), "r"(sj) : "memory");
+                    asm volatile("st.shared.u8 [%0], %1;" ::"r"(sb + F.sp + jw), "r"(si) : "memory");
+                    sts_u16(sb + F.spids + 2u * (oi + hi), jw);
+                    sts_u16(sb + F.spids + 2u * (oj + hj), iw);
+                    __syncwarp();
+                    E += lds_f64(pw);
+                    swap_committed = true;
                 };
-                const uint32_t hi = find(oi, ni, iw), hj = find(oj, nj, jw);
-                __syncwarp();
-                asm volatile("st.shared.u8 [%0], %1;" ::"r"(sb + F.sp + iw), "r"(sj) : "memory");
-                asm volatile("st.shared.u8 [%0], %1;" ::"r"(sb + F.sp + jw), "r"(si) : "memory");
-                sts_u16(sb + F.spids + 2u * (oi + hi), jw);
-                sts_u16(sb + F.spids + 2u * (oj + hj), iw);
-                __syncwarp();
-                E += lds_f64(pw);
-                swap_committed = true;
-            };
-            if constexpr (NW == 4) {
-            uint32_t cqo[NW], cqn[NW];  // packed old / new position of trials accepted in this round
-            uint32_t cmask = 0;
+                if constexpr (NW == 4) {
+                    uint32_t cqo[NW], cqn[NW];  // packed old / new position of trials accepted in this round
+                    uint32_t cmask = 0;
 #pragma unroll
-            for (int w = 0; w < NW; w++) {
-                if (w < nspec && ndone == w) {  // uniform
-                    const uint32_t pw = pa + (uint32_t)kPubBytes * (uint32_t)w;
-                    uint32_t umq, fthr, qo, qn;
-                    uint32_t iw, fl, wr, mv;
-                    lds_u32x4(pw + 48, iw, fl, wr, mv);
-                    const bool wswap = SWAPS && (fl & 2u) != 0u;
-                    int conflict = 0;
-                    if (w > 0 && cmask != 0u) {
-                        lds_u32x4(pw + 32, umq, fthr, qo, qn);
+                    for (int w = 0; w < NW; w++) {
+                        if (w < nspec && ndone == w) {  // uniform
+                            const uint32_t pw = pa + (uint32_t)kPubBytes * (uint32_t)w;
+                            uint32_t umq, fthr, qo, qn;
+                            uint32_t iw, fl, wr, mv;
+                            lds_u32x4(pw + 48, iw, fl, wr, mv);
+                            const bool wswap = SWAPS && (fl & 2u) != 0u;
+                            int conflict = 0;
+                            if (w > 0 && cmask != 0u) {
+                                lds_u32x4(pw + 32, umq, fthr, qo, qn);
 #pragma unroll
-                        for (int v = 0; v < w; v++) {
-                            if (cmask & (1u << v)) {
-                                const uint32_t ta = __vabsdiffu4(umq, cqo[v]), tb_ = __vabsdiffu4(umq, cqn[v]);
-                                conflict |= __dp4a((int)ta, (int)ta, (int)fthr) | __dp4a((int)tb_, (int)tb_, (int)fthr);
-                                if (wswap) {  // second sphere of a swap: around its particle j
-                                    const uint32_t tc = __vabsdiffu4(qn, cqo[v]), td = __vabsdiffu4(qn, cqn[v]);
-                                    conflict |= __dp4a((int)tc, (int)tc, (int)fthr) | __dp4a((int)td, (int)td, (int)fthr);
+                                for (int v = 0; v < w; v++) {
+                                    if (cmask & (1u << v)) {
+                                        const uint32_t ta = __vabsdiffu4(umq, cqo[v]), tb_ = __vabsdiffu4(umq, cqn[v]);
+                                        conflict |= __dp4a((int)ta, (int)ta, (int)fthr) | __dp4a((int)tb_, (int)tb_, (int)fthr);
+                                        if (wswap) {  // second sphere of a swap: around its particle j
+                                            const uint32_t tc = __vabsdiffu4(qn, cqo[v]), td = __vabsdiffu4(qn, cqn[v]);
+                                            conflict |= __dp4a((int)tc, (int)tc, (int)fthr) | __dp4a((int)td, (int)td, (int)fthr);
+                                        }
+                                    }
+                                }
+                                if (wswap && swap_committed) conflict = -1;
+                            }
+                            if (conflict >= 0) {  // stands: retire it
+                                ndone = w + 1;
+                                const bool acc = (fl & 1u) != 0u;
+                                if (acc) {
+                                    if (w == 0 || cmask == 0u) lds_u32x4(pw + 32, umq, fthr, qo, qn);
+                                    cmask |= 1u << w;
+                                    cqo[w] = qo;
+                                    cqn[w] = qn;
+                                    if (wswap) {
+                                        commit_swap(pw, iw, wr);
+                                    } else {
+                                        if constexpr (MIXED) {
+                                            uint32_t n0, n1, n2, pad_;
+                                            lds_u32x4(pw + 16, n0, n1, n2, pad_);
+                                            const uint32_t ua = sb + F.x + 4u * iw;
+                                            sts_u32(ua, n0);
+                                            sts_u32(ua + nb4, n1);
+                                            if constexpr (DIM == 3) sts_u32(ua + 2 * nb4, n2);
+                                            E += lds_f64(pw);
+                                        } else {
+                                            double dE, x0, x1, x2;
+                                            lds_f64x2(pw, dE, x0);
+                                            lds_f64x2(pw + 16, x1, x2);
+                                            const uint32_t xa = sb + F.x + 8u * iw;
+                                            sts_f64(xa, x0);
+                                            sts_f64(xa + nb8, x1);
+                                            if constexpr (DIM == 3) sts_f64(xa + 2 * nb8, x2);
+                                            E += dE;
+                                        }
+                                        sts_u32(sb + F.pk + 4u * iw, qn);
+                                        if (tid == kImgThread && wr != 0x15u) {  // some coordinate wrapped around the box
+                                            const int w0 = (int)(wr & 3u) - 1, w1 = (int)((wr >> 2) & 3u) - 1, w2 = (int)((wr >> 4) & 3u) - 1;
+                                            if (w0) atomicAdd(&gimg[iw], w0);
+                                            if (w1) atomicAdd(&gimg[gNpad + iw], w1);
+                                            if (DIM == 3 && w2) atomicAdd(&gimg[2 * gNpad + iw], w2);
+                                        }
+                                    }
+                                }
+                                if (tid == kCntThread) {
+                                    uint32_t *c32 = (uint32_t *)(smem_raw + F.cnt32);
+                                    atomicAdd(&c32[mv], 1u);
+                                    if (acc) atomicAdd(&c32[PMC_MAX_MOVES + mv], 1u);
+                                    if (dbg_out) {
+                                        if (A.acc_out) A.acc_out[(size_t)c * A.n_trials + tb + cur + w] = acc ? 1 : 0;
+                                        if (A.dE_out) A.dE_out[(size_t)c * A.n_trials + tb + cur + w] = lds_f64(pw);
+                                    }
                                 }
                             }
                         }
-                        if (wswap && swap_committed) conflict = -1;
                     }
-                    if (conflict >= 0) {  // stands: retire it
+                } else {
+                    // the same retirement, rolled: the packed positions of the accepted trials are read back from the
+                    // published entries instead of living in registers
+                    uint32_t cmask = 0;
+                    for (int w = 0; w < nspec; w++) {
+                        const uint32_t pw = pa + (uint32_t)kPubBytes * (uint32_t)w;
+                        uint32_t umq, fthr, qo, qn;
+                        lds_u32x4(pw + 32, umq, fthr, qo, qn);
+                        uint32_t iw, fl, wr, mv;
+                        lds_u32x4(pw + 48, iw, fl, wr, mv);
+                        const bool wswap = SWAPS && (fl & 2u) != 0u;
+                        int conflict = 0;
+                        for (uint32_t mm = cmask; mm; mm &= mm - 1u) {
+                            const uint32_t pv = pa + (uint32_t)kPubBytes * (uint32_t)(__ffs((int)mm) - 1);
+                            const uint32_t p0 = lds_u32(pv + 40), p1 = lds_u32(pv + 44);
+                            const uint32_t ta = __vabsdiffu4(umq, p0), tb_ = __vabsdiffu4(umq, p1);
+                            conflict |= __dp4a((int)ta, (int)ta, (int)fthr) | __dp4a((int)tb_, (int)tb_, (int)fthr);
+                            if (wswap) {
+                                const uint32_t tc = __vabsdiffu4(qn, p0), td = __vabsdiffu4(qn, p1);
+                                conflict |= __dp4a((int)tc, (int)tc, (int)fthr) | __dp4a((int)td, (int)td, (int)fthr);
+                            }
+                        }
+                        if (wswap && swap_committed) conflict = -1;
+                        if (conflict < 0) break;
                         ndone = w + 1;
                         const bool acc = (fl & 1u) != 0u;
-                        if (acc) {
-                            if (w == 0 || cmask == 0u) lds_u32x4(pw + 32, umq, fthr, qo, qn);
+                        if (acc && wswap) {
                             cmask |= 1u << w;
-                            cqo[w] = qo;
-                            cqn[w] = qn;
-                            if (wswap) {
-                                commit_swap(pw, iw, wr);
-                            } else
-                            {
-                            if constexpr (MIXED) {
-                                uint32_t n0, n1, n2, pad_;
-                                lds_u32x4(pw + 16, n0, n1, n2, pad_);
-                                const uint32_t ua = sb + F.x + 4u * iw;
-                                sts_u32(ua, n0);
-                                sts_u32(ua + nb4, n1);
-                                if constexpr (DIM == 3) sts_u32(ua + 2 * nb4, n2);
-                                E += lds_f64(pw);
-                            } else {
-                                double dE, x0, x1, x2;
-                                lds_f64x2(pw, dE, x0);
-                                lds_f64x2(pw + 16, x1, x2);
-                                const uint32_t xa = sb + F.x + 8u * iw;
-                                sts_f64(xa, x0);
-                                sts_f64(xa + nb8, x1);
-                                if constexpr (DIM == 3) sts_f64(xa + 2 * nb8, x2);
-                                E += dE;
-                            }
+                            commit_swap(pw, iw, wr);
+                        } else if (acc) {
+                            cmask |= 1u << w;
+                            double dE, x0, x1, x2;
+                            lds_f64x2(pw, dE, x0);
+                            lds_f64x2(pw + 16, x1, x2);
+                            const uint32_t xa = sb + F.x + 8u * iw;
+                            sts_f64(xa, x0);
+                            sts_f64(xa + nb8, x1);
+                            if constexpr (DIM == 3) sts_f64(xa + 2 * nb8, x2);
+                            E += dE;
                             sts_u32(sb + F.pk + 4u * iw, qn);
-                            if (tid == kImgThread && wr != 0x15u) {  // some coordinate wrapped around the box
+                            if (tid == kImgThread && wr != 0x15u) {
                                 const int w0 = (int)(wr & 3u) - 1, w1 = (int)((wr >> 2) & 3u) - 1, w2 = (int)((wr >> 4) & 3u) - 1;
                                 if (w0) atomicAdd(&gimg[iw], w0);
                                 if (w1) atomicAdd(&gimg[gNpad + iw], w1);
                                 if (DIM == 3 && w2) atomicAdd(&gimg[2 * gNpad + iw], w2);
                             }
-                                                    }
                         }
                         if (tid == kCntThread) {
                             uint32_t *c32 = (uint32_t *)(smem_raw + F.cnt32);
@@ -723,66 +781,7 @@ __global__ void __launch_bounds__(32 * NW, NPAD <= 1024 ? (MIXED ? 8 : (MOL ? 5 
                         }
                     }
                 }
-            }
-            } else {
-                // the same retirement, rolled: the packed positions of the accepted trials are read back from the
-                // published entries instead of living in registers
-                uint32_t cmask = 0;
-                for (int w = 0; w < nspec; w++) {
-                    const uint32_t pw = pa + (uint32_t)kPubBytes * (uint32_t)w;
-                    uint32_t umq, fthr, qo, qn;
-                    lds_u32x4(pw + 32, umq, fthr, qo, qn);
-                    uint32_t iw, fl, wr, mv;
-                    lds_u32x4(pw + 48, iw, fl, wr, mv);
-                    const bool wswap = SWAPS && (fl & 2u) != 0u;
-                    int conflict = 0;
-                    for (uint32_t mm = cmask; mm; mm &= mm - 1u) {
-                        const uint32_t pv = pa + (uint32_t)kPubBytes * (uint32_t)(__ffs((int)mm) - 1);
-                        const uint32_t p0 = lds_u32(pv + 40), p1 = lds_u32(pv + 44);
-                        const uint32_t ta = __vabsdiffu4(umq, p0), tb_ = __vabsdiffu4(umq, p1);
-                        conflict |= __dp4a((int)ta, (int)ta, (int)fthr) | __dp4a((int)tb_, (int)tb_, (int)fthr);
-                        if (wswap) {
-                            const uint32_t tc = __vabsdiffu4(qn, p0), td = __vabsdiffu4(qn, p1);
-                            conflict |= __dp4a((int)tc, (int)tc, (int)fthr) | __dp4a((int)td, (int)td, (int)fthr);
-                        }
-                    }
-                    if (wswap && swap_committed) conflict = -1;
-                    if (conflict < 0) break;
-                    ndone = w + 1;
-                    const bool acc = (fl & 1u) != 0u;
-                    if (acc && wswap) {
-                        cmask |= 1u << w;
-                        commit_swap(pw, iw, wr);
-                    } else if (acc) {
-                        cmask |= 1u << w;
-                        double dE, x0, x1, x2;
-                        lds_f64x2(pw, dE, x0);
-                        lds_f64x2(pw + 16, x1, x2);
-                        const uint32_t xa = sb + F.x + 8u * iw;
-                        sts_f64(xa, x0);
-                        sts_f64(xa + nb8, x1);
-                        if constexpr (DIM == 3) sts_f64(xa + 2 * nb8, x2);
-                        E += dE;
-                        sts_u32(sb + F.pk + 4u * iw, qn);
-                        if (tid == kImgThread && wr != 0x15u) {
-                            const int w0 = (int)(wr & 3u) - 1, w1 = (int)((wr >> 2) & 3u) - 1, w2 = (int)((wr >> 4) & 3u) - 1;
-                            if (w0) atomicAdd(&gimg[iw], w0);
-                            if (w1) atomicAdd(&gimg[gNpad + iw], w1);
-                            if (DIM == 3 && w2) atomicAdd(&gimg[2 * gNpad + iw], w2);
-                        }
-                    }
-                    if (tid == kCntThread) {
-                        uint32_t *c32 = (uint32_t *)(smem_raw + F.cnt32);
-                        atomicAdd(&c32[mv], 1u);
-                        if (acc) atomicAdd(&c32[PMC_MAX_MOVES + mv], 1u);
-                        if (dbg_out) {
-                            if (A.acc_out) A.acc_out[(size_t)c * A.n_trials + tb + cur + w] = acc ? 1 : 0;
-                            if (A.dE_out) A.dE_out[(size_t)c * A.n_trials + tb + cur + w] = lds_f64(pw);
-                        }
-                    }
-                }
-            }
-            if (lane == 0) sts_u32(sb + F.pub + 2u * kPubBytes * NW, (uint32_t)ndone);
+                if (lane == 0) sts_u32(sb + F.pub + 2u * kPubBytes * NW, (uint32_t)ndone);
             }
             __syncthreads();
             cur += (int)lds_u32(sb + F.pub + 2u * kPubBytes * NW);
