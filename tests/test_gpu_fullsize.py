@@ -1,0 +1,71 @@
+"""BASELINE.json's full sizes (config 2: 4096 chains x N = 1000; config 3: one box of N = 2^20), checked through
+size-independent properties: the running energy equals a recomputation from the final configuration, chains do not
+influence each other (a subset run alone reproduces the same chains bit for bit), composition and counters are
+conserved, the same seed gives the same trajectory."""
+import numpy as np
+import pytest
+
+from particlesmc_b200 import _lib as L
+from particlesmc_b200 import models as M
+from particlesmc_b200.device import DeviceContext
+from particlesmc_b200.synthetic import ka_lattice
+
+pytestmark = pytest.mark.gpu
+
+
+def ka_chains(ctx, pos, sp, box, n, T=1.0):
+    ctx.set_model(M.flatten_model_matrix(M.KobAndersen()))
+    ctx.upload(np.broadcast_to(pos, (n,) + pos.shape).copy(), np.broadcast_to(sp, (n,) + sp.shape).copy(), box, T)
+    ctx.init_energy()
+    ctx.set_moves([dict(kind="displacement", prob=1.0, sigma=0.05)])
+    ctx.seed(42)
+
+
+def test_config2_4096_chains_of_1000():
+    N, nch, sweeps = 1000, 4096, 3
+    pos, sp, box = ka_lattice(N, 1.2, seed=0)
+    with DeviceContext(nch, N, 3, 2, M.MODEL_LJ) as ctx:
+        ka_chains(ctx, pos, sp, box, nch)
+        e0 = ctx.energy()
+        assert np.all(e0 == e0[0])  # identical replicas, identical initial energies
+        ctx.run(sweeps * N)
+        e_run, e_tot = ctx.energy(), ctx.total_energy()
+        assert np.max(np.abs(e_run - e_tot) / np.abs(e_tot)) < 1e-11
+        calls, acc = ctx.counters()
+        assert np.all(calls[:, 0] == sweeps * N) and np.all(acc[:, 0] > 0) and np.all(acc[:, 0] < sweeps * N)
+        assert len(np.unique(e_run)) == nch  # every chain drew its own stream
+        p_all, s_all = ctx.download(0, nch)
+        assert np.array_equal(s_all, np.broadcast_to(sp, s_all.shape))
+        # per-chain checksum of the coordinates, and a checksum of the checksums
+        chk = np.frombuffer(np.ascontiguousarray(p_all).tobytes(), dtype=np.uint64).reshape(nch, -1).sum(axis=1)
+    # the last 5 chains alone (global indices through chain_offset): same streams, same coordinates
+    with DeviceContext(5, N, 3, 2, M.MODEL_LJ, chain_offset=nch - 5) as sub:
+        ka_chains(sub, pos, sp, box, 5)
+        sub.run(sweeps * N)
+        p_sub, _ = sub.download(0, 5)
+        chk_sub = np.frombuffer(np.ascontiguousarray(p_sub).tobytes(), dtype=np.uint64).reshape(5, -1).sum(axis=1)
+        assert np.array_equal(chk_sub, chk[-5:])
+        assert np.array_equal(sub.energy(), e_run[-5:])
+
+
+def test_config3_box_of_2_to_the_20():
+    N = 1 << 20
+    pos, sp, box = ka_lattice(N, 1.2, seed=0)
+    par = M.flatten_model_matrix(M.KobAndersen())
+    finals = []
+    for _ in range(2):
+        with DeviceContext(1, N, 3, 2, M.MODEL_LJ, mode=L.MODE_BOX) as ctx:
+            ctx.set_model(par)
+            ctx.upload(pos, sp, box, 1.0)
+            ctx.init_energy()
+            ctx.set_moves([dict(kind="displacement", prob=1.0, sigma=0.05)])
+            ctx.seed(42)
+            ctx.run(2 * N)
+            e_run, e_tot = ctx.energy()[0], ctx.total_energy()[0]
+            assert abs(e_run - e_tot) / abs(e_tot) < 1e-11
+            calls, acc = ctx.counters()
+            assert calls[0, 0] == 2 * N and 0.1 < acc[0, 0] / calls[0, 0] < 0.9
+            p, s = ctx.download()
+            assert np.array_equal(np.bincount(s[0]), np.bincount(sp))
+            finals.append(p[0])
+    assert np.array_equal(finals[0], finals[1])
