@@ -11,7 +11,8 @@ One "step" = one pass of the hot path over the whole batch: every chain advanced
              launch stream (max over ranks), L2 flushed between steps.
   e2e        the same metric through the C ABI with HOST buffers: every step uploads all chain states from
              pinned host memory (pmc_upload + pmc_init_energy), runs the sweeps and downloads energies and
-             full states (pmc_energy + pmc_download).
+             full states (pmc_energy + pmc_download).  The chains are held by --e2e-contexts library contexts
+             on separate streams, so one context's copies overlap another's sweeps (same chains, same bytes).
   roofline   pair-evaluation roofline of the sweep kernel (FP64 CUDA-core pipe): achieved =
              moves/s x P x F with P = reference-equivalent candidate pairs per move and F flops per pair,
              against the DFMA burst peak measured in this run (MEASURED_PEAKS.json has no FP64 figure).
@@ -71,6 +72,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-sweeps", type=int, default=200)
+    ap.add_argument("--e2e-contexts", type=int, default=4,
+                    help="chains workload, e2e leg: the chains are held by this many library contexts on separate streams, so "
+                         "that one context's host<->device copies overlap another's sweeps (1 = a single context)")
     return ap.parse_args()
 
 
@@ -318,15 +322,49 @@ def run_ours(args):
     # ---- end to end through the C ABI with host buffers -------------------------------------------------
     e2e = None
     if not args.no_e2e:
+        K = args.e2e_contexts if (args.workload == "chains" and args.e2e_contexts > 1 and Mc % args.e2e_contexts == 0) else 1
+        if K > 1:
+            # the same chains (same global indices, same seed) split over K contexts with their own streams: while one
+            # context sweeps, the next one's upload and the previous one's download use the copy engines
+            Mk = Mc // K
+            parts = []
+            for k in range(K):
+                c = DeviceContext(Mk, N, 3, 2, M.MODEL_LJ, mode=mode, device=local, chain_offset=rank * Mc + k * Mk,
+                                  threads=args.threads, prefilter=args.prefilter,
+                                  precision=L.MIXED if args.precision == "mixed" else L.FP64)
+                st = torch.cuda.Stream(device=dev)
+                c.set_stream(st.cuda_stream)
+                c.set_model(par)
+                parts.append((c, st, k * Mk))
+            def up(c, o):
+                c.upload_raw(h_pos.data_ptr() + o * N * 3 * 8, h_sp.data_ptr() + o * N * 8, h_box.data_ptr() + o * 3 * 8,
+                             h_T.data_ptr() + o * 8, 0, Mk)
+                c.init_energy()
+            def down(c, o):
+                c.energy_into(h_E.data_ptr() + o * 8)
+                c.download_raw(h_pos.data_ptr() + o * N * 3 * 8, h_sp.data_ptr() + o * N * 8, 0, Mk)
+            for c, st, o in parts:
+                up(c, o)
+                c.set_moves([dict(kind="displacement", prob=1.0, sigma=0.05)])
+                c.seed(42)
+            def e2e_step():
+                for c, st, o in parts:
+                    up(c, o)
+                    c.run(trials_per_step, sync=False)
+                for c, st, o in parts:
+                    down(c, o)
+        else:
+            def e2e_step():
+                upload()
+                ctx.run(trials_per_step, sync=False)
+                download()
         for _ in range(2):
-            upload(); ctx.run(trials_per_step, sync=False); download()
+            e2e_step()
         barrier()
         t0 = time.perf_counter()
         ev[0].record()
         for _ in range(args.steps):
-            upload()
-            ctx.run(trials_per_step, sync=False)
-            download()
+            e2e_step()
         ev[1].record()
         barrier()
         wall_ms = (time.perf_counter() - t0) * 1e3
@@ -336,8 +374,11 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         h2d = h_pos.numel() * 8 + h_sp.numel() * 8 + h_box.numel() * 8 + h_T.numel() * 8
         d2h = h_pos.numel() * 8 + h_sp.numel() * 8 + h_E.numel() * 8
+        if K > 1:
+            for c, st, o in parts:
+                c.close()
         e2e = {"value": moves_per_step * args.steps / (float(t.item()) * 1e-3), "unit": UNIT,
-               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "contexts": K,
                "energy_per_particle_mean": float(h_E.numpy().mean() / N)}
 
     # ---- energy sanity in the same run: bookkeeping vs recomputed --------------------------------------
