@@ -20,8 +20,8 @@ def ka(N, seed):
     return pos - np.floor(pos / box) * box, sp, box
 
 
-def ctx_for(precision, n_chains, N, pos, sp, box, T=1.0):
-    ctx = DeviceContext(n_chains, N, 3, 2, M.MODEL_LJ, precision=precision)
+def ctx_for(precision, n_chains, N, pos, sp, box, T=1.0, prefilter=0):
+    ctx = DeviceContext(n_chains, N, 3, 2, M.MODEL_LJ, precision=precision, prefilter=prefilter)
     ctx.set_model(M.flatten_model_matrix(M.KobAndersen()))
     ctx.upload(np.stack([pos] * n_chains), np.stack([sp] * n_chains), box, T)
     ctx.init_energy()
@@ -30,11 +30,12 @@ def ctx_for(precision, n_chains, N, pos, sp, box, T=1.0):
     return ctx
 
 
-def test_mixed_delta_e_within_1e6_of_oracle():
+@pytest.mark.parametrize("prefilter", [0, 1])  # 0: speculative schedule, 1: one trial at a time (k_chain_sweep_mixed)
+def test_mixed_delta_e_within_1e6_of_oracle(prefilter):
     N, n = 1000, 1500
     pos, sp, box = ka(N, 3)
     par = M.flatten_model_matrix(M.KobAndersen())
-    with ctx_for(L.MIXED, 1, N, pos, sp, box) as ctx:
+    with ctx_for(L.MIXED, 1, N, pos, sp, box, prefilter=prefilter) as ctx:
         tr, acc, dE = ctx.run_traced(n)
         e_run, e_tot = ctx.energy()[0], ctx.total_energy()[0]
     orc = O.OracleSystem(pos, sp, box, 1.0, M.MODEL_LJ, par, O.LINKEDLIST)
@@ -71,6 +72,23 @@ def test_mixed_bookkeeping_and_statistics_match_fp64():
     err = np.hypot(m64.std(), mmx.std()) / np.sqrt(n_chains)
     assert abs(m64.mean() - mmx.mean()) < 4 * err + 2e-3, (m64.mean(), mmx.mean(), err)
     assert abs(res["fp64"][1].mean() - res["mixed"][1].mean()) < 0.01
+
+
+def test_mixed_schedules_take_identical_decisions():
+    """PMC_MIXED in the speculative schedule and one trial at a time: same integer state, same fp32 pair terms per
+    trial -> identical decisions and identical final fixed-point coordinates (dE differs only by summation order)."""
+    N = 512
+    pos, sp, box = ka(N, 7)
+    with ctx_for(L.MIXED, 4, N, pos, sp, box, prefilter=0) as a, ctx_for(L.MIXED, 4, N, pos, sp, box, prefilter=1) as b:
+        _, acc_a, dE_a = a.run_traced(6 * N + 5)
+        _, acc_b, dE_b = b.run_traced(6 * N + 5)
+        same = acc_a == acc_b
+        # fp32 rounding of a different summation order can flip a decision that sits within 1e-7 of its threshold;
+        # once it does the chains part ways, so compare up to the first difference and require it to be rare
+        for c in range(4):
+            first = same.shape[1] if same[c].all() else int(np.argmin(same[c]))
+            assert first >= 0.5 * same.shape[1], f"chain {c}: decisions diverged after {first} trials"
+            assert np.max(np.abs(dE_a[c][:first] - dE_b[c][:first])) < 1e-4
 
 
 def test_mixed_rejects_unsupported_shapes():
