@@ -13,7 +13,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
 CSRC = os.path.join(_HERE, "csrc")
 LIB_DIR = os.path.join(_HERE, "lib")
-LIB_PATH = os.path.join(LIB_DIR, "libpmc_b200.so")
+# PMC_B200_LIB names an alternative build of the library (A/B measurements of build-time kernel switches, built with
+# `python -m particlesmc_b200.build --out NAME -DSWITCH=VALUE ...`); the product default is libpmc_b200.so
+LIB_PATH = os.path.join(LIB_DIR, os.environ.get("PMC_B200_LIB", "libpmc_b200.so"))
 SOURCES = ["api.cu", "chains.cu", "chains_fast.cu", "chains_spec.cu", "box.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -33,20 +35,22 @@ def find_nvcc() -> str:
     return nvcc
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
+def build_library(force: bool = False, verbose: bool = False, out: str | None = None, defines: tuple = ()) -> str:
     """Compile if the library is missing or older than any source. Returns the library path."""
-    if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= _newest_source_mtime():
-        return LIB_PATH
+    lib_path = os.path.join(LIB_DIR, out) if out else LIB_PATH
+    if not force and os.path.exists(lib_path) and os.path.getmtime(lib_path) >= _newest_source_mtime():
+        return lib_path
     os.makedirs(LIB_DIR, exist_ok=True)
     import tempfile
-    obj_dir = os.path.join(tempfile.gettempdir(), "pmc_b200_build")  # objects stay out of the repo snapshot
+    # objects stay out of the repo snapshot
+    obj_dir = os.path.join(tempfile.gettempdir(), "pmc_b200_build_" + os.path.basename(lib_path))
     os.makedirs(obj_dir, exist_ok=True)
     nvcc = find_nvcc()
     inc = ["-I", os.path.join(ROOT, "include"), "-I", CSRC]
 
     def compile_one(src: str):
         obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, *inc, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *defines, *inc, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         res = subprocess.run(cmd, capture_output=True, text=True)
@@ -61,14 +65,16 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError(f"nvcc failed on {src}:\n" + res.stdout + res.stderr)
         if verbose:
             print(res.stderr)
-    link = subprocess.run([nvcc, "-shared", "-ccbin", "/usr/bin/g++", "-o", LIB_PATH, *[o for _, o, _ in results]],
+    link = subprocess.run([nvcc, "-shared", "-ccbin", "/usr/bin/g++", "-o", lib_path, *[o for _, o, _ in results]],
                           capture_output=True, text=True)
     if link.returncode != 0:
         raise RuntimeError("link failed:\n" + link.stdout + link.stderr)
-    return LIB_PATH
+    return lib_path
 
 
 if __name__ == "__main__":
     import sys
 
-    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    out_name = sys.argv[sys.argv.index("--out") + 1] if "--out" in sys.argv else None
+    print(build_library(force="--force" in sys.argv or out_name is not None, verbose="-v" in sys.argv, out=out_name,
+                        defines=tuple(a for a in sys.argv[1:] if a.startswith("-D"))))

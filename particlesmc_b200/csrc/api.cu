@@ -194,6 +194,7 @@ struct pmc_ctx {
     int n_mol = 0;
     int mol_uniform_len = 0;  // > 0: every molecule has this many sites (pmc_chain_correlation)
     int *bad = nullptr;
+    int32_t *queue = nullptr;  // [1 + n_chains] work queue of the speculative kernel (chains_spec.cuh)
     // staging
     double *raw_pos = nullptr;
     long long *raw_sp = nullptr;
@@ -354,7 +355,7 @@ int sweep(pmc_ctx *c, int64_t n_trials, const pmc_trial *d_replay, pmc_trial *d_
             c->spec_smem = ss;
             c->spec_swaps = any_swap;
         }
-        CU(pmc::launch_chain_sweep_spec(c->cfg.dim, c->cfg.model_kind, c->cfg.n_chains, ss, a, c->stream, mixed, mol, any_swap));
+        CU(pmc::launch_chain_sweep_spec(c->cfg.dim, c->cfg.model_kind, c->cfg.n_chains, ss, a, c->stream, mixed, mol, any_swap, c->queue));
     } else if (mixed) {
         if (!fastk || any_swap)
             return fail(PMC_ERR_UNSUPPORTED, "PMC_MIXED needs a cubic box, a Displacement-only pool and %d threads per CTA", 128);
@@ -445,6 +446,7 @@ int pmc_create(const pmc_config *cfg, pmc_ctx **out) {
     if (a == cudaSuccess) a = dalloc(&c->accepted, M * PMC_MAX_MOVES);
     if (a == cudaSuccess) a = dalloc(&c->par, (size_t)PMC_MAX_SPECIES * PMC_MAX_SPECIES * PMC_NPAR);
     if (a == cudaSuccess) a = dalloc(&c->bad, 1);
+    if (a == cudaSuccess && cfg->mode == PMC_MODE_CHAINS) a = dalloc(&c->queue, M + 1);
     // the zero-fills above ran on the legacy default stream, which the context's non-blocking stream does not
     // wait for: drain them before any kernel of this context can touch the buffers
     if (a == cudaSuccess) a = cudaDeviceSynchronize();
@@ -470,7 +472,7 @@ void pmc_destroy(pmc_ctx *c) {
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
     if (c->boxst) pmc::box_destroy(c->boxst);
     void *bufs[] = {c->x, c->img, c->sp, c->spids, c->heads, c->spoff, c->box, c->temp, c->energy, c->etot, c->eloc,
-                    c->par, c->calls, c->accepted, c->bonds, c->bad, c->raw_pos, c->raw_sp, c->mol_start, c->mol_len};
+                    c->par, c->calls, c->accepted, c->bonds, c->bad, c->queue, c->raw_pos, c->raw_sp, c->mol_start, c->mol_len};
     for (void *p : bufs)
         if (p) cudaFree(p);
     if (c->ev0) cudaEventDestroy(c->ev0);

@@ -49,6 +49,12 @@ struct ChainArgs {
     uint8_t *acc_out;
     double *dE_out;
     int32_t exact_exp;  // 1: accept iff min(1, exp(-(e2-e1)/T)) > u (reference form); 0: -dE/T > log u
+    // work queue of the speculative kernel (chains_spec.cuh): with more chains than resident CTAs the launch is cut into
+    // n_seg segments of seg_len trials per chain and persistent CTAs pull (chain, segment) units from queue[0];
+    // queue[1 + chain] counts the finished segments of a chain (a unit waits for its predecessor).  nullptr: one CTA per chain.
+    int32_t *queue;
+    int32_t n_chains, n_seg;
+    long long seg_len;
 };
 
 struct EnergyArgs {
@@ -83,7 +89,7 @@ bool chain_spec_supported(int dim, int model, int Npad, int threads, bool mol, b
 size_t chain_spec_smem_bytes(int dim, int Npad, int model, bool mixed, bool mol, bool swaps);
 cudaError_t configure_chain_spec(int dim, int model, int Npad, size_t smem, bool mixed, bool mol, bool swaps);
 cudaError_t launch_chain_sweep_spec(int dim, int model, int M, size_t smem, const ChainArgs &a, cudaStream_t st, bool mixed,
-                                    bool mol, bool swaps);
+                                    bool mol, bool swaps, int32_t *queue);
 // local energies through the 8-bit prefilter (Atoms, cubic box, N <= 1024)
 cudaError_t launch_chain_energy_fast(int dim, int model, int M, const EnergyArgs &a, cudaStream_t st);
 // PMC_MIXED variant of the fast kernel (fp32 pair terms on fixed-point coordinates, fp64 accumulation)

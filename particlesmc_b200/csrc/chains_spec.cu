@@ -2,6 +2,9 @@
 // unit so that the kernel families compile in parallel.
 #include <cuda_runtime.h>
 
+#include <algorithm>
+#include <cstdlib>
+
 #include "chains.cuh"
 #include "chains_spec.cuh"
 
@@ -18,6 +21,7 @@ int spec_npad(int Npad) {
 template <bool MIXED, bool SWAPS, typename F>
 cudaError_t spec_dispatch(int dim, int model, int Npad, bool mol, int threads, F &&f) {
     const int np = spec_npad(Npad);
+    constexpr int kNwS = (MIXED || SWAPS) ? 4 : PMC_SPEC_NW_SMALL;  // trials in flight for the small shapes
     if (SWAPS && (mol || MIXED || model == PMC_MODEL_KG)) return cudaErrorInvalidValue;
     if (mol) {
         if (MIXED || dim != 3 || model != PMC_MODEL_KG) return cudaErrorInvalidValue;
@@ -37,9 +41,9 @@ cudaError_t spec_dispatch(int dim, int model, int Npad, bool mol, int threads, F
 #define PMC_CASE(D, MDL)                                                                                                \
     if (dim == D && model == MDL) {                                                                                     \
         if constexpr (!SWAPS || MDL != PMC_MODEL_KG) {                                                                  \
-            if (np == 256) return f(spec::k_chain_sweep_spec<D, MDL, 256, MIXED, false, 4, SWAPS>);                     \
-            if (np == 512) return f(spec::k_chain_sweep_spec<D, MDL, 512, MIXED, false, 4, SWAPS>);                     \
-            if (np == 1024) return f(spec::k_chain_sweep_spec<D, MDL, 1024, MIXED, false, 4, SWAPS>);                   \
+            if (np == 256) return f(spec::k_chain_sweep_spec<D, MDL, 256, MIXED, false, kNwS, SWAPS>);                  \
+            if (np == 512) return f(spec::k_chain_sweep_spec<D, MDL, 512, MIXED, false, kNwS, SWAPS>);                  \
+            if (np == 1024) return f(spec::k_chain_sweep_spec<D, MDL, 1024, MIXED, false, kNwS, SWAPS>);                \
             if constexpr (!MIXED) {                                                                                     \
                 if (np == 2048) return f(spec::k_chain_sweep_spec<D, MDL, 2048, false, false, D == 2 ? 4 : 8, SWAPS>);  \
             }                                                                                                           \
@@ -58,13 +62,16 @@ cudaError_t spec_dispatch(int dim, int model, int Npad, bool mol, int threads, F
     return cudaErrorInvalidValue;
 }
 
-int spec_warps(int dim, int Npad, bool mol) { return spec_npad(Npad) <= 1024 || (dim == 2 && !mol) ? 4 : 8; }
+int spec_warps(int dim, int Npad, bool mol, bool mixed, bool swaps) {
+    if (spec_npad(Npad) <= 1024 && !mol && !mixed && !swaps) return PMC_SPEC_NW_SMALL;
+    return spec_npad(Npad) <= 1024 || (dim == 2 && !mol) ? 4 : 8;
+}
 
 }  // namespace
 
 bool chain_spec_supported(int dim, int model, int Npad, int threads, bool mol, bool mixed, bool swaps) {
     const int np = spec_npad(Npad);
-    if (Npad > np || threads != 32 * spec_warps(dim, Npad, mol)) return false;
+    if (Npad > np || threads != 32 * spec_warps(dim, Npad, mol, mixed, swaps)) return false;
     if (swaps && (mol || mixed || model == PMC_MODEL_KG)) return false;
     if (mixed) return !mol && np <= 1024;
     if (mol) return dim == 3 && model == PMC_MODEL_KG;
@@ -73,12 +80,12 @@ bool chain_spec_supported(int dim, int model, int Npad, int threads, bool mol, b
 
 size_t chain_spec_smem_bytes(int dim, int Npad, int model, bool mixed, bool mol, bool swaps) {
     const bool full_par = !mixed && (mol || !(model == PMC_MODEL_LJ || model == PMC_MODEL_KG));
-    return spec::spec_layout(dim, spec_npad(Npad), full_par, mixed, spec_warps(dim, Npad, mol), swaps).total;
+    return spec::spec_layout(dim, spec_npad(Npad), full_par, mixed, spec_warps(dim, Npad, mol, mixed, swaps), swaps).total;
 }
 
 template <typename F>
 static cudaError_t spec_dispatch_rt(int dim, int model, int Npad, bool mixed, bool mol, bool swaps, F &&f) {
-    const int th = 32 * spec_warps(dim, Npad, mol);
+    const int th = 32 * spec_warps(dim, Npad, mol, mixed, swaps);
     if (mixed) return spec_dispatch<true, false>(dim, model, Npad, mol, th, f);
     if (swaps) return spec_dispatch<false, true>(dim, model, Npad, mol, th, f);
     return spec_dispatch<false, false>(dim, model, Npad, mol, th, f);
@@ -90,11 +97,47 @@ cudaError_t configure_chain_spec(int dim, int model, int Npad, size_t smem, bool
     });
 }
 
-cudaError_t launch_chain_sweep_spec(int dim, int model, int M, size_t smem, const ChainArgs &a, cudaStream_t st, bool mixed,
-                                    bool mol, bool swaps) {
-    const int th = 32 * spec_warps(dim, a.Npad, mol);
-    return spec_dispatch_rt(dim, model, a.Npad, mixed, mol, swaps, [&](auto kernel) {
-        kernel<<<M, th, smem, st>>>(a);
+// One CTA per chain, or -- when the chains do not fill a whole number of waves of resident CTAs -- persistent CTAs
+// pulling (chain, segment) units from `queue` (chains_spec.cuh).  PMC_SPEC_QUEUE=0 in the environment forces the plain
+// launch (A/B measurements).
+cudaError_t launch_chain_sweep_spec(int dim, int model, int M, size_t smem, const ChainArgs &a_in, cudaStream_t st, bool mixed,
+                                    bool mol, bool swaps, int32_t *queue) {
+    const int th = 32 * spec_warps(dim, a_in.Npad, mol, mixed, swaps);
+    static const bool queue_on = [] {
+        const char *e = std::getenv("PMC_SPEC_QUEUE");
+        return !(e && e[0] == '0');
+    }();
+    return spec_dispatch_rt(dim, model, a_in.Npad, mixed, mol, swaps, [&](auto kernel) {
+        ChainArgs a = a_in;
+        int grid = M;
+        a.queue = nullptr;
+        a.n_chains = M;
+        a.n_seg = 1;
+        a.seg_len = a.n_trials;
+        if (queue && queue_on && !a.replay && !a.trace && !a.acc_out && !a.dE_out) {
+            int dev = 0, sms = 0, occ = 0;
+            cudaError_t e = cudaGetDevice(&dev);
+            if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, th, smem);
+            if (e != cudaSuccess) return e;
+            const long long slots = (long long)sms * occ;
+            if (slots > 0 && M > slots && M % slots != 0) {
+                // >= 24 waves of units, segments of at least four proposal batches (state load/store stays < 1 %)
+                long long nseg = std::min((24 * slots + M - 1) / M, a.n_trials / (4 * spec::kSpecBatch));
+                if (nseg >= 2) {
+                    long long len = (a.n_trials + nseg - 1) / nseg;
+                    len = (len + spec::kSpecBatch - 1) / spec::kSpecBatch * spec::kSpecBatch;
+                    nseg = (a.n_trials + len - 1) / len;
+                    a.queue = queue;
+                    a.n_seg = (int)nseg;
+                    a.seg_len = len;
+                    grid = (int)std::min<long long>(slots, (long long)M * nseg);
+                    e = cudaMemsetAsync(queue, 0, sizeof(int32_t) * ((size_t)M + 1), st);
+                    if (e != cudaSuccess) return e;
+                }
+            }
+        }
+        kernel<<<grid, th, smem, st>>>(a);
         return cudaGetLastError();
     });
 }

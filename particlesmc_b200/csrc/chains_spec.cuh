@@ -38,6 +38,18 @@ constexpr int kSpecBatch = 56;                 // parked proposals (56 x 80 B ke
 constexpr int kSpecQCap = 256;                 // survivor queue entries per warp (beyond: unqueued fallback)
 constexpr int kPubBytes = 64;                  // published result of one trial
 
+// Build-time switches of the schedule (A/B numbers in DESIGN.md section 7):
+//   PMC_SPEC_ROTATE  the retiring warp and the proposal-generating warps rotate from round to round (warp w of every CTA
+//                    sits on SM sub-partition w % 4; measured +0.5 %).
+// Measured and dropped in round 2: minimum image / cutoff as predicated PTX (ptxas turns them back into selects, -1.4 %);
+// eight trials in flight at N = 1000 (6.6e8 vs 9.5e8 moves/s: longer rounds, more re-evaluated trials).
+#ifndef PMC_SPEC_ROTATE
+#define PMC_SPEC_ROTATE 1
+#endif
+#ifndef PMC_SPEC_NW_SMALL
+#define PMC_SPEC_NW_SMALL 4  // trials in flight per round for Atoms, fp64, N <= 1024
+#endif
+
 __device__ __forceinline__ void lds_u32x4(uint32_t a, uint32_t &v0, uint32_t &v1, uint32_t &v2, uint32_t &v3) {
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(a) : "memory");
 }
@@ -62,7 +74,7 @@ __host__ __device__ inline SpecLayout spec_layout(int dim, int Npad, bool full_p
     };
     f.x = take((mixed ? 4u : 8u) * dim * Npad);  // fp64 positions, or the 32-bit fixed-point state of PMC_MIXED
     f.sp = take(Npad);
-    f.pk = take(4u * Npad);  // packed 8-bit coordinates (common.cuh), word j = particle j
+    f.pk = take(4u * Npad);  // packed 8-bit coordinates (common.cuh), word pk_pos(j) = particle j
     f.q = take(2u * kSpecQCap * nw);
     f.cp = take(32u * PMC_MAX_SPECIES * PMC_MAX_SPECIES);
     f.rec = take((uint32_t)kRecBytes * kSpecBatch);
@@ -78,12 +90,15 @@ __host__ __device__ inline SpecLayout spec_layout(int dim, int Npad, bool full_p
     return f;
 }
 
-// particle index of the candidate behind bit b of a survivor mask
+// Candidate k of a lane is particle 32 * k + lane (consecutive particles sit in different lanes); its bit in the
+// survivor mask is KC - 1 - k.  The packed table is stored so that one LDS.128 per lane still fetches four candidates:
+// table word 128 * c + 4 * lane + e holds particle 32 * (4 c + e) + lane.
 template <int KC>
 __device__ __forceinline__ uint32_t cand_index(int b, int lane) {
-    const uint32_t k = (uint32_t)(KC - 1 - b);
-    return (k >> 2) * 128u + 4u * (uint32_t)lane + (k & 3u);
+    return ((uint32_t)(KC - 1 - b) << 5) + (uint32_t)lane;
 }
+// word of particle j in the packed table
+__device__ __forceinline__ uint32_t pk_pos(uint32_t j) { return (j & ~127u) | ((j & 31u) << 2) | ((j >> 5) & 3u); }
 
 // The packed candidates live in a shared-memory table that every warp streams through with LDS.128 (4 candidates per
 // load): keeping them in 32 registers per thread instead (96 registers, 5 CTAs per SM) measured slower than this
@@ -99,7 +114,7 @@ __device__ __forceinline__ uint32_t cand_index(int b, int lane) {
 // SWAPS = true adds DiscreteSwap trials (src/moves.jl:137-214): positions fixed, four local energies in one pass over
 // the survivors of two spheres; an accepted swap ends the round for later swaps (the species lists changed).
 template <int DIM, int MODEL, int NPAD, bool MIXED = false, bool MOL = false, int NW = 4, bool SWAPS = false>
-__global__ void __launch_bounds__(32 * NW, NPAD <= 1024 ? (MIXED ? 8 : (MOL ? 5 : 6)) : (NW == 4 ? 4 : 2)) k_chain_sweep_spec(const __grid_constant__ ChainArgs A) {
+__global__ void __launch_bounds__(32 * NW, NPAD <= 1024 ? (NW == 8 ? 3 : (MIXED ? 8 : (MOL ? 5 : 6))) : (NW == 4 ? 4 : 2)) k_chain_sweep_spec(const __grid_constant__ ChainArgs A) {
     constexpr int NT = 32 * NW;
     static_assert(!(MIXED && MOL) && !(MIXED && NW != 4), "PMC_MIXED is implemented for Atoms, N <= 1024");
     static_assert(!(SWAPS && (MIXED || MOL)), "DiscreteSwap pools: Atoms, fp64");
@@ -108,15 +123,49 @@ __global__ void __launch_bounds__(32 * NW, NPAD <= 1024 ? (MIXED ? 8 : (MOL ? 5 
     constexpr int NM = (KC + 31) / 32, KCW = KC < 32 ? KC : 32;  // mask words per lane, candidates per word
     static_assert(KC >= 4 && KC % 4 == 0 && (KC <= 32 || KC % 32 == 0) && NM <= 4, "candidates come four per LDS.128, 32 per mask word");
     constexpr int Npad = NPAD;
-    constexpr int kImgThread = 1, kCntThread = 2;  // lanes of warp 0 (the retiring warp)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int c = blockIdx.x;
     const int N = A.N, gNpad = A.Npad, ns = A.ns;
     constexpr bool kFullPar = !MIXED && (MOL || !(MODEL == PMC_MODEL_LJ || MODEL == PMC_MODEL_KG));
     const SpecLayout F = spec_layout(DIM, Npad, kFullPar, MIXED, NW, SWAPS);
     const uint32_t sb = (uint32_t)__cvta_generic_to_shared(smem_raw);
     const uint32_t nb8 = 8u * (uint32_t)Npad;  // byte stride between coordinate planes (fp64)
     constexpr uint32_t nb4 = 4u * (uint32_t)NPAD;  // ... of the fixed-point planes (MIXED)
+    const uint32_t tail = sb + F.pub + 2u * kPubBytes * NW;  // [0] retired count of the round, [4] work unit, [8] running energy
+    // survivor-mask bits of this lane that are particles (index < N): padding never reaches the fp64 pass
+    uint32_t vmask[NM];
+#pragma unroll
+    for (int mw = 0; mw < NM; mw++) {
+        vmask[mw] = 0u;
+#pragma unroll
+        for (int b = 0; b < KCW; b++)
+            if (cand_index<KCW>(b, lane) + 1024u * (uint32_t)mw < (uint32_t)N) vmask[mw] |= 1u << b;
+    }
+
+  // One CTA per chain (queue == nullptr), or persistent CTAs that pull (chain, segment) units from a global counter: with
+  // M chains on S resident CTA slots a plain launch runs ceil(M / S) waves and leaves the last one partly empty (4096
+  // chains on 888 slots: 4.61 -> 5 waves, 8 % of the launch); units of a fraction of the launch even that out.  The trial
+  // streams are counter-based, so cutting a launch into segments changes nothing (tests: split launches == one launch).
+  for (;;) {
+    int c = blockIdx.x, seg = 0;
+    long long seg_lo = 0, seg_hi = A.n_trials;
+    if (A.queue) {
+        __syncthreads();  // the previous unit is done with the shared state
+        if (tid == 0) sts_u32(tail + 4, (uint32_t)atomicAdd(A.queue, 1));
+        __syncthreads();
+        const int unit = (int)lds_u32(tail + 4);
+        if (unit >= A.n_chains * A.n_seg) break;
+        c = unit % A.n_chains;
+        seg = unit / A.n_chains;
+        seg_lo = (long long)seg * A.seg_len;
+        seg_hi = min(A.n_trials, seg_lo + A.seg_len);
+        if (seg > 0 && tid == 0) {
+            // the predecessor was handed out earlier, to a CTA that is running and waits for nothing but ITS predecessor
+            const volatile int32_t *done = A.queue + 1 + c;
+            while (*done < seg) __nanosleep(100);
+            __threadfence();
+        }
+        __syncthreads();
+    }
 
     // ---- load chain state -----------------------------------------------------------------------------
     const double L = A.box[c * 3], hL = 0.5 * L;
@@ -127,15 +176,15 @@ __global__ void __launch_bounds__(32 * NW, NPAD <= 1024 ? (MIXED ? 8 : (MOL ? 5 
         if constexpr (MIXED) {
             uint32_t *su = (uint32_t *)(smem_raw + F.x);
             for (int a = 0; a < DIM; a++)
-                for (int k = tid; k < Npad; k += NT) su[a * Npad + k] = k < gNpad ? to_fixed32(gx[a * gNpad + k], fscale) : 0u;
+                for (int k = tid; k < Npad; k += NT) su[a * Npad + k] = k < gNpad ? to_fixed32(__ldcg(gx + a * gNpad + k), fscale) : 0u;
         } else {
             double *sx = (double *)(smem_raw + F.x);
             for (int a = 0; a < DIM; a++)
-                for (int k = tid; k < Npad; k += NT) sx[a * Npad + k] = k < gNpad ? gx[a * gNpad + k] : 0.0;
+                for (int k = tid; k < Npad; k += NT) sx[a * Npad + k] = k < gNpad ? __ldcg(gx + a * gNpad + k) : 0.0;
         }
         uint8_t *ssp = smem_raw + F.sp;
         const uint8_t *gsp = A.sp + (size_t)c * gNpad;
-        for (int k = tid; k < Npad; k += NT) ssp[k] = k < gNpad ? gsp[k] : 0;
+        for (int k = tid; k < Npad; k += NT) ssp[k] = k < gNpad ? __ldcg(gsp + k) : 0;
         double *scp = (double *)(smem_raw + F.cp);
         if constexpr (kFullPar) {
             double *spar = (double *)(smem_raw + F.par);
@@ -168,9 +217,9 @@ __global__ void __launch_bounds__(32 * NW, NPAD <= 1024 ? (MIXED ? 8 : (MOL ? 5 
         if constexpr (SWAPS) {
             uint16_t *si_ = (uint16_t *)(smem_raw + F.spids);
             const uint16_t *gi = A.spids + (size_t)c * gNpad;
-            for (int k = tid; k < Npad; k += NT) si_[k] = k < gNpad ? gi[k] : 0;
+            for (int k = tid; k < Npad; k += NT) si_[k] = k < gNpad ? __ldcg(gi + k) : 0;
             int *sso = (int *)(smem_raw + F.spoff);
-            if (tid <= PMC_MAX_SPECIES) sso[tid] = A.spoff[c * (PMC_MAX_SPECIES + 1) + tid];
+            if (tid <= PMC_MAX_SPECIES) sso[tid] = __ldcg(A.spoff + c * (PMC_MAX_SPECIES + 1) + tid);
             if (tid == 0) {  // one conservative threshold over all species pairs (swap filter: no displacement)
                 double rc2 = 0.0;
                 for (int k = 0; k < ns * ns; k++) rc2 = fmax(rc2, A.par[k * PMC_NPAR + PMC_P_RCUT2]);
@@ -186,12 +235,12 @@ __global__ void __launch_bounds__(32 * NW, NPAD <= 1024 ? (MIXED ? 8 : (MOL ? 5 
     for (int j = tid; j < Npad; j += NT) {
         uint32_t u[3] = {0u, 0u, 0u};
 #pragma unroll
-        for (int a = 0; a < DIM; a++) u[a] = j < gNpad ? to_fixed32(gx[a * gNpad + j], fscale) : 0u;
-        ((uint32_t *)(smem_raw + F.pk))[j] = pack8(u[0], u[1], u[2]);
+        for (int a = 0; a < DIM; a++) u[a] = j < gNpad ? to_fixed32(__ldcg(gx + a * gNpad + j), fscale) : 0u;
+        ((uint32_t *)(smem_raw + F.pk))[pk_pos((uint32_t)j)] = pack8(u[0], u[1], u[2]);
     }
     const uint32_t pka = sb + F.pk + 16u * (uint32_t)lane;
     const double Tk = A.temp[c];
-    double E = A.energy[c];
+    if (tid == 0) sts_f64(tail + 8, __ldcg(A.energy + c));  // running energy[1]: lives in shared memory, the retiring warp rotates
     const uint32_t k0 = (uint32_t)A.seed, k1 = (uint32_t)(A.seed >> 32);
     const uint32_t gchain = (uint32_t)(A.chain_offset + c);
     int32_t *gimg = A.img + (size_t)c * DIM * gNpad;
@@ -199,8 +248,9 @@ __global__ void __launch_bounds__(32 * NW, NPAD <= 1024 ? (MIXED ? 8 : (MOL ? 5 
     uint32_t slot = 0;
     const bool dbg_out = A.acc_out != nullptr || A.dE_out != nullptr;
 
-    for (long long tb = 0; tb < A.n_trials; tb += kSpecBatch) {
-        const int nb = (int)min((long long)kSpecBatch, A.n_trials - tb);
+    uint32_t rnd = 0;  // rounds so far: selects the retiring warp
+    for (long long tb = seg_lo; tb < seg_hi; tb += kSpecBatch) {
+        const int nb = (int)min((long long)kSpecBatch, seg_hi - tb);
         __syncthreads();
         if (tid >= NT - 2 * PMC_MAX_MOVES) {  // fold the counters of the previous batch
             const int k = tid - (NT - 2 * PMC_MAX_MOVES);
@@ -209,8 +259,14 @@ __global__ void __launch_bounds__(32 * NW, NPAD <= 1024 ? (MIXED ? 8 : (MOL ? 5 
             c32[k] = 0u;
         }
         // ---- proposals of trials tb .. tb+nb-1, parked in shared memory (same stream as every other kernel) ----
-        if (tid < nb) {
-            const long long q = tb + tid;
+        // generated by two warps (ceil(batch / 32)); which two alternates from batch to batch (PMC_SPEC_ROTATE)
+#if PMC_SPEC_ROTATE
+        const int pidx = (((warp - (int)(((tb - seg_lo) / kSpecBatch) * ((kSpecBatch + 31) / 32))) & (NW - 1)) << 5) | lane;
+#else
+        const int pidx = tid;
+#endif
+        if (pidx < nb) {
+            const long long q = tb + pidx;
             pmc_trial tr;
             if (A.replay) {
                 tr = A.replay[(size_t)c * A.n_trials + q];
@@ -246,7 +302,7 @@ __global__ void __launch_bounds__(32 * NW, NPAD <= 1024 ? (MIXED ? 8 : (MOL ? 5 
                 if (A.trace) A.trace[(size_t)c * A.n_trials + q] = tr;
             }
             // record: f64 delta[3], f64 thr | s32 dint[3], s32 i | s32 m, pad[3] | u32 ~thr8[4]
-            unsigned char *rec = smem_raw + F.rec + (size_t)kRecBytes * tid;
+            unsigned char *rec = smem_raw + F.rec + (size_t)kRecBytes * pidx;
             double *rd = (double *)rec;
             int *ri = (int *)(rec + 32);
             uint32_t *rt = (uint32_t *)(rec + 64);
@@ -300,7 +356,7 @@ __global__ void __launch_bounds__(32 * NW, NPAD <= 1024 ? (MIXED ? 8 : (MOL ? 5 
                         const double xi0 = lds_f64(xia), xi1 = lds_f64(xia + nb8), xi2 = DIM == 3 ? lds_f64(xia + 2 * nb8) : 0.0;
                         const double xj0 = lds_f64(xja), xj1 = lds_f64(xja + nb8), xj2 = DIM == 3 ? lds_f64(xja + 2 * nb8) : 0.0;
                         const uint32_t si = lds_u8(sb + F.sp + iu), sj = lds_u8(sb + F.sp + ju);
-                        const uint32_t qi = lds_u32(sb + F.pk + 4u * iu), qj = lds_u32(sb + F.pk + 4u * ju);
+                        const uint32_t qi = lds_u32(sb + F.pk + 4u * pk_pos(iu)), qj = lds_u32(sb + F.pk + 4u * pk_pos(ju));
                         const int gthr = (int)lds_u32(soa + 4u * (PMC_MAX_SPECIES + 1));
                         constexpr int NCHUNK = KCW / 4, NCH = NCHUNK >= 4 ? 4 : NCHUNK, CG = NCHUNK / NCH;
                         uint32_t m[NM];
@@ -474,6 +530,11 @@ __global__ void __launch_bounds__(32 * NW, NPAD <= 1024 ? (MIXED ? 8 : (MOL ? 5 
                         uint32_t mm = mc[0];
 #pragma unroll
                         for (int h = 1; h < NCH; h++) mm = (mm << (4 * CG)) | mc[h];
+                        // padding slots and the moved particle itself (always inside its own sphere) leave here, so the
+                        // fp64 pass needs no validity test per survivor
+                        mm &= vmask[mw];
+                        if ((uint32_t)lane == ((uint32_t)i & 31u) && (uint32_t)mw == ((uint32_t)i >> 10))
+                            mm &= ~(1u << (KCW - 1 - (int)(((uint32_t)i >> 5) & 31u)));
                         m[mw] = mm;
                         mine += __popc(mm);
                     }
@@ -493,7 +554,7 @@ __global__ void __launch_bounds__(32 * NW, NPAD <= 1024 ? (MIXED ? 8 : (MOL ? 5 
                     }
                     // pair term of candidate j, branch-free (selects) so that two of them interleave in the unrolled loop
                     auto term = [&](uint32_t j) -> double {
-                        bool valid = j < (uint32_t)N && j != (uint32_t)i;
+                        bool valid = true;
                         if constexpr (MOL) {  // bonded partners are handled by the bond pass below
 #pragma unroll
                             for (int k = 0; k < PMC_MAX_BONDS; k++) valid = valid && j != bi[k];
@@ -511,7 +572,7 @@ __global__ void __launch_bounds__(32 * NW, NPAD <= 1024 ? (MIXED ? 8 : (MOL ? 5 
                             const float eo = pair_potential_f32<MODEL>(r2o, eps, sig2, shift, c0, c2, c4);
                             const float en = pair_potential_f32<MODEL>(r2n, eps, sig2, shift, c0, c2, c4);
                             const float d = (r2n <= rc2 ? en : 0.0f) - (r2o <= rc2 ? eo : 0.0f);
-                            return valid ? (double)d : 0.0;
+                            return (double)d;
                         }
                         const uint32_t ja = sb + F.x + 8u * j;
                         const double xj0 = lds_f64(ja), xj1 = lds_f64(ja + nb8);
@@ -539,7 +600,8 @@ __global__ void __launch_bounds__(32 * NW, NPAD <= 1024 ? (MIXED ? 8 : (MOL ? 5 
                             un = pair_potential<MODEL>(p, r2n);
                         }
                         const double d = (r2n <= rc2 ? un : 0.0) - (r2o <= rc2 ? uo : 0.0);
-                        return valid ? d : 0.0;
+                        if constexpr (MOL) return valid ? d : 0.0;
+                        return d;
                     };
                     if (total <= kSpecQCap) {
                         // compaction: each lane appends its survivors (ascending candidate index) at its scan offset
@@ -617,174 +679,141 @@ __global__ void __launch_bounds__(32 * NW, NPAD <= 1024 ? (MIXED ? 8 : (MOL ? 5 
                 }  // !is_swap
             }
             __syncthreads();
-            // ---- retire the round in trial order: warp 0 alone, the others wait at the second barrier --------------
-            if (warp == 0) {
-                int ndone = 0;
-                bool swap_committed = false;  // SWAPS: an accepted swap changed the species lists -> later swaps of the round wait
-                auto commit_swap = [&](uint32_t pw, uint32_t iw, uint32_t jw) {  // update_species_list! (src/moves.jl:175-179)
-                    const uint32_t si = lds_u8(sb + F.sp + iw), sj = lds_u8(sb + F.sp + jw);
-                    const uint32_t oi = lds_u32(sb + F.spoff + 4u * si), oj = lds_u32(sb + F.spoff + 4u * sj);
-                    const uint32_t ni = lds_u32(sb + F.spoff + 4u * si + 4u) - oi, nj = lds_u32(sb + F.spoff + 4u * sj + 4u) - oj;
-                    // where i and j sit in their species lists: a warp search, paid only by accepted swaps
-                    auto find = [&](uint32_t off, uint32_t n, uint32_t who) -> uint32_t {
-                        uint32_t pos = 0;
-                        for (uint32_t b0 = 0; b0 < n; b0 += 32) {
-                            const uint32_t k = b0 + (uint32_t)lane;
-                            const bool hit = k < n && lds_u16(sb + F.spids + 2u * (off + k)) == who;
-                            const unsigned bal = __ballot_sync(0xffffffffu, hit);
-                            if (bal) pos = b0 + (uint32_t)__ffs((int)bal) - 1u;
+            // ---- retire the round in trial order: ONE warp, the others wait at the second barrier ------------------
+#if PMC_SPEC_ROTATE
+            const int rw = (int)(rnd & (uint32_t)(NW - 1));
+#else
+            constexpr int rw = 0;
+#endif
+            rnd++;
+            if (warp == rw) {
+                // The retiring warp works on all trials of the round at once: G = 32 / NW lanes per trial.  Lane (w, v) tests
+                // trial w against the EARLIER trial v (accepted, old or new position inside w's filter sphere -- the very
+                // test that defines w's survivors); one ballot gives the first trial that does not stand, i.e. the number
+                // retired.  Accepted standing trials of one round touch different particles outside each other's spheres,
+                // so their commits are independent stores issued side by side by the lanes of their groups; only the
+                // running energy is summed in trial order (one lane).  The round's critical path is one dependent load /
+                // test / ballot / store sequence instead of NW of them back to back.
+                constexpr int G = 32 / NW;
+                const int w = lane / G, sub = lane % G;
+                const uint32_t pw = pa + (uint32_t)kPubBytes * (uint32_t)w;
+                uint32_t umq, fthr, qo, qn, iw, fl, wr, mv;
+                lds_u32x4(pw + 32, umq, fthr, qo, qn);
+                lds_u32x4(pw + 48, iw, fl, wr, mv);
+                const bool live = w < nspec;
+                const bool wswap = SWAPS && (fl & 2u) != 0u;
+                int conflict = 0;
+                for (int v = sub; v < w; v += G) {
+                    const uint32_t pv = pa + (uint32_t)kPubBytes * (uint32_t)v;
+                    uint32_t a_, b_, qov, qnv, iv, flv, c_, d_;
+                    lds_u32x4(pv + 32, a_, b_, qov, qnv);
+                    lds_u32x4(pv + 48, iv, flv, c_, d_);
+                    if (live && (flv & 1u)) {
+                        const uint32_t ta = __vabsdiffu4(umq, qov), tb_ = __vabsdiffu4(umq, qnv);
+                        conflict |= __dp4a((int)ta, (int)ta, (int)fthr) | __dp4a((int)tb_, (int)tb_, (int)fthr);
+                        if (wswap) {  // second sphere of a swap: around its particle j; the species lists changed under it
+                            const uint32_t tc = __vabsdiffu4(qn, qov), td = __vabsdiffu4(qn, qnv);
+                            conflict |= __dp4a((int)tc, (int)tc, (int)fthr) | __dp4a((int)td, (int)td, (int)fthr);
+                            if (flv & 2u) conflict = -1;
                         }
-                        return pos;
-                    };
-                    const uint32_t hi = find(oi, ni, iw), hj = find(oj, nj, jw);
-                    __syncwarp();
-                    asm volatile("st.shared.u8 [%0], %1;" ::"r"(sb + F.sp + iw), "r"(sj) : "memory");
-                    asm volatile("st.shared.u8 [%0], %1;" ::"r"(sb + F.sp + jw), "r"(si) : "memory");
-                    sts_u16(sb + F.spids + 2u * (oi + hi), jw);
-                    sts_u16(sb + F.spids + 2u * (oj + hj), iw);
-                    __syncwarp();
-                    E += lds_f64(pw);
-                    swap_committed = true;
-                };
-                if constexpr (NW == 4) {
-                    uint32_t cqo[NW], cqn[NW];  // packed old / new position of trials accepted in this round
-                    uint32_t cmask = 0;
+                        if constexpr (MOL) {
+                            // a bonded partner that moved changes the bond term even from outside the pair cutoff sphere
+                            // (FENE bonds reach r0 > rc): src/molecules.jl:160-176
 #pragma unroll
-                    for (int w = 0; w < NW; w++) {
-                        if (w < nspec && ndone == w) {  // uniform
-                            const uint32_t pw = pa + (uint32_t)kPubBytes * (uint32_t)w;
-                            uint32_t umq, fthr, qo, qn;
-                            uint32_t iw, fl, wr, mv;
-                            lds_u32x4(pw + 48, iw, fl, wr, mv);
-                            const bool wswap = SWAPS && (fl & 2u) != 0u;
-                            int conflict = 0;
-                            if (w > 0 && cmask != 0u) {
-                                lds_u32x4(pw + 32, umq, fthr, qo, qn);
-#pragma unroll
-                                for (int v = 0; v < w; v++) {
-                                    if (cmask & (1u << v)) {
-                                        const uint32_t ta = __vabsdiffu4(umq, cqo[v]), tb_ = __vabsdiffu4(umq, cqn[v]);
-                                        conflict |= __dp4a((int)ta, (int)ta, (int)fthr) | __dp4a((int)tb_, (int)tb_, (int)fthr);
-                                        if (wswap) {  // second sphere of a swap: around its particle j
-                                            const uint32_t tc = __vabsdiffu4(qn, cqo[v]), td = __vabsdiffu4(qn, cqn[v]);
-                                            conflict |= __dp4a((int)tc, (int)tc, (int)fthr) | __dp4a((int)td, (int)td, (int)fthr);
-                                        }
-                                    }
-                                }
-                                if (wswap && swap_committed) conflict = -1;
-                            }
-                            if (conflict >= 0) {  // stands: retire it
-                                ndone = w + 1;
-                                const bool acc = (fl & 1u) != 0u;
-                                if (acc) {
-                                    if (w == 0 || cmask == 0u) lds_u32x4(pw + 32, umq, fthr, qo, qn);
-                                    cmask |= 1u << w;
-                                    cqo[w] = qo;
-                                    cqn[w] = qn;
-                                    if (wswap) {
-                                        commit_swap(pw, iw, wr);
-                                    } else {
-                                        if constexpr (MIXED) {
-                                            uint32_t n0, n1, n2, pad_;
-                                            lds_u32x4(pw + 16, n0, n1, n2, pad_);
-                                            const uint32_t ua = sb + F.x + 4u * iw;
-                                            sts_u32(ua, n0);
-                                            sts_u32(ua + nb4, n1);
-                                            if constexpr (DIM == 3) sts_u32(ua + 2 * nb4, n2);
-                                            E += lds_f64(pw);
-                                        } else {
-                                            double dE, x0, x1, x2;
-                                            lds_f64x2(pw, dE, x0);
-                                            lds_f64x2(pw + 16, x1, x2);
-                                            const uint32_t xa = sb + F.x + 8u * iw;
-                                            sts_f64(xa, x0);
-                                            sts_f64(xa + nb8, x1);
-                                            if constexpr (DIM == 3) sts_f64(xa + 2 * nb8, x2);
-                                            E += dE;
-                                        }
-                                        sts_u32(sb + F.pk + 4u * iw, qn);
-                                        if (tid == kImgThread && wr != 0x15u) {  // some coordinate wrapped around the box
-                                            const int w0 = (int)(wr & 3u) - 1, w1 = (int)((wr >> 2) & 3u) - 1, w2 = (int)((wr >> 4) & 3u) - 1;
-                                            if (w0) atomicAdd(&gimg[iw], w0);
-                                            if (w1) atomicAdd(&gimg[gNpad + iw], w1);
-                                            if (DIM == 3 && w2) atomicAdd(&gimg[2 * gNpad + iw], w2);
-                                        }
-                                    }
-                                }
-                                if (tid == kCntThread) {
-                                    uint32_t *c32 = (uint32_t *)(smem_raw + F.cnt32);
-                                    atomicAdd(&c32[mv], 1u);
-                                    if (acc) atomicAdd(&c32[PMC_MAX_MOVES + mv], 1u);
-                                    if (dbg_out) {
-                                        if (A.acc_out) A.acc_out[(size_t)c * A.n_trials + tb + cur + w] = acc ? 1 : 0;
-                                        if (A.dE_out) A.dE_out[(size_t)c * A.n_trials + tb + cur + w] = lds_f64(pw);
-                                    }
-                                }
-                            }
-                        }
-                    }
-                } else {
-                    // the same retirement, rolled: the packed positions of the accepted trials are read back from the
-                    // published entries instead of living in registers
-                    uint32_t cmask = 0;
-                    for (int w = 0; w < nspec; w++) {
-                        const uint32_t pw = pa + (uint32_t)kPubBytes * (uint32_t)w;
-                        uint32_t umq, fthr, qo, qn;
-                        lds_u32x4(pw + 32, umq, fthr, qo, qn);
-                        uint32_t iw, fl, wr, mv;
-                        lds_u32x4(pw + 48, iw, fl, wr, mv);
-                        const bool wswap = SWAPS && (fl & 2u) != 0u;
-                        int conflict = 0;
-                        for (uint32_t mm = cmask; mm; mm &= mm - 1u) {
-                            const uint32_t pv = pa + (uint32_t)kPubBytes * (uint32_t)(__ffs((int)mm) - 1);
-                            const uint32_t p0 = lds_u32(pv + 40), p1 = lds_u32(pv + 44);
-                            const uint32_t ta = __vabsdiffu4(umq, p0), tb_ = __vabsdiffu4(umq, p1);
-                            conflict |= __dp4a((int)ta, (int)ta, (int)fthr) | __dp4a((int)tb_, (int)tb_, (int)fthr);
-                            if (wswap) {
-                                const uint32_t tc = __vabsdiffu4(qn, p0), td = __vabsdiffu4(qn, p1);
-                                conflict |= __dp4a((int)tc, (int)tc, (int)fthr) | __dp4a((int)td, (int)td, (int)fthr);
-                            }
-                        }
-                        if (wswap && swap_committed) conflict = -1;
-                        if (conflict < 0) break;
-                        ndone = w + 1;
-                        const bool acc = (fl & 1u) != 0u;
-                        if (acc && wswap) {
-                            cmask |= 1u << w;
-                            commit_swap(pw, iw, wr);
-                        } else if (acc) {
-                            cmask |= 1u << w;
-                            double dE, x0, x1, x2;
-                            lds_f64x2(pw, dE, x0);
-                            lds_f64x2(pw + 16, x1, x2);
-                            const uint32_t xa = sb + F.x + 8u * iw;
-                            sts_f64(xa, x0);
-                            sts_f64(xa + nb8, x1);
-                            if constexpr (DIM == 3) sts_f64(xa + 2 * nb8, x2);
-                            E += dE;
-                            sts_u32(sb + F.pk + 4u * iw, qn);
-                            if (tid == kImgThread && wr != 0x15u) {
-                                const int w0 = (int)(wr & 3u) - 1, w1 = (int)((wr >> 2) & 3u) - 1, w2 = (int)((wr >> 4) & 3u) - 1;
-                                if (w0) atomicAdd(&gimg[iw], w0);
-                                if (w1) atomicAdd(&gimg[gNpad + iw], w1);
-                                if (DIM == 3 && w2) atomicAdd(&gimg[2 * gNpad + iw], w2);
-                            }
-                        }
-                        if (tid == kCntThread) {
-                            uint32_t *c32 = (uint32_t *)(smem_raw + F.cnt32);
-                            atomicAdd(&c32[mv], 1u);
-                            if (acc) atomicAdd(&c32[PMC_MAX_MOVES + mv], 1u);
-                            if (dbg_out) {
-                                if (A.acc_out) A.acc_out[(size_t)c * A.n_trials + tb + cur + w] = acc ? 1 : 0;
-                                if (A.dE_out) A.dE_out[(size_t)c * A.n_trials + tb + cur + w] = lds_f64(pw);
-                            }
+                            for (int k = 0; k < PMC_MAX_BONDS; k++)
+                                if ((uint32_t)__ldg(A.bonds + (size_t)iw * PMC_MAX_BONDS + k) == iv) conflict = -1;
                         }
                     }
                 }
-                if (lane == 0) sts_u32(sb + F.pub + 2u * kPubBytes * NW, (uint32_t)ndone);
+                const unsigned cb = __ballot_sync(0xffffffffu, live && conflict < 0);
+                const int ndone = cb ? min(nspec, (__ffs((int)cb) - 1) / G) : nspec;
+                const bool mine = live && w < ndone;
+                const bool acc = mine && (fl & 1u) != 0u;
+                const unsigned accb = __ballot_sync(0xffffffffu, acc && sub == 0);
+                if (acc && !wswap) {
+                    if constexpr (MIXED) {
+                        if (sub == 0) {
+                            uint32_t n0, n1, n2, pad_;
+                            lds_u32x4(pw + 16, n0, n1, n2, pad_);
+                            const uint32_t ua = sb + F.x + 4u * iw;
+                            sts_u32(ua, n0);
+                            sts_u32(ua + nb4, n1);
+                            if constexpr (DIM == 3) sts_u32(ua + 2 * nb4, n2);
+                        }
+                    } else {
+                        const uint32_t xa = sb + F.x + 8u * iw;
+                        if (sub == 0) {
+                            double dE, x0;
+                            lds_f64x2(pw, dE, x0);
+                            sts_f64(xa, x0);
+                        }
+                        if (sub == 1) {
+                            double x1, x2;
+                            lds_f64x2(pw + 16, x1, x2);
+                            sts_f64(xa + nb8, x1);
+                            if constexpr (DIM == 3) sts_f64(xa + 2 * nb8, x2);
+                        }
+                    }
+                    if (sub == 2) sts_u32(sb + F.pk + 4u * pk_pos(iw), qn);
+                    if (sub == 3 && wr != 0x15u) {  // some coordinate wrapped around the box
+                        const int w0 = (int)(wr & 3u) - 1, w1 = (int)((wr >> 2) & 3u) - 1, w2 = (int)((wr >> 4) & 3u) - 1;
+                        if (w0) atomicAdd(&gimg[iw], w0);
+                        if (w1) atomicAdd(&gimg[gNpad + iw], w1);
+                        if (DIM == 3 && w2) atomicAdd(&gimg[2 * gNpad + iw], w2);
+                    }
+                }
+                if (mine && sub == (4 % G)) {
+                    uint32_t *c32 = (uint32_t *)(smem_raw + F.cnt32);
+                    atomicAdd(&c32[mv], 1u);
+                    if (acc) atomicAdd(&c32[PMC_MAX_MOVES + mv], 1u);
+                    if (dbg_out) {
+                        if (A.acc_out) A.acc_out[(size_t)c * A.n_trials + tb + cur + w] = acc ? 1 : 0;
+                        if (A.dE_out) A.dE_out[(size_t)c * A.n_trials + tb + cur + w] = lds_f64(pw);
+                    }
+                }
+                if (lane == 0) {  // energy[1] += dE in trial order (src/moves.jl:11-20)
+                    double E = lds_f64(tail + 8);
+#pragma unroll
+                    for (int v = 0; v < NW; v++)
+                        if (accb & (1u << (G * v))) E += lds_f64(pa + (uint32_t)kPubBytes * (uint32_t)v);
+                    sts_f64(tail + 8, E);
+                    sts_u32(tail, (uint32_t)ndone);
+                }
+                if constexpr (SWAPS) {
+                    // accepted swaps: update_species_list! (src/moves.jl:175-179), one at a time -- finding i and j in
+                    // their species lists is a search by the whole warp, paid only by accepted swaps
+                    unsigned sw = __ballot_sync(0xffffffffu, acc && wswap && sub == 0);
+                    while (sw) {
+                        const int src = __ffs((int)sw) - 1;
+                        sw &= sw - 1u;
+                        const uint32_t is_ = __shfl_sync(0xffffffffu, iw, src), js_ = __shfl_sync(0xffffffffu, wr, src);
+                        const uint32_t si = lds_u8(sb + F.sp + is_), sj = lds_u8(sb + F.sp + js_);
+                        const uint32_t oi = lds_u32(sb + F.spoff + 4u * si), oj = lds_u32(sb + F.spoff + 4u * sj);
+                        const uint32_t ni = lds_u32(sb + F.spoff + 4u * si + 4u) - oi, nj = lds_u32(sb + F.spoff + 4u * sj + 4u) - oj;
+                        auto find = [&](uint32_t off, uint32_t n, uint32_t who) -> uint32_t {
+                            uint32_t pos = 0;
+                            for (uint32_t b0 = 0; b0 < n; b0 += 32) {
+                                const uint32_t k = b0 + (uint32_t)lane;
+                                const bool hit = k < n && lds_u16(sb + F.spids + 2u * (off + k)) == who;
+                                const unsigned bal = __ballot_sync(0xffffffffu, hit);
+                                if (bal) pos = b0 + (uint32_t)__ffs((int)bal) - 1u;
+                            }
+                            return pos;
+                        };
+                        const uint32_t hi = find(oi, ni, is_), hj = find(oj, nj, js_);
+                        __syncwarp();
+                        if (lane == 0) {
+                            asm volatile("st.shared.u8 [%0], %1;" ::"r"(sb + F.sp + is_), "r"(sj) : "memory");
+                            asm volatile("st.shared.u8 [%0], %1;" ::"r"(sb + F.sp + js_), "r"(si) : "memory");
+                            sts_u16(sb + F.spids + 2u * (oi + hi), js_);
+                            sts_u16(sb + F.spids + 2u * (oj + hj), is_);
+                        }
+                        __syncwarp();
+                    }
+                }
             }
             __syncthreads();
-            cur += (int)lds_u32(sb + F.pub + 2u * kPubBytes * NW);
+            cur += (int)lds_u32(tail);
             slot ^= 1u;
         }
     }
@@ -817,12 +846,17 @@ __global__ void __launch_bounds__(32 * NW, NPAD <= 1024 ? (MIXED ? 8 : (MOL ? 5 
         }
         const unsigned long long *scnt = (const unsigned long long *)(smem_raw + F.cnt);
         const uint32_t *c32 = (const uint32_t *)(smem_raw + F.cnt32);
-        if (tid == 0) A.energy[c] = E;
+        if (tid == 0) A.energy[c] = lds_f64(tail + 8);
         if (tid < A.n_moves) {
-            A.calls[(size_t)c * PMC_MAX_MOVES + tid] += scnt[tid] + c32[tid];
-            A.accepted[(size_t)c * PMC_MAX_MOVES + tid] += scnt[PMC_MAX_MOVES + tid] + c32[PMC_MAX_MOVES + tid];
+            atomicAdd(A.calls + (size_t)c * PMC_MAX_MOVES + tid, scnt[tid] + c32[tid]);
+            atomicAdd(A.accepted + (size_t)c * PMC_MAX_MOVES + tid, scnt[PMC_MAX_MOVES + tid] + c32[PMC_MAX_MOVES + tid]);
         }
     }
+    if (!A.queue) break;
+    __threadfence();  // this segment's state is visible before its completion is
+    __syncthreads();
+    if (tid == 0) *(volatile int32_t *)(A.queue + 1 + c) = seg + 1;
+  }
 }
 
 // ==================================================================================================
@@ -876,7 +910,7 @@ __global__ void __launch_bounds__(kSpecThreads, 5) k_chain_energy_fast(const __g
             uint32_t u[3] = {0u, 0u, 0u};
 #pragma unroll
             for (int a = 0; a < DIM; a++) u[a] = j < gNpad ? to_fixed32(gx[a * gNpad + j], fscale) : 0u;
-            ((uint32_t *)(smem_raw + F.pk))[j] = pack8(u[0], u[1], u[2]);
+            ((uint32_t *)(smem_raw + F.pk))[pk_pos((uint32_t)j)] = pack8(u[0], u[1], u[2]);
         }
         double *scp = (double *)(smem_raw + F.cp);
         if constexpr (kFullPar) {
@@ -903,7 +937,7 @@ __global__ void __launch_bounds__(kSpecThreads, 5) k_chain_energy_fast(const __g
         const uint32_t xa = sb + F.x + 8u * (uint32_t)i;
         const double x0 = lds_f64(xa), x1 = lds_f64(xa + nb8), x2 = (DIM == 3) ? lds_f64(xa + 2 * nb8) : 0.0;
         const uint32_t si = lds_u8(sb + F.sp + (uint32_t)i);
-        const uint32_t uq = lds_u32(sb + F.pk + 4u * (uint32_t)i);
+        const uint32_t uq = lds_u32(sb + F.pk + 4u * pk_pos((uint32_t)i));
         const int fthr = (int)lds_u32(sb + F.thr + 4u * si);
         constexpr int NCHUNK = KC / 4, NCH = NCHUNK >= 4 ? 4 : NCHUNK, CG = NCHUNK / NCH;
         uint32_t mc[NCH];
