@@ -15,6 +15,7 @@
 // reference is therefore statistical for trajectories and exact (1e-12) for energies.
 #include "box.cuh"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -58,6 +59,10 @@ struct Geom {
     double shift[3];  // grid origin of this sweep, in [0, cs)
 };
 
+// Flag block of a rank (inside the IPC-shared allocation): peer r announces in MY block that it finished the sweep /
+// the cell rebuild of stamp s.  Plain 32-bit stores over NVLink, each behind a system-scope fence.
+constexpr int kFlagSwept = 0, kFlagRebuilt = 8, kFlagWords = 64;
+
 struct BoxArgs {
     Geom g;
     int N, ns, cap;
@@ -65,11 +70,16 @@ struct BoxArgs {
     double *x;     // [dim][N] wrapped
     int32_t *img;  // [dim][N]
     uint8_t *sp;   // [N]
-    // cell-sorted state of the current grid
-    double *xs;       // [dim][N]
-    uint8_t *sps;     // [N]
-    int32_t *ids;     // [N] particle id of each sorted slot
-    int32_t *start;   // [ncell+1]
+    // cell-sorted state of the current grid.  Slots are reserved per x-PLANE of cells (plane_cap each), so the slot of
+    // (cell, k) is the same on every rank that keeps that plane without any rank having to bin the whole box.
+    int plane_cap;
+    int plane_lo, plane_n;  // this rank keeps cell lists for planes plane_lo .. plane_lo + plane_n - 1 (mod nc[0])
+    double *rs;             // [dim][nslot] coordinates INSIDE the particle's own cell, [0, cs)
+    uint32_t *qs;           // [nslot] the same as packed bytes in units of cs / 64 (prefilter, common.cuh)
+    uint8_t *sps;           // [nslot]
+    int32_t *ids;           // [nslot] particle id of each sorted slot
+    int32_t *start;         // [ncell] first slot of a cell
+    int32_t *count;         // [ncell]
     const double *par;
     double T;
     float sigma;
@@ -79,17 +89,53 @@ struct BoxArgs {
     double *cellE;            // [ncell] sum of accepted dE (sweep) or sum of local energies (energy)
     uint32_t *cell_acc;       // [ncell]
     double *eloc;             // [N] (energy kernel)
-    int *overflow;
-    // multi-GPU (replicated state): this rank sweeps active cells [cta_offset, cta_offset + gridDim.x) of the colour
-    // and pushes every accepted move into the peers' replicas with plain stores over NVLink peer memory
-    int cta_offset;
-    int n_peers;
+    int *overflow;  // 1: a stencil exceeds `cap`, 2: a plane exceeds plane_cap
+    int *error;     // 3: a wait on another GPU timed out
+    // dataflow of one sweep: persistent CTAs pull (phase, cell) units from work[0]; a cell starts when the neighbour
+    // cells of EARLIER phases carry this sweep's stamp in done[] -- no barrier between the colour phases
+    uint32_t stamp;
+    uint32_t *done;   // [ncell]
+    int *work;        // [0] next unit, [1] finished units
+    int cell_lo, cell_n;  // this rank's share of every colour: active cells [cell_lo, cell_lo + cell_n)
+    int order[8];         // colour processed in phase k
+    int phase_of[8];      // inverse
+    // multi-GPU: every rank holds the canonical state; cell lists only for its planes.  Accepted moves are stored
+    // straight into the peers' arrays over NVLink peer memory (canonical state: every peer; sorted copy and done[]:
+    // the peers that keep the plane)
+    int rank, n_peers;
+    volatile uint32_t *flags;  // my flag block
+    int peer_rank[PMC_MAX_PEERS];
+    int peer_plane_lo[PMC_MAX_PEERS], peer_plane_n[PMC_MAX_PEERS];
     double *peer_x[PMC_MAX_PEERS];
-    double *peer_xs[PMC_MAX_PEERS];
+    double *peer_rs[PMC_MAX_PEERS];
+    uint32_t *peer_qs[PMC_MAX_PEERS];
     int32_t *peer_img[PMC_MAX_PEERS];
     double *peer_cellE[PMC_MAX_PEERS];
     uint32_t *peer_cacc[PMC_MAX_PEERS];
+    uint32_t *peer_done[PMC_MAX_PEERS];
+    uint32_t *peer_flags[PMC_MAX_PEERS];
 };
+
+// Bounded wait on a 32-bit word another agent (CTA or GPU) will set: never hangs the device -- a peer that does not
+// arrive within ~20 s raises the error flag and the kernel runs on (the host reports PMC_ERR_CUDA at the next sync).
+__device__ __forceinline__ bool wait_for(const volatile uint32_t *p, uint32_t want, int *error, bool at_least) {
+    unsigned long long t0 = 0;
+    for (unsigned spins = 0;; spins++) {
+        const uint32_t v = *p;
+        if (at_least ? (int32_t)(v - want) >= 0 : v == want) return true;
+        if (*(volatile int *)error == 3) return false;
+        if ((spins & 1023u) == 1023u) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (t0 == 0) t0 = t;
+            if (t - t0 > 20000000000ull) {
+                atomicExch(error, 3);
+                return false;
+            }
+        }
+        if (spins > 64) __nanosleep(200);
+    }
+}
 
 // Cell coordinate and in-cell coordinate of a wrapped position under grid origin s.
 __device__ __forceinline__ int cell_of(double x, double s, double L, double cs, int n) {
@@ -103,6 +149,11 @@ __device__ __forceinline__ double in_frame(double x, double s, double L, double 
     if (y < 0.0) y += L;
     return y - (double)c * cs;
 }
+// byte of an in-cell coordinate: units of cs / 64, [0, 63]
+__device__ __forceinline__ uint32_t cell_byte(double r, double inv_unit) {
+    int q = (int)floor(r * inv_unit);
+    return (uint32_t)(q < 0 ? 0 : (q > 63 ? 63 : q));
+}
 
 template <int DIM>
 __device__ __forceinline__ int lin_cell(const int (&c)[3], const int (&nc)[3]) {  // last axis fastest (neighbours.jl:79-88)
@@ -110,6 +161,11 @@ __device__ __forceinline__ int lin_cell(const int (&c)[3], const int (&nc)[3]) {
     l = l * nc[1] + c[1];
     if constexpr (DIM == 3) l = l * nc[2] + c[2];
     return l;
+}
+__device__ __forceinline__ bool plane_kept(int px, int lo, int n, int nx) {
+    int d = px - lo;
+    if (d < 0) d += nx;
+    return d < n;
 }
 
 // ---- K0: ingest / egress -------------------------------------------------------------------------
@@ -142,135 +198,162 @@ __global__ void k_box_egress(const double *__restrict__ x, const int32_t *__rest
 }
 
 // ---- K1: cell list by sorting ----------------------------------------------------------------------
+// Replaces build_neighbour_list! (src/neighbours.jl:251-270).  A rank bins only the particles whose x-plane of cells
+// it keeps (all planes on one GPU); slots are reserved per plane (plane_cap), so the layout of a plane is the same on
+// every rank that keeps it.  With peers, the first kernel waits until every rank has finished the previous sweep (their
+// pushes into the canonical state have landed), the last one announces the finished rebuild.
 template <int DIM>
-__global__ void k_box_count(const double *__restrict__ x, int N, Geom g, int32_t *cid, int32_t *count) {
+__global__ void k_box_count(const __grid_constant__ BoxArgs A, int32_t *cid, uint32_t wait_stamp) {
+    if (A.n_peers && wait_stamp) {
+        if (threadIdx.x < A.n_peers) wait_for(A.flags + kFlagSwept + A.peer_rank[threadIdx.x], wait_stamp, A.error, true);
+        __syncthreads();
+    }
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
+    if (i >= A.N) return;
     int c[3] = {0, 0, 0};
+    c[0] = cell_of(__ldcg(A.x + i), A.g.shift[0], A.g.L[0], A.g.cs[0], A.g.nc[0]);
+    if (!plane_kept(c[0], A.plane_lo, A.plane_n, A.g.nc[0])) {
+        cid[i] = -1;
+        return;
+    }
 #pragma unroll
-    for (int a = 0; a < DIM; a++) c[a] = cell_of(x[(size_t)a * N + i], g.shift[a], g.L[a], g.cs[a], g.nc[a]);
-    const int l = lin_cell<DIM>(c, g.nc);
+    for (int a = 1; a < DIM; a++) c[a] = cell_of(__ldcg(A.x + (size_t)a * A.N + i), A.g.shift[a], A.g.L[a], A.g.cs[a], A.g.nc[a]);
+    const int l = lin_cell<DIM>(c, A.g.nc);
     cid[i] = l;
-    atomicAdd(&count[l], 1);
+    atomicAdd(&A.count[l], 1);
 }
 
-// exclusive prefix sum of count[0..n) into start[0..n] in two small launches:
-//   k_box_scan_local : every CTA scans its 1024 coalesced entries, writes the CTA-local exclusive prefix and its total
-//   k_box_scan_apply : every CTA adds the sum of the totals of the CTAs before it (<= a few dozen values)
-__global__ void k_box_scan_local(const int32_t *__restrict__ count, int32_t *start, int32_t *blocksum, int n) {
+// one CTA per kept plane: exclusive prefix sum of the plane's cell counts -> start[], cursor[] = 0
+__global__ void __launch_bounds__(1024) k_box_scan_plane(const __grid_constant__ BoxArgs A, int32_t *cursor) {
     __shared__ int s_warp[32];
+    __shared__ int s_carry;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int k = blockIdx.x * blockDim.x + tid;
-    const int v = k < n ? count[k] : 0;
-    int incl = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
-    }
-    if (lane == 31) s_warp[warp] = incl;
+    int px = A.plane_lo + blockIdx.x;
+    if (px >= A.g.nc[0]) px -= A.g.nc[0];
+    const int cpp = A.g.ncell / A.g.nc[0];
+    const int c0 = px * cpp;
+    if (tid == 0) s_carry = 0;
     __syncthreads();
-    if (warp == 0) {
-        int w = s_warp[lane];
+    for (int base = 0; base < cpp; base += 1024) {
+        const int k = base + tid;
+        const int v = k < cpp ? A.count[c0 + k] : 0;
+        int incl = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, w, o);
-            if (lane >= o) w += t;
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
         }
-        s_warp[lane] = w;
-    }
-    __syncthreads();
-    if (k < n) start[k] = (warp ? s_warp[warp - 1] : 0) + incl - v;
-    if (tid == 0) blocksum[blockIdx.x] = s_warp[31];
-}
-
-__global__ void k_box_scan_apply(int32_t *start, int32_t *cursor, const int32_t *__restrict__ blocksum, int n) {
-    __shared__ int s_off, s_tot;
-    if (threadIdx.x < 32) {
-        int off = 0, tot = 0;
-        for (int b = threadIdx.x; b < (int)gridDim.x; b += 32) {
-            const int v = blocksum[b];
-            tot += v;
-            if (b < (int)blockIdx.x) off += v;
-        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int w = s_warp[lane];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            off += __shfl_xor_sync(0xffffffffu, off, o);
-            tot += __shfl_xor_sync(0xffffffffu, tot, o);
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += t;
+            }
+            s_warp[lane] = w;
         }
-        if (threadIdx.x == 0) {
-            s_off = off;
-            s_tot = tot;
+        __syncthreads();
+        const int carry = s_carry;
+        if (k < cpp) {
+            A.start[c0 + k] = px * A.plane_cap + carry + (warp ? s_warp[warp - 1] : 0) + incl - v;
+            cursor[c0 + k] = 0;
         }
+        __syncthreads();
+        if (tid == 0) s_carry = carry + s_warp[31];
+        __syncthreads();
     }
-    __syncthreads();
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < n) {
-        start[k] += s_off;
-        cursor[k] = 0;
-    }
-    if (k == 0) start[n] = s_tot;
+    if (tid == 0 && s_carry > A.plane_cap) atomicExch(A.overflow, 2);
 }
 
 __global__ void k_box_scatter(const int32_t *__restrict__ cid, const int32_t *__restrict__ start, int32_t *cursor, int N,
-                              int32_t *ids) {
+                              int32_t *ids, const int *overflow) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
+    if (i >= N || *overflow) return;
     const int c = cid[i];
-    ids[start[c] + atomicAdd(&cursor[c], 1)] = i;
+    if (c >= 0) ids[start[c] + atomicAdd(&cursor[c], 1)] = i;
 }
 
-// canonical order inside each cell (descending particle id) + gather into the sorted SoA: one warp per cell,
-// rank sort through shuffles (cells hold ~20 particles); cells with more than 32 particles fall back to a serial
-// insertion sort by lane 0
+// canonical order inside each cell (descending particle id = the order head insertion produces, neighbours.jl:257-268)
+// + gather into the sorted arrays as IN-CELL coordinates (fp64 and packed bytes): one warp per cell, rank sort
+// through shuffles (cells hold ~20 particles); cells with more than 32 particles fall back to a serial insertion sort
 template <int DIM>
-__global__ void k_box_finalize(const int32_t *__restrict__ start, int32_t *ids, int ncell, int N,
-                               const double *__restrict__ x, const uint8_t *__restrict__ sp, double *xs, uint8_t *sps) {
+__global__ void k_box_finalize(const __grid_constant__ BoxArgs A, int *ticket, uint32_t announce_stamp) {
     const int lane = threadIdx.x & 31;
-    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (c >= ncell) return;
-    const int b = start[c], e = start[c + 1], cnt = e - b;
-    if (cnt <= 32) {
-        const int mine = lane < cnt ? ids[b + lane] : -1;
-        int rank = 0;
-        for (int k = 0; k < cnt; k++) {
-            const int v = __shfl_sync(0xffffffffu, mine, k);
-            rank += (v > mine) ? 1 : 0;
+    const int cpp = A.g.ncell / A.g.nc[0];
+    const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // cell within the kept planes
+    if (k < A.plane_n * cpp && !*A.overflow) {
+        int px = A.plane_lo + k / cpp;
+        if (px >= A.g.nc[0]) px -= A.g.nc[0];
+        const int c = px * cpp + k % cpp;
+        int cc[3] = {0, 0, 0};
+        {
+            int l = c;
+            if constexpr (DIM == 3) { cc[2] = l % A.g.nc[2]; l /= A.g.nc[2]; }
+            cc[1] = l % A.g.nc[1];
+            cc[0] = l / A.g.nc[1];
         }
-        __syncwarp();
-        if (lane < cnt) {
-            const int p = b + rank;
-            ids[p] = mine;
+        const int b = A.start[c], cnt = A.count[c], e = b + cnt;
+        const size_t ns_ = (size_t)A.g.nc[0] * A.plane_cap;
+        auto put = [&](int p, int i) {
+            uint32_t q = 0;
 #pragma unroll
-            for (int a = 0; a < DIM; a++) xs[(size_t)a * N + p] = x[(size_t)a * N + mine];
-            sps[p] = sp[mine];
-        }
-    } else {
-        if (lane == 0) {
-            for (int p = b + 1; p < e; p++) {  // insertion sort, descending
-                const int v = ids[p];
-                int q = p - 1;
-                while (q >= b && ids[q] < v) {
-                    ids[q + 1] = ids[q];
-                    q--;
-                }
-                ids[q + 1] = v;
+            for (int a = 0; a < DIM; a++) {
+                const double r = in_frame(__ldcg(A.x + (size_t)a * A.N + i), A.g.shift[a], A.g.L[a], A.g.cs[a], cc[a]);
+                A.rs[(size_t)a * ns_ + p] = r;
+                q |= cell_byte(r, 64.0 / A.g.cs[a]) << (8 * a);
             }
+            A.qs[p] = q;
+            A.sps[p] = A.sp[i];
+        };
+        if (cnt <= 32) {
+            const int mine = lane < cnt ? A.ids[b + lane] : -1;
+            int rank = 0;
+            for (int j = 0; j < cnt; j++) {
+                const int v = __shfl_sync(0xffffffffu, mine, j);
+                rank += (v > mine) ? 1 : 0;
+            }
+            __syncwarp();
+            if (lane < cnt) {
+                A.ids[b + rank] = mine;
+                put(b + rank, mine);
+            }
+        } else {
+            if (lane == 0) {
+                for (int p = b + 1; p < e; p++) {  // insertion sort, descending
+                    const int v = A.ids[p];
+                    int q = p - 1;
+                    while (q >= b && A.ids[q] < v) {
+                        A.ids[q + 1] = A.ids[q];
+                        q--;
+                    }
+                    A.ids[q + 1] = v;
+                }
+            }
+            __syncwarp();
+            for (int p = b + lane; p < e; p += 32) put(p, A.ids[p]);
         }
-        __syncwarp();
-        for (int p = b + lane; p < e; p += 32) {
-            const int i = ids[p];
-#pragma unroll
-            for (int a = 0; a < DIM; a++) xs[(size_t)a * N + p] = x[(size_t)a * N + i];
-            sps[p] = sp[i];
+    }
+    if (A.n_peers && announce_stamp) {  // the last CTA tells every peer that my arrays may be written into again
+        __threadfence();
+        __syncthreads();
+        __shared__ int s_last;
+        if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1) == (int)gridDim.x - 1;
+        __syncthreads();
+        if (s_last && (int)threadIdx.x < A.n_peers) {
+            __threadfence_system();
+            *(volatile uint32_t *)(A.peer_flags[threadIdx.x] + kFlagRebuilt + A.rank) = announce_stamp;
         }
+        if (s_last && threadIdx.x == 0) *ticket = 0;
     }
 }
 
-// ---- stencil loader shared by K2 and K5 ---------------------------------------------------------------
-// Gathers the particles of the 3^d cells around `cc` into shared memory in the frame of the central
-// cell (its particles in [0, cs)^d, neighbours shifted by whole cells), so no per-pair minimum image is
-// needed.  The central cell comes first: candidates [0, ncen) are the movable particles.
+// ---- stencil loader ---------------------------------------------------------------------------------------
+// Gathers the particles of the 3^d cells around `cc` into shared memory in the frame of the central cell (its
+// particles in [0, cs)^d, neighbours shifted by whole cells), so no per-pair minimum image is needed.  The central
+// cell comes first: candidates [0, ncen) are the movable particles.  The sorted arrays already hold in-cell
+// coordinates, so a candidate costs its loads and one add per axis.
 template <int DIM>
 struct Stencil {
     static constexpr int NST = DIM == 3 ? 27 : 9;
@@ -278,18 +361,23 @@ struct Stencil {
     int off[NST + 1];  // candidate offsets of the stencil cells in the gathered list
     int cnt[NST];      // particles in each stencil cell
     int base[NST];     // first sorted slot of each stencil cell
-    int cwrap[NST][3];
-    int o[NST][3];
+    double sh[NST][3];   // frame shift of the cell: o * cs
+    uint32_t qsh[NST];   // the same in packed bytes: (o + 1) * 64 per axis
 };
 
-template <int DIM>
-__device__ int load_stencil(const BoxArgs &A, const int (&cc)[3], Stencil<DIM> *st, double *sr, uint8_t *ssp) {
+// The candidate index space of the whole stencil is spread over ALL threads (thread t handles candidates t, t + NT,
+// ...), so the global loads of one CTA are independent and in flight together.  `sink(t, q)` receives the packed
+// byte coordinates of candidate t in the stencil frame (fast kernel: into the thread's registers).  Loads bypass L1:
+// inside a persistent kernel the sorted arrays change between the cells a CTA visits (own CTAs, other SMs, peer GPUs).
+template <int DIM, int NT, typename Sink>
+__device__ int load_stencil(const BoxArgs &A, const int (&cc)[3], Stencil<DIM> *st, double *sr, uint8_t *ssp, int cap, Sink &&sink) {
     constexpr int NST = Stencil<DIM>::NST;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+    const int tid = threadIdx.x;
     if (tid < NST) {
         // slot 0 = central cell; the others in first-axis-fastest order (Iterators.product, neighbours.jl:101)
         int k = tid == 0 ? (NST / 2) : (tid <= NST / 2 ? tid - 1 : tid);
         int c[3] = {0, 0, 0};
+        uint32_t qsh = 0;
 #pragma unroll
         for (int a = 0; a < DIM; a++) {
             const int oa = k % 3 - 1;
@@ -298,67 +386,14 @@ __device__ int load_stencil(const BoxArgs &A, const int (&cc)[3], Stencil<DIM> *
             if (v < 0) v += A.g.nc[a];
             if (v >= A.g.nc[a]) v -= A.g.nc[a];
             c[a] = v;
-            st->o[tid][a] = oa;
-            st->cwrap[tid][a] = v;
+            st->sh[tid][a] = (double)oa * A.g.cs[a];
+            qsh |= (uint32_t)((oa + 1) * 64) << (8 * a);
         }
         const int l = lin_cell<DIM>(c, A.g.nc);
         st->cell[tid] = l;
-        st->off[tid + 1] = A.start[l + 1] - A.start[l];
-    }
-    __syncthreads();
-    if (tid == 0) {
-        st->off[0] = 0;
-        for (int k = 0; k < NST; k++) st->off[k + 1] += st->off[k];
-    }
-    __syncthreads();
-    const int ncand = st->off[NST];
-    if (ncand > A.cap) {
-        if (tid == 0) atomicExch(A.overflow, 1);
-        return -1;
-    }
-    for (int s = warp; s < NST; s += nwarp) {
-        const int b = A.start[st->cell[s]], n = st->off[s + 1] - st->off[s], dst = st->off[s];
-        for (int p = lane; p < n; p += 32) {
-#pragma unroll
-            for (int a = 0; a < DIM; a++) {
-                const double r = in_frame(A.xs[(size_t)a * A.N + b + p], A.g.shift[a], A.g.L[a], A.g.cs[a], st->cwrap[s][a]);
-                sr[a * A.cap + dst + p] = r + (double)st->o[s][a] * A.g.cs[a];
-            }
-            ssp[dst + p] = A.sps[b + p];
-        }
-    }
-    __syncthreads();
-    return ncand;
-}
-
-// Flat variant used by the fast sweep kernel: the candidate index space of the whole stencil is spread over ALL
-// threads (thread t handles candidates t, t + NT, ...), so the global loads of one CTA are independent and in
-// flight together instead of one dependent start[] -> xs[] chain per stencil cell.  Same candidate order as
-// load_stencil.  (A variant that also dropped candidates farther than rc from the central cell -- 24 % of the
-// stencil -- was measured slower: the second pass over the stencil costs more than the smaller scan saves.)
-template <int DIM, int NT>
-__device__ int load_stencil_flat(const BoxArgs &A, const int (&cc)[3], Stencil<DIM> *st, double *sr, uint8_t *ssp) {
-    constexpr int NST = Stencil<DIM>::NST;
-    const int tid = threadIdx.x;
-    if (tid < NST) {
-        int k = tid == 0 ? (NST / 2) : (tid <= NST / 2 ? tid - 1 : tid);
-        int c[3] = {0, 0, 0};
-#pragma unroll
-        for (int a = 0; a < DIM; a++) {
-            const int oa = k % 3 - 1;
-            k /= 3;
-            int v = cc[a] + oa;
-            if (v < 0) v += A.g.nc[a];
-            if (v >= A.g.nc[a]) v -= A.g.nc[a];
-            c[a] = v;
-            st->o[tid][a] = oa;
-            st->cwrap[tid][a] = v;
-        }
-        const int l = lin_cell<DIM>(c, A.g.nc);
-        const int b = A.start[l];
-        st->cell[tid] = l;
-        st->base[tid] = b;
-        st->cnt[tid] = A.start[l + 1] - b;
+        st->qsh[tid] = qsh;
+        st->base[tid] = __ldcg(A.start + l);
+        st->cnt[tid] = __ldcg(A.count + l);
     }
     __syncthreads();
     if (tid == 0) {
@@ -367,10 +402,11 @@ __device__ int load_stencil_flat(const BoxArgs &A, const int (&cc)[3], Stencil<D
     }
     __syncthreads();
     const int nall = st->off[NST];
-    if (nall > A.cap) {
+    if (nall > cap) {
         if (tid == 0) atomicExch(A.overflow, 1);
         return -1;
     }
+    const size_t ns_ = (size_t)A.g.nc[0] * A.plane_cap;
     for (int t = tid; t < nall; t += NT) {
         int lo = 0, hi = NST;  // stencil cell of flat index t: binary search over the 3^d offsets
         while (hi - lo > 1) {
@@ -379,10 +415,9 @@ __device__ int load_stencil_flat(const BoxArgs &A, const int (&cc)[3], Stencil<D
         }
         const int slot = st->base[lo] + (t - st->off[lo]);
 #pragma unroll
-        for (int a = 0; a < DIM; a++)
-            sr[a * A.cap + t] = in_frame(A.xs[(size_t)a * A.N + slot], A.g.shift[a], A.g.L[a], A.g.cs[a], st->cwrap[lo][a]) +
-                                (double)st->o[lo][a] * A.g.cs[a];
-        ssp[t] = A.sps[slot];
+        for (int a = 0; a < DIM; a++) sr[a * cap + t] = __ldcg(A.rs + (size_t)a * ns_ + slot) + st->sh[lo][a];
+        ssp[t] = __ldcg(A.sps + slot);
+        sink(t, __ldcg(A.qs + slot) + st->qsh[lo]);
     }
     __syncthreads();
     return nall;
@@ -422,9 +457,9 @@ __global__ void __launch_bounds__(kBoxThreads) k_box_energy(const __grid_constan
         cc[1] = l % A.g.nc[1];
         cc[0] = l / A.g.nc[1];
     }
-    const int ncand = load_stencil<DIM>(A, cc, &st, sr, ssp);
+    const int ncand = load_stencil<DIM, kBoxThreads>(A, cc, &st, sr, ssp, A.cap, [](int, uint32_t) {});
     if (ncand < 0) return;
-    const int ncen = st.off[1], b = A.start[st.cell[0]];
+    const int ncen = st.off[1], b = st.base[0];
     double wsum = 0.0;
     for (int k = warp; k < ncen; k += kBoxWarps) {
         const double xi[3] = {sr[k], sr[A.cap + k], DIM == 3 ? sr[2 * A.cap + k] : 0.0};
@@ -449,142 +484,13 @@ __global__ void __launch_bounds__(kBoxThreads) k_box_energy(const __grid_constan
     }
 }
 
-// ---- K5: checkerboard sweep of one colour --------------------------------------------------------------
-template <int DIM, int MODEL>
-__global__ void __launch_bounds__(kBoxThreads) k_box_sweep(const __grid_constant__ BoxArgs A, int colour) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ Stencil<DIM> st;
-    __shared__ double s_par[PMC_MAX_SPECIES * PMC_MAX_SPECIES * PMC_NPAR];
-    __shared__ double s_red[2][kBoxWarps];
-    __shared__ double s_delta[kBoxThreads][3];
-    __shared__ double s_thr[kBoxThreads];
-    __shared__ int s_k[kBoxThreads];
-    double *sr = (double *)smem_raw;
-    uint8_t *ssp = (uint8_t *)(sr + DIM * A.cap);
-    uint8_t *moved = ssp + A.cap;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int k = tid; k < A.ns * A.ns * PMC_NPAR; k += kBoxThreads) s_par[k] = A.par[k];
-    // active cell of this CTA: coordinates 2*h + colour bit
-    int cc[3] = {0, 0, 0};
-    {
-        int l = blockIdx.x + A.cta_offset;
-        if constexpr (DIM == 3) { cc[2] = 2 * (l % (A.g.nc[2] / 2)) + ((colour >> 2) & 1); l /= (A.g.nc[2] / 2); }
-        cc[1] = 2 * (l % (A.g.nc[1] / 2)) + ((colour >> 1) & 1);
-        cc[0] = 2 * (l / (A.g.nc[1] / 2)) + (colour & 1);
-    }
-    const int ncand = load_stencil<DIM>(A, cc, &st, sr, ssp);
-    if (ncand < 0) return;
-    const int cell = st.cell[0], ncen = st.off[1], b = A.start[cell];
-    for (int k = tid; k < ncen; k += kBoxThreads) moved[k] = 0;
-    const double cs[3] = {A.g.cs[0], A.g.cs[1], A.g.cs[2]};
-    const uint32_t k0 = (uint32_t)A.seed, k1 = (uint32_t)(A.seed >> 32);
-    double Esum = 0.0;
-    uint32_t nacc = 0;
-    int last_k = -1, slot = 0;
-    double last_x[3] = {0.0, 0.0, 0.0};
-
-    for (int tb = 0; tb < ncen; tb += kBoxThreads) {  // n_cell trials in this cell (one sweep = N trials)
-        const int nb = min(kBoxThreads, ncen - tb);
-        __syncthreads();
-        if (tid < nb) {
-            const uint32_t q = (uint32_t)(tb + tid);
-            const Philox4 a = philox4x32_10(q, (uint32_t)cell, A.sweep, 0u, k0, k1);
-            const Philox4 bb = philox4x32_10(q, (uint32_t)cell, A.sweep, 1u, k0, k1);
-            float z0, z1, z2, z3;
-            box_muller(bb.v[0], bb.v[1], z0, z1);
-            box_muller(bb.v[2], bb.v[3], z2, z3);
-            s_k[tid] = (int)bounded(a.v[1], (uint32_t)ncen);
-            s_delta[tid][0] = (double)(A.sigma * z0);
-            s_delta[tid][1] = (double)(A.sigma * z1);
-            s_delta[tid][2] = (double)(A.sigma * z2);
-            s_thr[tid] = -A.T * log(uniform53(a.v[2], a.v[3]));
-        }
-        __syncthreads();
-        for (int t = 0; t < nb; t++) {
-            const int k = s_k[t];
-            double xo[3] = {0.0, 0.0, 0.0}, xn[3] = {0.0, 0.0, 0.0};
-            bool inside = true;
-#pragma unroll
-            for (int a = 0; a < DIM; a++) {
-                xo[a] = (k == last_k) ? last_x[a] : sr[a * A.cap + k];
-                xn[a] = xo[a] + s_delta[t][a];
-                inside &= (xn[a] >= 0.0) && (xn[a] < cs[a]);
-            }
-            if (!inside) continue;  // leaves the cell: rejected (uniform across the CTA)
-            const double *prow = s_par + ssp[k] * A.ns * PMC_NPAR;
-            double part = 0.0;
-            for (int j = tid; j < ncand; j += kBoxThreads) {
-                if (j == k) continue;
-                const double *p = prow + ssp[j] * PMC_NPAR;
-                const double rc2 = p[PMC_P_RCUT2];
-                const double r2o = d2_frame<DIM>(sr, A.cap, j, xo);
-                const double r2n = d2_frame<DIM>(sr, A.cap, j, xn);
-                if (r2o <= rc2) part -= pair_potential<MODEL>(p, r2o);
-                if (r2n <= rc2) part += pair_potential<MODEL>(p, r2n);
-            }
-            part = warp_sum(part);
-            if (lane == 0) s_red[slot][warp] = part;
-            __syncthreads();
-            double dE = s_red[slot][0];
-#pragma unroll
-            for (int w = 1; w < kBoxWarps; w++) dE += s_red[slot][w];
-            slot ^= 1;
-            if (dE < s_thr[t]) {
-                if (tid == k % kBoxThreads) {
-#pragma unroll
-                    for (int a = 0; a < DIM; a++) sr[a * A.cap + k] = xn[a];
-                    moved[k] = 1;
-                }
-                last_k = k;
-#pragma unroll
-                for (int a = 0; a < DIM; a++) last_x[a] = xn[a];
-                Esum += dE;
-                nacc++;
-            }
-        }
-    }
-    __syncthreads();
-    // write moved particles back: canonical arrays (+ image counters) and the sorted copy
-    for (int k = tid; k < ncen; k += kBoxThreads) {
-        if (!moved[k]) continue;
-        const int i = A.ids[b + k];
-#pragma unroll
-        for (int a = 0; a < DIM; a++) {
-            const double xold = A.xs[(size_t)a * A.N + b + k];
-            const double r0 = in_frame(xold, A.g.shift[a], A.g.L[a], A.g.cs[a], cc[a]);
-            int w;
-            const double xnew = wrap1(xold + (sr[a * A.cap + k] - r0), A.g.L[a], w);
-            const int im = A.img[(size_t)a * A.N + i] + w;
-            A.xs[(size_t)a * A.N + b + k] = xnew;
-            A.x[(size_t)a * A.N + i] = xnew;
-            if (w) A.img[(size_t)a * A.N + i] = im;
-            for (int p = 0; p < A.n_peers; p++) {
-                A.peer_xs[p][(size_t)a * A.N + b + k] = xnew;
-                A.peer_x[p][(size_t)a * A.N + i] = xnew;
-                if (w) A.peer_img[p][(size_t)a * A.N + i] = im;
-            }
-        }
-    }
-    if (tid == 0) {
-        A.cellE[cell] = Esum;
-        A.cell_acc[cell] = nacc;
-        for (int p = 0; p < A.n_peers; p++) {
-            A.peer_cellE[p][cell] = Esum;
-            A.peer_cacc[p][cell] = nacc;
-        }
-    }
-    if (A.n_peers) __threadfence_system();
-}
-
-// ---- K5 (fast): checkerboard sweep with the integer prefilter ---------------------------------------------
-// Same trials and the same fp64 pair terms as k_box_sweep, issued the way chains_fast.cuh does it: 128 threads
-// per active cell, every thread keeps the packed 8-bit frame coordinates of its KC candidates in registers, one
-// sphere test (midpoint of old/new, radius rc + |delta|/2; VABSDIFF4 + IDP.4A + funnel shift) per candidate, survivors
-// compacted with one warp prefix sum, fp64 only for survivors (no minimum image in the cell frame), explicit
-// 32-bit shared addressing.  Needs cubic cells (one fixed-point scale); otherwise k_box_sweep is used.
-// The one-warp-per-trial speculative scheme of chains_spec.cuh was tried here too and measured 17 % SLOWER
-// (5.3e8 vs 6.3e8 moves/s at N = 2^20): a cell holds only ~19 trials, so the rounds of four never fill up and
-// every warp has to stream the whole stencil.
+// ---- K5: checkerboard sweep -------------------------------------------------------------------------------
+// ONE persistent kernel per sweep.  CTAs pull (phase, cell) units from a global counter in phase order; a cell of
+// phase k is started once the neighbour cells that belong to EARLIER phases carry this sweep's stamp in done[] (one
+// warp polls its <= 26 flags).  There is no barrier between the colour phases, neither on the GPU nor between GPUs:
+// a cell only ever waits for its own neighbourhood, the tail of one colour overlaps the head of the next, and with
+// several GPUs only the cells next to a rank boundary wait for a flag that arrives over NVLink.  Units are handed
+// out in phase order, so whatever a cell waits for has been handed out before it: no deadlock, whatever the grid.
 constexpr int kBfThreads = 128;
 constexpr int kBfWarps = kBfThreads / 32;
 // register candidates per thread offered (capacity = threads x KC): 512 / 640 / 768 / 1024 candidates
@@ -651,20 +557,31 @@ __device__ __forceinline__ void bf_sts_u8(uint32_t a, uint32_t v) { asm volatile
 // reaches 128 and the signed-byte reading of VABSDIFF4 (common.cuh) never aliases in the frame.
 __device__ __forceinline__ uint32_t bf_fixed(double r, double cs, double scale) { return (uint32_t)__double2ull_rd((r + cs) * scale); }
 
+// KC > 0: the trials are issued the way chains_fast.cuh does it -- 128 threads per active cell, every thread keeps the
+// packed 8-bit frame coordinates of its KC candidates in registers, one sphere test (midpoint of old/new, radius rc +
+// |delta|/2; VABSDIFF4 + IDP.4A + funnel shift) per candidate, survivors compacted with one warp prefix sum, fp64 only
+// for survivors (no minimum image in the cell frame).  Needs cubic cells (one fixed-point scale).  KC == 0: every
+// candidate in fp64 (non-cubic cells, prefilter = -1).
+// The one-warp-per-trial speculative scheme of chains_spec.cuh was tried here too and measured 17 % SLOWER (5.3e8 vs
+// 6.3e8 moves/s at N = 2^20): the trials of a cell nearly always conflict (filter sphere > cell).
 template <int DIM, int MODEL, int KC>
-__global__ void __launch_bounds__(kBfThreads, kBfThreads == 64 ? 12 : 8) k_box_sweep_fast(const __grid_constant__ BoxArgs A, int colour) {
+__global__ void __launch_bounds__(kBfThreads, 8) k_box_sweep_all(const __grid_constant__ BoxArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ Stencil<DIM> st;
-    constexpr int CAP = kBfThreads * KC;
+    __shared__ int s_unit;
+    constexpr bool FAST = KC > 0;
+    constexpr int NST = Stencil<DIM>::NST;
+    const int CAP = FAST ? kBfThreads * KC : A.cap;
     const BfLayout F = bf_layout(DIM, CAP);
     const uint32_t sb = (uint32_t)__cvta_generic_to_shared(smem_raw);
-    constexpr uint32_t cap8 = 8u * CAP;
+    const uint32_t cap8 = 8u * (uint32_t)CAP;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double *sr = (double *)(smem_raw + F.r);
     uint8_t *ssp = smem_raw + F.sp;
+    const double *spar = (const double *)(smem_raw + F.par);
     {
-        double *spar = (double *)(smem_raw + F.par), *scp = (double *)(smem_raw + F.cp);
-        for (int k = tid; k < A.ns * A.ns * PMC_NPAR; k += kBfThreads) spar[k] = A.par[k];
+        double *wpar = (double *)(smem_raw + F.par), *scp = (double *)(smem_raw + F.cp);
+        for (int k = tid; k < A.ns * A.ns * PMC_NPAR; k += kBfThreads) wpar[k] = A.par[k];
         for (int k = tid; k < A.ns * A.ns; k += kBfThreads) {
             scp[4 * k + 0] = A.par[k * PMC_NPAR + PMC_P_RCUT2];
             scp[4 * k + 1] = A.par[k * PMC_NPAR + PMC_P_EPS];
@@ -677,225 +594,277 @@ __global__ void __launch_bounds__(kBfThreads, kBfThreads == 64 ? 12 : 8) k_box_s
             ((double *)(smem_raw + F.rcs))[tid] = sqrt(rc2);
         }
     }
-    int cc[3] = {0, 0, 0};
-    {
-        int l = blockIdx.x + A.cta_offset;
-        if constexpr (DIM == 3) { cc[2] = 2 * (l % (A.g.nc[2] / 2)) + ((colour >> 2) & 1); l /= (A.g.nc[2] / 2); }
-        cc[1] = 2 * (l % (A.g.nc[1] / 2)) + ((colour >> 1) & 1);
-        cc[0] = 2 * (l / (A.g.nc[1] / 2)) + (colour & 1);
-    }
-    const int ncand = load_stencil_flat<DIM, kBfThreads>(A, cc, &st, sr, ssp);  // A.cap == CAP on this path
-    if (ncand < 0) return;
-    const int cell = st.cell[0], ncen = st.off[1], bstart = A.start[cell];
-    for (int k = tid; k < ncen; k += kBfThreads) smem_raw[F.mv + k] = 0;
-    const double cs = A.g.cs[0];
-    const double fscale = 1073741824.0 / cs;  // 2^30 / cell side
-    uint32_t myq[KC];                          // packed 8-bit prefilter coordinates of this thread's candidates
-#pragma unroll
-    for (int k = 0; k < KC; k++) {
-        const int j = k * kBfThreads + tid;
-        uint32_t u[3] = {0u, 0u, 0u};
-#pragma unroll
-        for (int a = 0; a < DIM; a++) u[a] = j < ncand ? bf_fixed(sr[a * CAP + j], cs, fscale) : 0u;
-        myq[k] = pack8(u[0], u[1], u[2]);
-    }
+    const double cs0 = A.g.cs[0];
+    const double fscale = 1073741824.0 / cs0;  // 2^30 / cell side (FAST: cubic cells)
     const uint32_t k0 = (uint32_t)A.seed, k1 = (uint32_t)(A.seed >> 32);
-    const uint32_t qa = sb + F.q + (uint32_t)warp * (2u * KC * 32);
-    double Esum = 0.0;
-    uint32_t nacc = 0, slot = 0;
+    const uint32_t qa = sb + F.q + (uint32_t)warp * (2u * (FAST ? KC : 1) * 32);
+    const size_t ns_ = (size_t)A.g.nc[0] * A.plane_cap;
+    const int n_units = (1 << DIM) * A.cell_n;
+    uint32_t rebuilt_ok = 0;  // bit p: peer p has finished this sweep's rebuild (its arrays may be written into)
 
-    for (int tb = 0; tb < ncen; tb += kBfBatch) {
-        const int nb = min(kBfBatch, ncen - tb);
+    for (;;) {
         __syncthreads();
-        if (tid < nb) {
-            const uint32_t q = (uint32_t)(tb + tid);
-            const Philox4 a = philox4x32_10(q, (uint32_t)cell, A.sweep, 0u, k0, k1);
-            const Philox4 bb = philox4x32_10(q, (uint32_t)cell, A.sweep, 1u, k0, k1);
-            float z0, z1, z2, z3;
-            box_muller(bb.v[0], bb.v[1], z0, z1);
-            box_muller(bb.v[2], bb.v[3], z2, z3);
-            unsigned char *rec = smem_raw + F.rec + (size_t)kBfRec * tid;
-            double *rd = (double *)rec;
-            int *ri = (int *)(rec + 32);
-            uint32_t *rt = (uint32_t *)(rec + 64);
-            const double dx = (double)(A.sigma * z0), dy = (double)(A.sigma * z1), dz = DIM == 3 ? (double)(A.sigma * z2) : 0.0;
-            rd[0] = dx;
-            rd[1] = dy;
-            rd[2] = dz;
-            rd[3] = -A.T * log(uniform53(a.v[2], a.v[3]));
-            ri[0] = (int)__double2ll_rn(dx * fscale);
-            ri[1] = (int)__double2ll_rn(dy * fscale);
-            ri[2] = (int)__double2ll_rn(dz * fscale);
-            ri[3] = (int)bounded(a.v[1], (uint32_t)ncen);
-            const double hd = 0.5 * sqrt(dx * dx + dy * dy + dz * dz);
-            const double *rcs = (const double *)(smem_raw + F.rcs);
-#pragma unroll
-            for (int s = 0; s < PMC_MAX_SPECIES; s++) rt[s] = neg_thr8((rcs[s] + hd) * fscale * 0x1p-24);
+        if (tid == 0) s_unit = atomicAdd(A.work, 1);
+        __syncthreads();
+        const int unit = s_unit;
+        if (unit >= n_units) break;
+        const int phase = unit / A.cell_n, colour = A.order[phase];
+        int cc[3] = {0, 0, 0};
+        {
+            // within a phase the cells are taken from both ends of this rank's slab towards its middle: the cells other
+            // ranks wait for go first, and the cells that wait for other ranks find their flags long set
+            const int idx = unit % A.cell_n;
+            int l = (idx & 1) ? A.cell_lo + A.cell_n - 1 - (idx >> 1) : A.cell_lo + (idx >> 1);
+            if constexpr (DIM == 3) { cc[2] = 2 * (l % (A.g.nc[2] / 2)) + ((colour >> 2) & 1); l /= (A.g.nc[2] / 2); }
+            cc[1] = 2 * (l % (A.g.nc[1] / 2)) + ((colour >> 1) & 1);
+            cc[0] = 2 * (l / (A.g.nc[1] / 2)) + (colour & 1);
         }
-        __syncthreads();
-        for (int t = 0; t < nb; t++) {
-            const uint32_t ra = sb + F.rec + (uint32_t)kBfRec * (uint32_t)t;
-            double d0, d1, d2, thr;
-            int di0, di1, di2, k;
-            bf_lds_f64x2(ra, d0, d1);
-            bf_lds_f64x2(ra + 16, d2, thr);
-            bf_lds_s32x4(ra + 32, di0, di1, di2, k);
-            const uint32_t xa = sb + F.r + 8u * (uint32_t)k;
-            double xo[3], xn[3];
-            xo[0] = bf_lds_f64(xa);
-            xo[1] = bf_lds_f64(xa + cap8);
-            xo[2] = DIM == 3 ? bf_lds_f64(xa + 2 * cap8) : 0.0;
-            xn[0] = xo[0] + d0;
-            xn[1] = xo[1] + d1;
-            xn[2] = xo[2] + d2;
-            bool inside = xn[0] >= 0.0 && xn[0] < cs && xn[1] >= 0.0 && xn[1] < cs;
-            if constexpr (DIM == 3) inside = inside && xn[2] >= 0.0 && xn[2] < cs;
-            if (!inside) continue;  // leaves the cell: rejected (uniform across the CTA)
-            const uint32_t si = bf_lds_u8(sb + F.sp + (uint32_t)k);
-            const uint32_t um0 = bf_fixed(xo[0], cs, fscale) + (uint32_t)(di0 >> 1);
-            const uint32_t um1 = bf_fixed(xo[1], cs, fscale) + (uint32_t)(di1 >> 1);
-            const uint32_t um2 = DIM == 3 ? bf_fixed(xo[2], cs, fscale) + (uint32_t)(di2 >> 1) : 0u;
-            const int fthr = (int)bf_lds_u32(ra + 64 + 4u * si);
-            const uint32_t umq = pack8(um0, um1, um2);
-            uint32_t m = 0;
+        // ---- wait for the neighbour cells of earlier phases (they may be another CTA's, or another GPU's) ----
+        if (phase > 0) {
+            if (tid >= 1 && tid < NST) {
+                int k = tid <= NST / 2 ? tid - 1 : tid, c[3] = {0, 0, 0}, col = 0;
 #pragma unroll
-            for (int kk = 0; kk < KC; kk++) {  // survivor: bit KC-1-kk
-                const uint32_t v = __vabsdiffu4(umq, myq[kk]);
-                m = __funnelshift_l((uint32_t)__dp4a((int)v, (int)v, fthr), m, 1);
-            }
-            const int mine = __popc(m);
-            int incl = mine;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int v = __shfl_up_sync(0xffffffffu, incl, o);
-                incl += (lane >= o) ? v : 0;
-            }
-            const int total = __shfl_sync(0xffffffffu, incl, 31);
-            uint32_t wp = qa + 2u * (uint32_t)(incl - mine);
-#pragma unroll
-            for (int kk = 0; kk < KC; kk++) {
-                if (m & (1u << (KC - 1 - kk))) {
-                    bf_sts_u16(wp, (uint32_t)(kk * kBfThreads + tid));
-                    wp += 2;
+                for (int a = 0; a < DIM; a++) {
+                    int v = cc[a] + k % 3 - 1;
+                    k /= 3;
+                    if (v < 0) v += A.g.nc[a];
+                    if (v >= A.g.nc[a]) v -= A.g.nc[a];
+                    c[a] = v;
+                    col |= (v & 1) << a;
                 }
+                if (A.phase_of[col] < phase) wait_for(A.done + lin_cell<DIM>(c, A.g.nc), A.stamp, A.error, false);
             }
-            __syncwarp();
-            double part = 0.0;
-            const uint32_t prow = si * (uint32_t)A.ns;
-            for (int q = lane; q < total; q += 32) {
-                const uint32_t j = bf_lds_u16(qa + 2u * (uint32_t)q);
-                if (j < (uint32_t)ncand && j != (uint32_t)k) {
-                    const uint32_t ja = sb + F.r + 8u * j;
-                    const double x0 = bf_lds_f64(ja), x1 = bf_lds_f64(ja + cap8);
-                    double a_ = xo[0] - x0, b_ = xn[0] - x0;
-                    double r2o = a_ * a_, r2n = b_ * b_;
-                    a_ = xo[1] - x1;
-                    b_ = xn[1] - x1;
-                    r2o = fma(a_, a_, r2o);
-                    r2n = fma(b_, b_, r2n);
-                    if constexpr (DIM == 3) {
-                        const double x2 = bf_lds_f64(ja + 2 * cap8);
-                        a_ = xo[2] - x2;
-                        b_ = xn[2] - x2;
+            __syncthreads();
+        }
+        uint32_t myq[FAST ? KC : 1];  // packed 8-bit prefilter coordinates of this thread's candidates
+#pragma unroll
+        for (int k = 0; k < (FAST ? KC : 1); k++) myq[k] = 0u;
+        const int ncand = load_stencil<DIM, kBfThreads>(A, cc, &st, sr, ssp, CAP, [&](int t, uint32_t q) {
+            if constexpr (FAST) {
+#pragma unroll
+                for (int k = 0; k < KC; k++)
+                    if (t / kBfThreads == k) myq[k] = q;
+            }
+        });
+        const int cell = st.cell[0];
+        double Esum = 0.0;
+        uint32_t nacc = 0;
+        if (ncand >= 0) {
+            const int ncen = st.off[1];
+            for (int k = tid; k < ncen; k += kBfThreads) smem_raw[F.mv + k] = 0;
+            uint32_t slot = 0;
+            for (int tb = 0; tb < ncen; tb += kBfBatch) {  // n_cell trials in this cell (one sweep = N trials)
+                const int nb = min(kBfBatch, ncen - tb);
+                __syncthreads();
+                if (tid < nb) {
+                    const uint32_t q = (uint32_t)(tb + tid);
+                    const Philox4 a = philox4x32_10(q, (uint32_t)cell, A.sweep, 0u, k0, k1);
+                    const Philox4 bb = philox4x32_10(q, (uint32_t)cell, A.sweep, 1u, k0, k1);
+                    float z0, z1, z2, z3;
+                    box_muller(bb.v[0], bb.v[1], z0, z1);
+                    box_muller(bb.v[2], bb.v[3], z2, z3);
+                    unsigned char *rec = smem_raw + F.rec + (size_t)kBfRec * tid;
+                    double *rd = (double *)rec;
+                    int *ri = (int *)(rec + 32);
+                    uint32_t *rt = (uint32_t *)(rec + 64);
+                    const double dx = (double)(A.sigma * z0), dy = (double)(A.sigma * z1), dz = DIM == 3 ? (double)(A.sigma * z2) : 0.0;
+                    rd[0] = dx;
+                    rd[1] = dy;
+                    rd[2] = dz;
+                    rd[3] = -A.T * log(uniform53(a.v[2], a.v[3]));
+                    ri[0] = (int)__double2ll_rn(dx * fscale);
+                    ri[1] = (int)__double2ll_rn(dy * fscale);
+                    ri[2] = (int)__double2ll_rn(dz * fscale);
+                    ri[3] = (int)bounded(a.v[1], (uint32_t)ncen);
+                    const double hd = 0.5 * sqrt(dx * dx + dy * dy + dz * dz);
+                    const double *rcs = (const double *)(smem_raw + F.rcs);
+#pragma unroll
+                    for (int s = 0; s < PMC_MAX_SPECIES; s++) rt[s] = neg_thr8((rcs[s] + hd) * fscale * 0x1p-24);
+                }
+                __syncthreads();
+                for (int t = 0; t < nb; t++) {
+                    const uint32_t ra = sb + F.rec + (uint32_t)kBfRec * (uint32_t)t;
+                    double d0, d1, d2, thr;
+                    int di0, di1, di2, k;
+                    bf_lds_f64x2(ra, d0, d1);
+                    bf_lds_f64x2(ra + 16, d2, thr);
+                    bf_lds_s32x4(ra + 32, di0, di1, di2, k);
+                    const uint32_t xa = sb + F.r + 8u * (uint32_t)k;
+                    double xo[3], xn[3];
+                    xo[0] = bf_lds_f64(xa);
+                    xo[1] = bf_lds_f64(xa + cap8);
+                    xo[2] = DIM == 3 ? bf_lds_f64(xa + 2 * cap8) : 0.0;
+                    xn[0] = xo[0] + d0;
+                    xn[1] = xo[1] + d1;
+                    xn[2] = xo[2] + d2;
+                    bool inside = xn[0] >= 0.0 && xn[0] < A.g.cs[0] && xn[1] >= 0.0 && xn[1] < A.g.cs[1];
+                    if constexpr (DIM == 3) inside = inside && xn[2] >= 0.0 && xn[2] < A.g.cs[2];
+                    if (!inside) continue;  // leaves the cell: rejected (uniform across the CTA)
+                    const uint32_t si = bf_lds_u8(sb + F.sp + (uint32_t)k);
+                    const uint32_t prow = si * (uint32_t)A.ns;
+                    double part = 0.0;
+                    auto pair_terms = [&](uint32_t j) {
+                        const uint32_t ja = sb + F.r + 8u * j;
+                        const double x0 = bf_lds_f64(ja), x1 = bf_lds_f64(ja + cap8);
+                        double a_ = xo[0] - x0, b_ = xn[0] - x0;
+                        double r2o = a_ * a_, r2n = b_ * b_;
+                        a_ = xo[1] - x1;
+                        b_ = xn[1] - x1;
                         r2o = fma(a_, a_, r2o);
                         r2n = fma(b_, b_, r2n);
-                    }
-                    const uint32_t sj = bf_lds_u8(sb + F.sp + j);
-                    if constexpr (MODEL == PMC_MODEL_LJ || MODEL == PMC_MODEL_KG) {
-                        double rc2, eps4, sig2, shift;
-                        const uint32_t pa = sb + F.cp + 32u * (prow + sj);
-                        bf_lds_f64x2(pa, rc2, eps4);
-                        bf_lds_f64x2(pa + 16, sig2, shift);
-                        const double uo = lj_core(r2o, eps4, sig2) - shift;
-                        const double un = lj_core(r2n, eps4, sig2) - shift;
-                        part += (r2n <= rc2 ? un : 0.0) - (r2o <= rc2 ? uo : 0.0);
+                        if constexpr (DIM == 3) {
+                            const double x2 = bf_lds_f64(ja + 2 * cap8);
+                            a_ = xo[2] - x2;
+                            b_ = xn[2] - x2;
+                            r2o = fma(a_, a_, r2o);
+                            r2n = fma(b_, b_, r2n);
+                        }
+                        const uint32_t sj = bf_lds_u8(sb + F.sp + j);
+                        if constexpr (MODEL == PMC_MODEL_LJ || MODEL == PMC_MODEL_KG) {
+                            double rc2, eps4, sig2, shift;
+                            const uint32_t pa = sb + F.cp + 32u * (prow + sj);
+                            bf_lds_f64x2(pa, rc2, eps4);
+                            bf_lds_f64x2(pa + 16, sig2, shift);
+                            const double uo = lj_core(r2o, eps4, sig2) - shift;
+                            const double un = lj_core(r2n, eps4, sig2) - shift;
+                            part += (r2n <= rc2 ? un : 0.0) - (r2o <= rc2 ? uo : 0.0);
+                        } else {
+                            const double *p = spar + (prow + sj) * PMC_NPAR;
+                            const double rc2 = p[PMC_P_RCUT2];
+                            if (r2o <= rc2) part -= pair_potential<MODEL>(p, r2o);
+                            if (r2n <= rc2) part += pair_potential<MODEL>(p, r2n);
+                        }
+                    };
+                    if constexpr (FAST) {
+                        const uint32_t um0 = bf_fixed(xo[0], cs0, fscale) + (uint32_t)(di0 >> 1);
+                        const uint32_t um1 = bf_fixed(xo[1], cs0, fscale) + (uint32_t)(di1 >> 1);
+                        const uint32_t um2 = DIM == 3 ? bf_fixed(xo[2], cs0, fscale) + (uint32_t)(di2 >> 1) : 0u;
+                        const int fthr = (int)bf_lds_u32(ra + 64 + 4u * si);
+                        const uint32_t umq = pack8(um0, um1, um2);
+                        uint32_t m = 0;
+#pragma unroll
+                        for (int kk = 0; kk < KC; kk++) {  // survivor: bit KC-1-kk
+                            const uint32_t v = __vabsdiffu4(umq, myq[kk]);
+                            m = __funnelshift_l((uint32_t)__dp4a((int)v, (int)v, fthr), m, 1);
+                        }
+                        const int mine = __popc(m);
+                        int incl = mine;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                            incl += (lane >= o) ? v : 0;
+                        }
+                        const int total = __shfl_sync(0xffffffffu, incl, 31);
+                        uint32_t wp = qa + 2u * (uint32_t)(incl - mine);
+#pragma unroll
+                        for (int kk = 0; kk < KC; kk++) {
+                            if (m & (1u << (KC - 1 - kk))) {
+                                bf_sts_u16(wp, (uint32_t)(kk * kBfThreads + tid));
+                                wp += 2;
+                            }
+                        }
+                        __syncwarp();
+                        for (int q = lane; q < total; q += 32) {
+                            const uint32_t j = bf_lds_u16(qa + 2u * (uint32_t)q);
+                            if (j < (uint32_t)ncand && j != (uint32_t)k) pair_terms(j);
+                        }
+                        __syncwarp();
                     } else {
-                        const double *p = (const double *)(smem_raw + F.par) + (prow + sj) * PMC_NPAR;
-                        const double rc2 = p[PMC_P_RCUT2];
-                        if (r2o <= rc2) part -= pair_potential<MODEL>(p, r2o);
-                        if (r2n <= rc2) part += pair_potential<MODEL>(p, r2n);
+                        for (int j = tid; j < ncand; j += kBfThreads)
+                            if (j != k) pair_terms((uint32_t)j);
+                    }
+                    part = warp_sum(part);
+                    const uint32_t rda = sb + F.red + 8u * kBfWarps * slot;
+                    if (lane == 0) bf_sts_f64(rda + 8u * (uint32_t)warp, part);
+                    __syncthreads();
+                    double s0, s1, s2 = 0.0, s3 = 0.0;
+                    bf_lds_f64x2(rda, s0, s1);
+                    if constexpr (kBfWarps == 4) bf_lds_f64x2(rda + 16, s2, s3);
+                    const double dE = kBfWarps == 4 ? ((s0 + s1) + s2) + s3 : s0 + s1;
+                    slot ^= 1u;
+                    if (dE < thr) {
+                        bf_sts_f64(xa, xn[0]);
+                        bf_sts_f64(xa + cap8, xn[1]);
+                        if constexpr (DIM == 3) bf_sts_f64(xa + 2 * cap8, xn[2]);
+                        bf_sts_u8(sb + F.mv + (uint32_t)k, 1u);
+                        Esum += dE;
+                        nacc++;
+                        if constexpr (FAST) {
+                            if (tid == (k & (kBfThreads - 1))) {  // owner refreshes its register copy
+                                const int ki = k / kBfThreads;
+                                const uint32_t f = pack8(bf_fixed(xn[0], cs0, fscale), bf_fixed(xn[1], cs0, fscale), DIM == 3 ? bf_fixed(xn[2], cs0, fscale) : 0u);
+#pragma unroll
+                                for (int kk = 0; kk < KC; kk++) myq[kk] = kk == ki ? f : myq[kk];
+                            }
+                        }
                     }
                 }
             }
-            __syncwarp();
-            part = warp_sum(part);
-            const uint32_t rda = sb + F.red + 8u * kBfWarps * slot;
-            if (lane == 0) bf_sts_f64(rda + 8u * (uint32_t)warp, part);
             __syncthreads();
-            double s0, s1, s2 = 0.0, s3 = 0.0;
-            bf_lds_f64x2(rda, s0, s1);
-            if constexpr (kBfWarps == 4) bf_lds_f64x2(rda + 16, s2, s3);
-            const double dE = kBfWarps == 4 ? ((s0 + s1) + s2) + s3 : s0 + s1;
-            slot ^= 1u;
-            if (dE < thr) {
-                bf_sts_f64(xa, xn[0]);
-                bf_sts_f64(xa + cap8, xn[1]);
-                if constexpr (DIM == 3) bf_sts_f64(xa + 2 * cap8, xn[2]);
-                bf_sts_u8(sb + F.mv + (uint32_t)k, 1u);
-                Esum += dE;
-                nacc++;
-                if (tid == (k & (kBfThreads - 1))) {  // owner refreshes its register copy
-                    const int ki = k / kBfThreads;
-                    const uint32_t f = pack8(bf_fixed(xn[0], cs, fscale), bf_fixed(xn[1], cs, fscale), DIM == 3 ? bf_fixed(xn[2], cs, fscale) : 0u);
+            // ---- write moved particles back: canonical arrays (+ image counters) and the sorted copy, here and on the peers ----
+            const int bstart = st.base[0];
+            if (A.n_peers) {  // a peer's arrays may only be written once it has rebuilt its cell lists for this sweep
+                if (tid < A.n_peers && !(rebuilt_ok & (1u << tid))) wait_for(A.flags + kFlagRebuilt + A.peer_rank[tid], A.stamp, A.error, true);
+                __syncthreads();
+                rebuilt_ok = 0xFFu;
+            }
+            uint32_t keeps = 0;  // peers that keep the plane of this cell (they need the sorted copy and done[])
+            for (int p = 0; p < A.n_peers; p++)
+                if (plane_kept(cc[0], A.peer_plane_lo[p], A.peer_plane_n[p], A.g.nc[0])) keeps |= 1u << p;
+            for (int k = tid; k < ncen; k += kBfThreads) {
+                if (!smem_raw[F.mv + k]) continue;
+                const int i = A.ids[bstart + k];
+                uint32_t q = 0;
 #pragma unroll
-                    for (int kk = 0; kk < KC; kk++) myq[kk] = kk == ki ? f : myq[kk];
+                for (int a = 0; a < DIM; a++) {
+                    const double rnew = sr[a * CAP + k];
+                    const double r0 = __ldcg(A.rs + (size_t)a * ns_ + bstart + k);
+                    int w;
+                    const double xnew = wrap1(__ldcg(A.x + (size_t)a * A.N + i) + (rnew - r0), A.g.L[a], w);
+                    const int im = __ldcg(A.img + (size_t)a * A.N + i) + w;
+                    A.rs[(size_t)a * ns_ + bstart + k] = rnew;
+                    A.x[(size_t)a * A.N + i] = xnew;
+                    if (w) A.img[(size_t)a * A.N + i] = im;
+                    q |= cell_byte(rnew, 64.0 / A.g.cs[a]) << (8 * a);
+                    for (int p = 0; p < A.n_peers; p++) {
+                        A.peer_x[p][(size_t)a * A.N + i] = xnew;
+                        if (w) A.peer_img[p][(size_t)a * A.N + i] = im;
+                        if (keeps & (1u << p)) A.peer_rs[p][(size_t)a * ns_ + bstart + k] = rnew;
+                    }
+                }
+                A.qs[bstart + k] = q;
+                for (int p = 0; p < A.n_peers; p++)
+                    if (keeps & (1u << p)) A.peer_qs[p][bstart + k] = q;
+            }
+            if (tid == 0) {
+                A.cellE[cell] = Esum;
+                A.cell_acc[cell] = nacc;
+                for (int p = 0; p < A.n_peers; p++) {
+                    A.peer_cellE[p][cell] = Esum;
+                    A.peer_cacc[p][cell] = nacc;
                 }
             }
-        }
-    }
-    __syncthreads();
-    // write moved particles back: canonical arrays (+ image counters) and the sorted copy
-    for (int k = tid; k < ncen; k += kBfThreads) {
-        if (!smem_raw[F.mv + k]) continue;
-        const int i = A.ids[bstart + k];
-#pragma unroll
-        for (int a = 0; a < DIM; a++) {
-            const double xold = A.xs[(size_t)a * A.N + bstart + k];
-            const double r0 = in_frame(xold, A.g.shift[a], A.g.L[a], A.g.cs[a], cc[a]);
-            int w;
-            const double xnew = wrap1(xold + (sr[a * CAP + k] - r0), A.g.L[a], w);
-            const int im = A.img[(size_t)a * A.N + i] + w;
-            A.xs[(size_t)a * A.N + bstart + k] = xnew;
-            A.x[(size_t)a * A.N + i] = xnew;
-            if (w) A.img[(size_t)a * A.N + i] = im;
-            for (int p = 0; p < A.n_peers; p++) {
-                A.peer_xs[p][(size_t)a * A.N + bstart + k] = xnew;
-                A.peer_x[p][(size_t)a * A.N + i] = xnew;
-                if (w) A.peer_img[p][(size_t)a * A.N + i] = im;
+            // ---- publish: this cell is done for this sweep (system-wide only if a peer keeps its plane; the pushes into the
+            // canonical state of the other peers are fenced once, when the CTA leaves) ----
+            if (keeps) __threadfence_system(); else __threadfence();
+            __syncthreads();
+            if (tid == 0) {
+                *(volatile uint32_t *)(A.done + cell) = A.stamp;
+                for (int p = 0; p < A.n_peers; p++)
+                    if (keeps & (1u << p)) *(volatile uint32_t *)(A.peer_done[p] + cell) = A.stamp;
             }
+        } else if (tid == 0) {
+            *(volatile uint32_t *)(A.done + cell) = A.stamp;  // overflow: reported by the host, nobody may hang on this cell
+            for (int p = 0; p < A.n_peers; p++) *(volatile uint32_t *)(A.peer_done[p] + cell) = A.stamp;
         }
     }
-    if (tid == 0) {
-        A.cellE[cell] = Esum;
-        A.cell_acc[cell] = nacc;
-        for (int p = 0; p < A.n_peers; p++) {
-            A.peer_cellE[p][cell] = Esum;
-            A.peer_cacc[p][cell] = nacc;
-        }
-    }
-    if (A.n_peers) __threadfence_system();
-}
-
-// (Fusing this barrier into the colour kernels -- last CTA signals, every CTA of the next colour waits -- was tried and
-// measured 6 % slower on 2 GPUs: the system-scope fence + counter per CTA costs more than the launch it saves.)
-// Inter-GPU barrier between colour phases: every rank stores `epoch` into its slot of every peer's flag array
-// (NVLink peer store, after a system fence so the sweep kernel's pushes are visible first), then spins on its own
-// flag array until all ranks have arrived.  Bounded spin: a peer that never arrives raises an error flag
-// instead of hanging the GPU.
-__global__ void k_peer_barrier(volatile uint32_t *local_flags, uint32_t *const *peer_flags, int rank, int world, uint32_t epoch,
-                               int *error) {
-    const int t = threadIdx.x;
-    if (t < world) {
+    // the CTA that leaves last tells every peer that this rank's sweep (all its pushes) is complete
+    if (A.n_peers) {
         __threadfence_system();
-        volatile uint32_t *dst = peer_flags[t] + rank;
-        *dst = epoch;
-        __threadfence_system();
-        unsigned long long spins = 0;
-        while ((int32_t)(local_flags[t] - epoch) < 0) {
-            if (++spins > 50000000ull) {
-                atomicExch(error, 3);
-                break;
-            }
+        __syncthreads();
+        if (tid == 0 && atomicAdd(A.work + 1, 1) == (int)gridDim.x - 1) {
+            __threadfence_system();
+            for (int p = 0; p < A.n_peers; p++) *(volatile uint32_t *)(A.peer_flags[p] + kFlagSwept + A.rank) = A.stamp;
         }
     }
 }
@@ -919,11 +888,11 @@ __global__ void __launch_bounds__(kBoxThreads) k_box_pair_histogram(const __grid
         cc[1] = l % A.g.nc[1];
         cc[0] = l / A.g.nc[1];
     }
-    const int ncand = load_stencil<DIM>(A, cc, &st, sr, ssp);
+    const int ncand = load_stencil<DIM, kBoxThreads>(A, cc, &st, sr, ssp, A.cap, [](int, uint32_t) {});
     if (ncand < 0) return;
     // particle ids of the candidates (to count every unordered pair once: only id_i < id_j)
     for (int s = 0; s < Stencil<DIM>::NST; s++) {
-        const int b = A.start[st.cell[s]], n = st.off[s + 1] - st.off[s];
+        const int b = st.base[s], n = st.cnt[s];
         for (int p = tid; p < n; p += kBoxThreads) sid[st.off[s] + p] = A.ids[b + p];
     }
     __syncthreads();
@@ -951,18 +920,24 @@ __global__ void __launch_bounds__(kBoxThreads) k_box_pair_histogram(const __grid
         if (sh[k]) atomicAdd(&hist[k], (unsigned long long)sh[k]);
 }
 
-// deterministic reduction of per-cell values: out[0] (+)= scale * sum(cellE), acc[0] += sum(cell_acc)
-__global__ void k_box_reduce(const double *__restrict__ cellE, const uint32_t *__restrict__ cell_acc, int n, double scale,
-                             int accumulate, double *outE, unsigned long long *out_acc) {
+// Deterministic reduction of per-cell values: out[0] (+)= scale * sum(cellE), acc[0] += sum(cell_acc).  Every CTA sums a
+// fixed chunk of 1024 cells in a fixed order; the CTA that finishes last adds the partial sums in chunk order, so the
+// result does not depend on the number of GPUs or on timing.  With peers, waits first until every rank has finished the
+// sweep (their per-cell values have landed here).
+__global__ void __launch_bounds__(1024) k_box_reduce(const __grid_constant__ BoxArgs A, uint32_t wait_stamp, int with_acc, double scale,
+                                                     int accumulate, double *partE, unsigned long long *partA, int *ticket, double *outE,
+                                                     unsigned long long *out_acc) {
     __shared__ double s_e[32];
     __shared__ unsigned long long s_a[32];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
-    double e = 0.0;
-    unsigned long long a = 0;
-    for (int k = tid; k < n; k += blockDim.x) {
-        e += cellE[k];
-        if (cell_acc) a += cell_acc[k];
+    __shared__ int s_last;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (A.n_peers && wait_stamp) {
+        if (tid < A.n_peers) wait_for(A.flags + kFlagSwept + A.peer_rank[tid], wait_stamp, A.error, true);
+        __syncthreads();
     }
+    const int k = blockIdx.x * 1024 + tid;
+    double e = k < A.g.ncell ? __ldcg(A.cellE + k) : 0.0;
+    unsigned long long a = (with_acc && k < A.g.ncell) ? __ldcg(A.cell_acc + k) : 0ull;
     e = warp_sum(e);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
@@ -974,12 +949,27 @@ __global__ void k_box_reduce(const double *__restrict__ cellE, const uint32_t *_
     if (tid == 0) {
         double te = 0.0;
         unsigned long long ta = 0;
-        for (int w = 0; w < nwarp; w++) {
+        for (int w = 0; w < 32; w++) {
             te += s_e[w];
             ta += s_a[w];
         }
+        partE[blockIdx.x] = te;
+        partA[blockIdx.x] = ta;
+        __threadfence();
+        s_last = atomicAdd(ticket, 1) == (int)gridDim.x - 1;
+    }
+    __syncthreads();
+    if (s_last && tid == 0) {
+        __threadfence();
+        double te = 0.0;
+        unsigned long long ta = 0;
+        for (int b = 0; b < (int)gridDim.x; b++) {
+            te += __ldcg(partE + b);
+            ta += __ldcg(partA + b);
+        }
         outE[0] = (accumulate ? outE[0] : 0.0) + scale * te;
         if (out_acc) out_acc[0] += ta;
+        *ticket = 0;
     }
 }
 
@@ -993,31 +983,35 @@ struct BoxState {
     int N = 0, dim = 0, ns = 0, cap = 0;
     double rcut_max = 0.0, T = 1.0, sigma = 0.05;
     unsigned long long seed = 0;
-    uint32_t sweep = 0;
+    uint32_t sweep = 0;   // sweeps since pmc_seed: RNG counter
+    uint32_t stamp = 0;   // sweeps since creation: never reset, tags done[] and the inter-GPU flags
     bool geom_ready = false, model_ready = false;
-    double *x = nullptr, *xs = nullptr, *par = nullptr, *cellE = nullptr, *eloc = nullptr, *energy = nullptr, *etmp = nullptr;
-    int32_t *img = nullptr, *ids = nullptr, *start = nullptr, *cursor = nullptr, *count = nullptr, *cid = nullptr;
+    // canonical state + everything a peer GPU writes into: ONE allocation (one IPC handle, fixed offsets on every rank)
+    unsigned char *shared_block = nullptr;
+    size_t shared_bytes = 0;
+    double *x = nullptr, *rs = nullptr, *cellE = nullptr;
+    int32_t *img = nullptr;
+    uint32_t *qs = nullptr, *cell_acc = nullptr, *done = nullptr, *bar_flags = nullptr;
+    // local only
+    double *par = nullptr, *eloc = nullptr, *energy = nullptr, *etmp = nullptr, *partE = nullptr;
+    unsigned long long *partA = nullptr;
+    int32_t *ids = nullptr, *start = nullptr, *cursor = nullptr, *count = nullptr, *cid = nullptr;
     uint8_t *sp = nullptr, *sps = nullptr;
-    uint32_t *cell_acc = nullptr;
     unsigned long long *acc_total = nullptr;
-    int *flags = nullptr;  // [0] bad input, [1] overflow
+    int *flags = nullptr;  // [0] bad input (1, 2) / peer timeout (3), [1] overflow (1 stencil, 2 plane)
+    int *work = nullptr;   // [0] next unit, [1] finished units, [2] finalize ticket, [3] reduce ticket
     double *raw = nullptr;
     long long *rsp = nullptr;
     int64_t calls = 0;
     int64_t launches = 0;
-    size_t smem = 0;
-    int fast_kc = 0;        // > 0: k_box_sweep_fast<.., KC> is used for the sweeps
-    // multi-GPU replicas (box_peer_attach)
+    size_t smem = 0;        // energy / histogram kernels
+    int fast_kc = 0;        // > 0: k_box_sweep_all<.., KC> with the prefilter
+    size_t sweep_smem = 0;
+    int sweep_grid = 0;     // persistent CTAs of the sweep kernel
+    int plane_cap = 0, ncell_alloc = 0;
+    // multi-GPU
     int rank = 0, world = 1;
-    uint32_t *bar_flags = nullptr;      // [8] local barrier flags
-    uint32_t **d_peer_flags = nullptr;  // device array [world] of flag arrays (self included)
-    uint32_t epoch = 0;
-    unsigned char *shared_block = nullptr;  // ONE allocation [x | xs | img | cellE | cell_acc | flags]: one IPC handle
-    size_t shared_bytes = 0;
     unsigned char *peer_block[PMC_MAX_PEERS + 1] = {};  // opened IPC mapping of every rank's block (self = local)
-    size_t fast_smem = 0;
-    int ncell_alloc = 0;
-    int32_t *cid_blocksum = nullptr;  // [ceil(ncell/1024)] partial sums of the cell-count scan
 };
 
 namespace {
@@ -1047,9 +1041,9 @@ int bdispatch(int dim, int model, F &&f) {
 
 // Everything a peer GPU writes into lives in ONE allocation: one IPC handle, fixed offsets on every rank.
 struct BlockLayout {
-    size_t x, xs, img, cellE, cacc, flags, total;
+    size_t x, img, rs, qs, cellE, cacc, done, flags, total;
 };
-BlockLayout block_layout(int N, int dim, int ncell) {
+BlockLayout block_layout(int N, int dim, int ncell, size_t nslot) {
     BlockLayout l;
     size_t o = 0;
     auto take = [&](size_t bytes) {
@@ -1058,16 +1052,48 @@ BlockLayout block_layout(int N, int dim, int ncell) {
         return p;
     };
     l.x = take(sizeof(double) * dim * (size_t)N);
-    l.xs = take(sizeof(double) * dim * (size_t)N);
     l.img = take(sizeof(int32_t) * dim * (size_t)N);
+    l.rs = take(sizeof(double) * dim * nslot);
+    l.qs = take(sizeof(uint32_t) * nslot);
     l.cellE = take(sizeof(double) * (size_t)ncell);
     l.cacc = take(sizeof(uint32_t) * (size_t)ncell);
-    l.flags = take(256);
+    l.done = take(sizeof(uint32_t) * (size_t)ncell);
+    l.flags = take(sizeof(uint32_t) * kFlagWords);
     l.total = o;
     return l;
 }
 
+int active_cells(const BoxState *b) {
+    int n = 1;
+    for (int a = 0; a < b->dim; a++) n *= b->g.nc[a] / 2;
+    return n;
+}
+
+// Rank r of `world` sweeps the active cells [lo, hi) of every colour (x-major order: a slab of the box, cut to
+// balance) and keeps cell lists for the planes those cells and their stencils touch.
+void rank_share(const BoxState *b, int r, int world, int &lo, int &hi, int &plane_lo, int &plane_n) {
+    const int nactive = active_cells(b), nx = b->g.nc[0];
+    lo = (int)((int64_t)nactive * r / world);
+    hi = (int)((int64_t)nactive * (r + 1) / world);
+    if (world == 1 || hi <= lo) {
+        plane_lo = 0;
+        plane_n = nx;
+        return;
+    }
+    const int app = nactive / (nx / 2);  // active cells per x-plane of active cells
+    const int ax_lo = lo / app, ax_hi = (hi - 1) / app;
+    plane_lo = 2 * ax_lo - 1;          // active x-coordinate 2h or 2h+1, stencil +-1
+    plane_n = 2 * (ax_hi - ax_lo) + 4;
+    if (plane_n >= nx) {
+        plane_lo = 0;
+        plane_n = nx;
+    } else if (plane_lo < 0) {
+        plane_lo += nx;
+    }
+}
+
 void fill_args(BoxState *b, BoxArgs &a) {
+    memset(&a, 0, sizeof a);
     a.g = b->g;
     a.N = b->N;
     a.ns = b->ns;
@@ -1075,10 +1101,13 @@ void fill_args(BoxState *b, BoxArgs &a) {
     a.x = b->x;
     a.img = b->img;
     a.sp = b->sp;
-    a.xs = b->xs;
+    a.plane_cap = b->plane_cap;
+    a.rs = b->rs;
+    a.qs = b->qs;
     a.sps = b->sps;
     a.ids = b->ids;
     a.start = b->start;
+    a.count = b->count;
     a.par = b->par;
     a.T = b->T;
     a.sigma = (float)b->sigma;
@@ -1087,56 +1116,77 @@ void fill_args(BoxState *b, BoxArgs &a) {
     a.cellE = b->cellE;
     a.cell_acc = b->cell_acc;
     a.eloc = b->eloc;
+    a.error = b->flags;
     a.overflow = b->flags + 1;
-    a.cta_offset = 0;
+    a.stamp = b->stamp;
+    a.done = b->done;
+    a.work = b->work;
+    a.rank = b->rank;
+    a.flags = b->bar_flags;
+    int lo, hi;
+    rank_share(b, b->rank, b->world, lo, hi, a.plane_lo, a.plane_n);
+    a.cell_lo = lo;
+    a.cell_n = hi - lo;
     a.n_peers = 0;
     if (b->world > 1) {
-        const BlockLayout bl = block_layout(b->N, b->dim, b->g.ncell);
+        const size_t nslot = (size_t)b->g.nc[0] * b->plane_cap;
+        const BlockLayout bl = block_layout(b->N, b->dim, b->g.ncell, nslot);
         for (int r = 0; r < b->world; r++) {
             if (r == b->rank) continue;
             const int p = a.n_peers++;
             unsigned char *blk = b->peer_block[r];
+            int plo, phi;
+            rank_share(b, r, b->world, plo, phi, a.peer_plane_lo[p], a.peer_plane_n[p]);
+            a.peer_rank[p] = r;
             a.peer_x[p] = (double *)(blk + bl.x);
-            a.peer_xs[p] = (double *)(blk + bl.xs);
             a.peer_img[p] = (int32_t *)(blk + bl.img);
+            a.peer_rs[p] = (double *)(blk + bl.rs);
+            a.peer_qs[p] = (uint32_t *)(blk + bl.qs);
             a.peer_cellE[p] = (double *)(blk + bl.cellE);
             a.peer_cacc[p] = (uint32_t *)(blk + bl.cacc);
+            a.peer_done[p] = (uint32_t *)(blk + bl.done);
+            a.peer_flags[p] = (uint32_t *)(blk + bl.flags);
         }
     }
 }
 
-// K1: (re)build the cell-sorted arrays for grid origin g.shift
-int build_cells(BoxState *b) {
+// K1: (re)build the cell lists of this rank's planes for grid origin g.shift.  whole_box: every plane (energies and
+// histograms look at all cells); wait_stamp / announce_stamp: the inter-GPU handshake around a sweep's rebuild.
+int build_cells(BoxState *b, bool whole_box, uint32_t wait_stamp, uint32_t announce_stamp) {
     const int N = b->N, nb = (N + 255) / 256;
+    BoxArgs A;
+    fill_args(b, A);
+    if (whole_box) {
+        A.plane_lo = 0;
+        A.plane_n = b->g.nc[0];
+    }
     BCU(cudaMemsetAsync(b->count, 0, sizeof(int32_t) * b->g.ncell, b->stream));
     if (b->dim == 3)
-        k_box_count<3><<<nb, 256, 0, b->stream>>>(b->x, N, b->g, b->cid, b->count);
+        k_box_count<3><<<nb, 256, 0, b->stream>>>(A, b->cid, wait_stamp);
     else
-        k_box_count<2><<<nb, 256, 0, b->stream>>>(b->x, N, b->g, b->cid, b->count);
-    {
-        const int nsb = (b->g.ncell + 1023) / 1024;
-        k_box_scan_local<<<nsb, 1024, 0, b->stream>>>(b->count, b->start, b->cid_blocksum, b->g.ncell);
-        k_box_scan_apply<<<nsb, 1024, 0, b->stream>>>(b->start, b->cursor, b->cid_blocksum, b->g.ncell);
-    }
-    k_box_scatter<<<nb, 256, 0, b->stream>>>(b->cid, b->start, b->cursor, N, b->ids);
-    const int nbc = (b->g.ncell + 7) / 8;  // one warp per cell, 8 warps per CTA
+        k_box_count<2><<<nb, 256, 0, b->stream>>>(A, b->cid, wait_stamp);
+    k_box_scan_plane<<<A.plane_n, 1024, 0, b->stream>>>(A, b->cursor);
+    k_box_scatter<<<nb, 256, 0, b->stream>>>(b->cid, b->start, b->cursor, N, b->ids, b->flags + 1);
+    const int cells = A.plane_n * (b->g.ncell / b->g.nc[0]);
+    const int nbc = (cells + 7) / 8;  // one warp per cell, 8 warps per CTA
     if (b->dim == 3)
-        k_box_finalize<3><<<nbc, 256, 0, b->stream>>>(b->start, b->ids, b->g.ncell, N, b->x, b->sp, b->xs, b->sps);
+        k_box_finalize<3><<<nbc, 256, 0, b->stream>>>(A, b->work + 2, announce_stamp);
     else
-        k_box_finalize<2><<<nbc, 256, 0, b->stream>>>(b->start, b->ids, b->g.ncell, N, b->x, b->sp, b->xs, b->sps);
+        k_box_finalize<2><<<nbc, 256, 0, b->stream>>>(A, b->work + 2, announce_stamp);
     BCU(cudaGetLastError());
-    b->launches += 5;
+    b->launches += 4;
     return PMC_OK;
 }
 
 int setup_geometry(BoxState *b, const double *box3) {
     if (!b->model_ready) return bfail(PMC_ERR_STATE, "pmc_set_model must precede pmc_upload in PMC_MODE_BOX");
-    b->g.ncell = 1;
+    Geom g{};
+    g.ncell = 1;
     for (int a = 0; a < 3; a++) {
-        b->g.nc[a] = 1;
-        b->g.L[a] = 1.0;
-        b->g.cs[a] = 1.0;
-        b->g.shift[a] = 0.0;
+        g.nc[a] = 1;
+        g.L[a] = 1.0;
+        g.cs[a] = 1.0;
+        g.shift[a] = 0.0;
     }
     double occ = (double)b->N;
     for (int a = 0; a < b->dim; a++) {
@@ -1146,11 +1196,14 @@ int setup_geometry(BoxState *b, const double *box3) {
         if (n < 2)
             return bfail(PMC_ERR_UNSUPPORTED, "box side %g holds fewer than 2 cells of side >= rcut %g: use PMC_MODE_CHAINS",
                          box3[a], b->rcut_max);
-        b->g.nc[a] = n;
-        b->g.L[a] = box3[a];
-        b->g.cs[a] = box3[a] / (double)n;
-        b->g.ncell *= n;
+        g.nc[a] = n;
+        g.L[a] = box3[a];
+        g.cs[a] = box3[a] / (double)n;
+        g.ncell *= n;
     }
+    if (b->world > 1 && (g.ncell != b->g.ncell || memcmp(g.nc, b->g.nc, sizeof g.nc) != 0))
+        return bfail(PMC_ERR_STATE, "the cell grid changed after peers were attached");
+    b->g = g;
     occ /= (double)b->g.ncell;
     const int nst = b->dim == 3 ? 27 : 9;
     int cap = (int)(occ * nst * 1.5) + 96;
@@ -1158,7 +1211,7 @@ int setup_geometry(BoxState *b, const double *box3) {
     b->cap = cap;
     b->smem = sizeof(double) * (size_t)b->dim * cap + 2 * (size_t)cap + 16;
     if (b->smem > 200 * 1024) return bfail(PMC_ERR_UNSUPPORTED, "stencil of %d candidates does not fit shared memory", cap);
-    // fast sweep kernel: cubic cells, stencil fits kBfThreads x KC register candidates
+    // prefilter kernel: cubic cells, stencil fits kBfThreads x KC register candidates
     b->fast_kc = 0;
     bool cubic = true;
     for (int a = 1; a < b->dim; a++) cubic = cubic && b->g.cs[a] == b->g.cs[0];
@@ -1172,47 +1225,62 @@ int setup_geometry(BoxState *b, const double *box3) {
     }
     if (b->fast_kc) {
         b->cap = kBfThreads * b->fast_kc;
-        b->fast_smem = bf_layout(b->dim, b->cap).total;
         b->smem = sizeof(double) * (size_t)b->dim * b->cap + 2 * (size_t)b->cap + 16;
     }
+    b->sweep_smem = bf_layout(b->dim, b->cap).total;
+    int sms = 0;
+    BCU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, b->cfg.device));
     int rc = bdispatch(b->dim, b->cfg.model_kind, [&](auto D, auto MDL) {
-        if (b->fast_kc) {
-            BCU(cudaFuncSetAttribute(k_box_sweep_fast<decltype(D)::value, decltype(MDL)::value, kBfKc0>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bf_layout(b->dim, kBfThreads * kBfKc0).total));
-            BCU(cudaFuncSetAttribute(k_box_sweep_fast<decltype(D)::value, decltype(MDL)::value, kBfKc1>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bf_layout(b->dim, kBfThreads * kBfKc1).total));
-            BCU(cudaFuncSetAttribute(k_box_sweep_fast<decltype(D)::value, decltype(MDL)::value, kBfKc2>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bf_layout(b->dim, kBfThreads * kBfKc2).total));
-            BCU(cudaFuncSetAttribute(k_box_sweep_fast<decltype(D)::value, decltype(MDL)::value, kBfKc3>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bf_layout(b->dim, kBfThreads * kBfKc3).total));
-        }
-        BCU(cudaFuncSetAttribute(k_box_sweep<decltype(D)::value, decltype(MDL)::value>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem));
-        BCU(cudaFuncSetAttribute(k_box_energy<decltype(D)::value, decltype(MDL)::value>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem));
+        constexpr int d = decltype(D)::value, mdl = decltype(MDL)::value;
+        int occb = 0;
+        auto prep = [&](auto kernel) {
+            BCU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->sweep_smem));
+            BCU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occb, kernel, kBfThreads, b->sweep_smem));
+            return (int)PMC_OK;
+        };
+        int r2;
+        if (b->fast_kc == kBfKc0) r2 = prep(k_box_sweep_all<d, mdl, kBfKc0>);
+        else if (b->fast_kc == kBfKc1) r2 = prep(k_box_sweep_all<d, mdl, kBfKc1>);
+        else if (b->fast_kc == kBfKc2) r2 = prep(k_box_sweep_all<d, mdl, kBfKc2>);
+        else if (b->fast_kc == kBfKc3) r2 = prep(k_box_sweep_all<d, mdl, kBfKc3>);
+        else r2 = prep(k_box_sweep_all<d, mdl, 0>);
+        if (r2) return r2;
+        if (occb < 1) return bfail(PMC_ERR_UNSUPPORTED, "the sweep kernel does not fit an SM (%zu B of shared memory)", b->sweep_smem);
+        b->sweep_grid = sms * occb;
+        BCU(cudaFuncSetAttribute(k_box_energy<d, mdl>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem));
         return (int)PMC_OK;
     });
     if (rc) return rc;
     if (b->ncell_alloc != b->g.ncell) {  // buffers survive re-uploads of the same geometry (peers map them)
-        if (b->world > 1) return bfail(PMC_ERR_STATE, "the cell grid changed after peers were attached");
-        for (void *p : {(void *)b->count, (void *)b->cursor, (void *)b->start, (void *)b->shared_block})
+        for (void *p : {(void *)b->count, (void *)b->cursor, (void *)b->start, (void *)b->shared_block, (void *)b->ids,
+                        (void *)b->sps, (void *)b->partE, (void *)b->partA})
             if (p) cudaFree(p);
-        b->count = b->cursor = b->start = nullptr;
+        b->count = b->cursor = b->start = b->ids = nullptr;
         b->shared_block = nullptr;
+        b->sps = nullptr;
+        b->partE = nullptr;
+        b->partA = nullptr;
+        // sorted slots are reserved per x-plane of cells: 1.5 x the mean plane occupancy (a lattice start puts 3 or 4
+        // lattice planes into a plane of cells); overflow is detected by the scan and reported
+        b->plane_cap = ((int)((double)b->N / b->g.nc[0] * 1.5) + 64 + 31) / 32 * 32;
+        const size_t nslot = (size_t)b->g.nc[0] * b->plane_cap;
         BCU(balloc(&b->count, b->g.ncell));
         BCU(balloc(&b->cursor, b->g.ncell));
         BCU(balloc(&b->start, b->g.ncell + 1));
-        if (b->cid_blocksum) cudaFree(b->cid_blocksum);
-        BCU(balloc(&b->cid_blocksum, (b->g.ncell + 1023) / 1024));
-        // everything a peer GPU writes into lives in ONE allocation, so one IPC handle and fixed offsets suffice
-        const BlockLayout bl = block_layout(b->N, b->dim, b->g.ncell);
+        BCU(balloc(&b->ids, nslot));
+        BCU(balloc(&b->sps, nslot));
+        BCU(balloc(&b->partE, (b->g.ncell + 1023) / 1024));
+        BCU(balloc(&b->partA, (b->g.ncell + 1023) / 1024));
+        const BlockLayout bl = block_layout(b->N, b->dim, b->g.ncell, nslot);
         BCU(balloc(&b->shared_block, bl.total));
         b->shared_bytes = bl.total;
         b->x = (double *)(b->shared_block + bl.x);
-        b->xs = (double *)(b->shared_block + bl.xs);
         b->img = (int32_t *)(b->shared_block + bl.img);
+        b->rs = (double *)(b->shared_block + bl.rs);
+        b->qs = (uint32_t *)(b->shared_block + bl.qs);
         b->cellE = (double *)(b->shared_block + bl.cellE);
         b->cell_acc = (uint32_t *)(b->shared_block + bl.cacc);
+        b->done = (uint32_t *)(b->shared_block + bl.done);
         b->bar_flags = (uint32_t *)(b->shared_block + bl.flags);
         BCU(cudaDeviceSynchronize());  // zero-fills ran on the legacy default stream
         b->ncell_alloc = b->g.ncell;
@@ -1225,15 +1293,27 @@ int check_overflow(BoxState *b) {
     int fl[2] = {0, 0};
     BCU(cudaMemcpyAsync(fl, b->flags, sizeof fl, cudaMemcpyDeviceToHost, b->stream));
     BCU(cudaStreamSynchronize(b->stream));
+    if (fl[1] == 2) return bfail(PMC_ERR_UNSUPPORTED, "an x-plane of cells holds more than %d particles (density too inhomogeneous)", b->plane_cap);
     if (fl[1]) return bfail(PMC_ERR_UNSUPPORTED, "a 3^d-cell neighbourhood holds more than %d particles (density too inhomogeneous)", b->cap);
-    if (fl[0] == 3) return bfail(PMC_ERR_CUDA, "inter-GPU barrier timed out: a peer rank did not arrive");
+    if (fl[0] == 3) return bfail(PMC_ERR_CUDA, "inter-GPU handshake timed out: a peer rank did not arrive");
+    return PMC_OK;
+}
+
+int reduce_cells(BoxState *b, const BoxArgs &A, uint32_t wait_stamp, bool sweep) {
+    const int nb = (b->g.ncell + 1023) / 1024;
+    if (sweep)
+        k_box_reduce<<<nb, 1024, 0, b->stream>>>(A, wait_stamp, 1, 1.0, 1, b->partE, b->partA, b->work + 3, b->energy, b->acc_total);
+    else
+        k_box_reduce<<<nb, 1024, 0, b->stream>>>(A, 0u, 0, 0.5, 0, b->partE, b->partA, b->work + 3, b->etmp, nullptr);
+    BCU(cudaGetLastError());
+    b->launches++;
     return PMC_OK;
 }
 
 // local energies (grid origin 0) -> eloc in particle order, etmp[0] = sum/2
 int compute_energy(BoxState *b) {
     for (int a = 0; a < 3; a++) b->g.shift[a] = 0.0;
-    int rc = build_cells(b);
+    int rc = build_cells(b, true, 0u, 0u);
     if (rc) return rc;
     BoxArgs A;
     fill_args(b, A);
@@ -1243,18 +1323,10 @@ int compute_energy(BoxState *b) {
         return (int)PMC_OK;
     });
     if (rc) return rc;
-    k_box_reduce<<<1, 1024, 0, b->stream>>>(b->cellE, nullptr, b->g.ncell, 0.5, 0, b->etmp, nullptr);
-    BCU(cudaGetLastError());
-    b->launches += 2;
+    b->launches++;
+    rc = reduce_cells(b, A, 0u, false);
+    if (rc) return rc;
     return check_overflow(b);
-}
-
-// one inter-GPU barrier on the context's stream
-int peer_barrier(BoxState *b) {
-    b->epoch++;
-    k_peer_barrier<<<1, 32, 0, b->stream>>>(b->bar_flags, b->d_peer_flags, b->rank, b->world, b->epoch, b->flags);
-    BCU(cudaGetLastError());
-    return PMC_OK;
 }
 
 }  // namespace
@@ -1268,7 +1340,7 @@ int box_pair_histogram(BoxState *b, int sa, int sb, double rmax, int nbins, unsi
     for (int a = 0; a < b->dim; a++)
         if (rmax > b->g.cs[a]) return bfail(PMC_ERR_INVALID, "rmax %g exceeds the cell side %g of the device cell list", rmax, b->g.cs[a]);
     for (int a = 0; a < 3; a++) b->g.shift[a] = 0.0;
-    int rc = build_cells(b);
+    int rc = build_cells(b, true, 0u, 0u);
     if (rc) return rc;
     BoxArgs A;
     fill_args(b, A);
@@ -1299,8 +1371,9 @@ int box_peer_attach(BoxState *b, int rank, int world, const unsigned char *handl
     if (world < 1 || world > PMC_MAX_PEERS + 1 || rank < 0 || rank >= world)
         return bfail(PMC_ERR_INVALID, "rank %d / world %d out of range (max %d ranks)", rank, world, PMC_MAX_PEERS + 1);
     if (b->world > 1) return bfail(PMC_ERR_STATE, "peers are already attached");
-    const BlockLayout bl = block_layout(b->N, b->dim, b->g.ncell);
-    std::vector<uint32_t *> flags(world);
+    if (b->stamp != 0) return bfail(PMC_ERR_STATE, "attach the peers before the first sweep (all ranks count sweeps alike)");
+    if (world > active_cells(b) / 2)
+        return bfail(PMC_ERR_UNSUPPORTED, "%d ranks for %d active cells per colour: the box is too small to split", world, active_cells(b));
     for (int r = 0; r < world; r++) {
         if (r == rank) {
             b->peer_block[r] = b->shared_block;
@@ -1311,14 +1384,9 @@ int box_peer_attach(BoxState *b, int rank, int world, const unsigned char *handl
             BCU(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
             b->peer_block[r] = (unsigned char *)ptr;
         }
-        flags[r] = (uint32_t *)(b->peer_block[r] + bl.flags);
     }
-    if (b->d_peer_flags) cudaFree(b->d_peer_flags);
-    BCU(cudaMalloc((void **)&b->d_peer_flags, sizeof(uint32_t *) * world));
-    BCU(cudaMemcpy(b->d_peer_flags, flags.data(), sizeof(uint32_t *) * world, cudaMemcpyHostToDevice));
     b->rank = rank;
     b->world = world;
-    b->epoch = 0;
     return PMC_OK;
 }
 
@@ -1331,16 +1399,15 @@ int box_create(BoxState **out, const pmc_config &cfg) {
     b->dim = cfg.dim;
     b->ns = cfg.n_species;
     const size_t N = b->N, d = b->dim;
-    cudaError_t e = balloc(&b->ids, N);
-    if (e == cudaSuccess) e = balloc(&b->cid, N);
+    cudaError_t e = balloc(&b->cid, N);
     if (e == cudaSuccess) e = balloc(&b->sp, N);
-    if (e == cudaSuccess) e = balloc(&b->sps, N);
     if (e == cudaSuccess) e = balloc(&b->eloc, N);
     if (e == cudaSuccess) e = balloc(&b->par, (size_t)PMC_MAX_SPECIES * PMC_MAX_SPECIES * PMC_NPAR);
     if (e == cudaSuccess) e = balloc(&b->energy, 1);
     if (e == cudaSuccess) e = balloc(&b->etmp, 1);
     if (e == cudaSuccess) e = balloc(&b->acc_total, 1);
     if (e == cudaSuccess) e = balloc(&b->flags, 2);
+    if (e == cudaSuccess) e = balloc(&b->work, 4);
     if (e == cudaSuccess) e = cudaMalloc((void **)&b->raw, sizeof(double) * d * N);
     if (e == cudaSuccess) e = cudaMalloc((void **)&b->rsp, sizeof(long long) * N);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();  // zero-fills ran on the legacy default stream
@@ -1357,7 +1424,7 @@ void box_destroy(BoxState *b) {
     for (int r = 0; r < b->world; r++)
         if (r != b->rank && b->peer_block[r]) cudaIpcCloseMemHandle(b->peer_block[r]);
     void *bufs[] = {b->shared_block, b->ids, b->cid, b->sp, b->sps, b->eloc, b->par, b->energy, b->etmp, b->acc_total,
-                    b->flags, b->raw, b->rsp, b->count, b->cursor, b->start, b->d_peer_flags, b->cid_blocksum};
+                    b->flags, b->work, b->raw, b->rsp, b->count, b->cursor, b->start, b->partE, b->partA};
     for (void *p : bufs)
         if (p) cudaFree(p);
     delete b;
@@ -1438,15 +1505,16 @@ int box_energy(BoxState *b, double *e_out) {
     return PMC_OK;
 }
 
-// One sweep = N trials: fresh random grid origin, rebuild the cell list, then the 2^d colours in a
-// random order.  n_trials is rounded up to whole sweeps.
+// One sweep = N trials: fresh random grid origin, rebuild this rank's cell lists, then ONE persistent kernel that runs
+// the 2^d colours in a random order (dataflow between cells, no barriers), then the deterministic reduction of the per-
+// cell energy changes.  n_trials is rounded up to whole sweeps.  Four small launches + one sweep kernel + one reduction
+// per sweep; with peers the only inter-GPU waits are flag polls inside these kernels (rebuild: peers finished the previous
+// sweep; first push into a peer: it finished its rebuild; cell: its neighbours; reduction: peers finished this sweep).
 int box_run(BoxState *b, int64_t n_trials) {
     if (!b->geom_ready) return bfail(PMC_ERR_STATE, "nothing uploaded yet");
     const int64_t sweeps = (n_trials + b->N - 1) / b->N;
     const int ncol = 1 << b->dim;
     const uint32_t k0 = (uint32_t)b->seed, k1 = (uint32_t)(b->seed >> 32);
-    int nactive = 1;
-    for (int a = 0; a < b->dim; a++) nactive *= b->g.nc[a] / 2;
     for (int64_t s = 0; s < sweeps; s++) {
         const Philox4 r = philox4x32_10(b->sweep, 0u, 0u, 2u, k0, k1);
         const Philox4 r2 = philox4x32_10(b->sweep, 1u, 0u, 2u, k0, k1);
@@ -1458,45 +1526,39 @@ int box_run(BoxState *b, int64_t n_trials) {
             order[k] = order[j];
             order[j] = t;
         }
-        int rc = build_cells(b);
+        const uint32_t prev = b->stamp;
+        b->stamp++;
+        int rc = build_cells(b, false, prev, b->stamp);
         if (rc) return rc;
         BoxArgs A;
         fill_args(b, A);
-        // multi-GPU: this rank sweeps an even share of the colour's active cells (same-colour cells never interact,
-        // so any split is valid); peers must have finished their rebuild before anyone pushes into their arrays
-        const int lo = (int)((int64_t)nactive * b->rank / b->world), hi = (int)((int64_t)nactive * (b->rank + 1) / b->world);
-        A.cta_offset = lo;
-        if (b->world > 1) {
-            rc = peer_barrier(b);
+        for (int k = 0; k < ncol; k++) {
+            A.order[k] = order[k];
+            A.phase_of[order[k]] = k;
+        }
+        BCU(cudaMemsetAsync(b->work, 0, 2 * sizeof(int), b->stream));
+        const int grid = std::min(b->sweep_grid, ncol * A.cell_n);
+        if (grid > 0) {
+            rc = bdispatch(b->dim, b->cfg.model_kind, [&](auto D, auto MDL) {
+                constexpr int d = decltype(D)::value, mdl = decltype(MDL)::value;
+                if (b->fast_kc == kBfKc0)
+                    k_box_sweep_all<d, mdl, kBfKc0><<<grid, kBfThreads, b->sweep_smem, b->stream>>>(A);
+                else if (b->fast_kc == kBfKc1)
+                    k_box_sweep_all<d, mdl, kBfKc1><<<grid, kBfThreads, b->sweep_smem, b->stream>>>(A);
+                else if (b->fast_kc == kBfKc2)
+                    k_box_sweep_all<d, mdl, kBfKc2><<<grid, kBfThreads, b->sweep_smem, b->stream>>>(A);
+                else if (b->fast_kc == kBfKc3)
+                    k_box_sweep_all<d, mdl, kBfKc3><<<grid, kBfThreads, b->sweep_smem, b->stream>>>(A);
+                else
+                    k_box_sweep_all<d, mdl, 0><<<grid, kBfThreads, b->sweep_smem, b->stream>>>(A);
+                BCU(cudaGetLastError());
+                return (int)PMC_OK;
+            });
             if (rc) return rc;
         }
-        rc = bdispatch(b->dim, b->cfg.model_kind, [&](auto D, auto MDL) {
-            constexpr int d = decltype(D)::value, mdl = decltype(MDL)::value;
-            for (int k = 0; k < ncol; k++) {
-                if (hi > lo) {
-                    if (b->fast_kc == kBfKc0)
-                        k_box_sweep_fast<d, mdl, kBfKc0><<<hi - lo, kBfThreads, b->fast_smem, b->stream>>>(A, order[k]);
-                    else if (b->fast_kc == kBfKc1)
-                        k_box_sweep_fast<d, mdl, kBfKc1><<<hi - lo, kBfThreads, b->fast_smem, b->stream>>>(A, order[k]);
-                    else if (b->fast_kc == kBfKc2)
-                        k_box_sweep_fast<d, mdl, kBfKc2><<<hi - lo, kBfThreads, b->fast_smem, b->stream>>>(A, order[k]);
-                    else if (b->fast_kc == kBfKc3)
-                        k_box_sweep_fast<d, mdl, kBfKc3><<<hi - lo, kBfThreads, b->fast_smem, b->stream>>>(A, order[k]);
-                    else
-                        k_box_sweep<d, mdl><<<hi - lo, kBoxThreads, b->smem, b->stream>>>(A, order[k]);
-                }
-                BCU(cudaGetLastError());
-                if (b->world > 1) {
-                    const int brc = peer_barrier(b);
-                    if (brc) return brc;
-                }
-            }
-            return (int)PMC_OK;
-        });
+        rc = reduce_cells(b, A, b->stamp, true);
         if (rc) return rc;
-        k_box_reduce<<<1, 1024, 0, b->stream>>>(b->cellE, b->cell_acc, b->g.ncell, 1.0, 1, b->energy, b->acc_total);
-        BCU(cudaGetLastError());
-        b->launches += ncol + 1 + (b->world > 1 ? ncol + 1 : 0);
+        b->launches += 1;
         b->sweep++;
         b->calls += b->N;
     }
