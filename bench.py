@@ -1,27 +1,37 @@
 #!/usr/bin/env python
 """bench.py -- attempted Metropolis moves per second on the BASELINE.json workloads.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload chains|box] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload all|chains|box] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...   (N > 1)
 
 One "step" = one pass of the hot path over the whole batch: every chain advanced by --sweeps sweeps
-(1 sweep = N_particles attempted moves) in one pmc_run call.  Prints ONE JSON line (rank 0).
+(1 sweep = N_particles attempted moves) in one pmc_run call.  Prints ONE JSON line (rank 0):
+
+  value / e2e / roofline / clocks   BASELINE config 2: KA N=1000 x 4096 independent chains PER GPU (weak scaling)
+  strong                            the same 4096 chains in TOTAL, split over the N GPUs (strong scaling)
+  box                               BASELINE config 3: ONE KA box of N=2^20 particles, checkerboard sweeps, the cell
+                                    grid cut into N slabs with NVLink halo pushes (strong scaling)
+  cpu_baseline                      the oracle (C restatement of the reference CPU algorithm, one chain per host thread)
+                                    on this box's cores, bounded sample, N = 1 only
 
   value      device-resident throughput: state already in HBM, K steps bracketed by CUDA events on the
              launch stream (max over ranks), L2 flushed between steps.
-  e2e        the same metric through the C ABI with HOST buffers: every step uploads all chain states from
-             pinned host memory (pmc_upload + pmc_init_energy), runs the sweeps and downloads energies and
-             full states (pmc_energy + pmc_download).  The chains are held by --e2e-contexts library contexts
-             on separate streams, so one context's copies overlap another's sweeps (same chains, same bytes).
-  roofline   pair-evaluation roofline of the sweep kernel (FP64 CUDA-core pipe): achieved =
-             moves/s x P x F with P = reference-equivalent candidate pairs per move and F flops per pair,
-             against the DFMA burst peak measured in this run (MEASURED_PEAKS.json has no FP64 figure).
-  cpu_baseline  the oracle (C restatement of the reference CPU algorithm, one chain per host thread) timed
-             on this box's cores on a bounded sample of the same workload.
+  e2e        the same metric through the C ABI with HOST buffers: every step uploads all states from pinned host
+             memory (pmc_upload + pmc_init_energy), runs the sweeps and downloads energies and full states
+             (pmc_energy + pmc_download).  The chains are held by --e2e-contexts library contexts on separate
+             streams, so one context's copies overlap another's sweeps (same chains, same bytes).
+  roofline   pair-evaluation roofline of the sweep kernel (FP64 CUDA-core pipe):
+               frac         reference-equivalent: moves/s x P x F with P = candidate pairs the REFERENCE evaluates per
+                            move and F flops per pair, over the DFMA burst peak measured in this run
+               frac_actual  the fp64 work the kernel really does: candidates that pass the integer prefilter, counted
+                            on the device in this run (pmc_work_counters), x the fp64 flops per survivor of the SASS
+               issue_frac   moves/s x warp-instructions per move (committed ncu capture) over the issue slots of the
+                            GPU at the clock sampled in this run
 """
 from __future__ import annotations
 
 import argparse
+import csv
 import json
 import os
 import subprocess
@@ -42,15 +52,11 @@ WORK = {
     "chains": dict(P=2000.0, F=21.0 + 9.0 * 0.079),   # KA N=1000: 3x3x3 cells = whole box, old + new position
     "box": dict(P=1032.0, F=21.0 + 9.0 * 0.152),      # KA N=2^20: 27-cell stencil ~516 candidates, x2
 }
-
-
-# figures of ONE launch from the committed `ncu --set full` captures (profiles/README.md)
-NCU_CHAINS = {"source": "profiles/r01_final_k_chain_sweep_spec_ncu_full_summary.csv", "dram_read_bytes": 105.62e6,
-              "dram_write_bytes": 42.96e6, "warp_instructions_per_move": 778, "issue_active_pct": 64.9,
-              "fp64_pipe_pct": 30.6, "alu_pipe_pct": 47.5, "registers": 80, "ctas_per_sm": 6}
-NCU_BOX = {"source": "profiles/r01_final_k_box_sweep_fast_ncu_full_summary.csv", "dram_read_bytes": 35.76e6,
-           "dram_write_bytes": 0.21e6, "issue_active_pct": 66.6, "fp64_pipe_pct": 31.7, "alu_pipe_pct": 33.3,
-           "registers": 64, "ctas_per_sm": 8}
+# fp64 flops the kernels spend on ONE surviving candidate (old and new position together), counted in the SASS of the
+# survivor loops (DFMA = 2): chains 14 DADD + 18 DFMA + 8 DMUL + 8 DSETP (minimum image per axis), box 8 DADD + 16 DFMA
+# + 10 DMUL + 2 DSETP (cell frame, no minimum image).  DESIGN.md section 4.
+FLOP_PER_SURVIVOR = {"chains": 14 + 2 * 18 + 8 + 8, "box": 8 + 2 * 16 + 10 + 2}
+NCU_INDEX = os.path.join(ROOT, "profiles", "ncu_index.json")
 
 
 def parse_args():
@@ -59,10 +65,11 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="chains", choices=["chains", "box"])
-    ap.add_argument("--chains", type=int, default=4096, help="chains PER GPU (weak scaling)")
-    ap.add_argument("--particles", type=int, default=0, help="particles per system (default 1000 / 2^20)")
-    ap.add_argument("--sweeps", type=int, default=0, help="sweeps per step (default 10 chains / 2 box)")
+    ap.add_argument("--workload", default="all", choices=["all", "chains", "box"])
+    ap.add_argument("--chains", type=int, default=4096, help="chains PER GPU of the weak-scaling leg; the strong leg splits this many over all GPUs")
+    ap.add_argument("--particles", type=int, default=0, help="particles per chain (default 1000)")
+    ap.add_argument("--box-particles", type=int, default=1 << 20)
+    ap.add_argument("--sweeps", type=int, default=0, help="sweeps per step (default 10 chains / 8 box)")
     ap.add_argument("--equil", type=int, default=100, help="untimed equilibration sweeps from the lattice")
     ap.add_argument("--threads", type=int, default=0, help="CTA size of the sweep kernel (0 = library default)")
     ap.add_argument("--temperature", type=float, default=1.0)
@@ -71,7 +78,8 @@ def parse_args():
     ap.add_argument("--prefilter", type=int, default=0, help="0 = fixed-point prefilter (default), -1 = visit all candidates in fp64")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--cpu-sweeps", type=int, default=200)
+    ap.add_argument("--no-strong", action="store_true")
+    ap.add_argument("--cpu-sweeps", type=int, default=600)
     ap.add_argument("--e2e-contexts", type=int, default=4,
                     help="chains workload, e2e leg: the chains are held by this many library contexts on separate streams, so "
                          "that one context's host<->device copies overlap another's sweeps (1 = a single context)")
@@ -119,37 +127,57 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
 
 
-def workload_config(args):
-    from particlesmc_b200.synthetic import ka_lattice
-    if args.workload == "chains":
+def workload_name(args, kind):
+    if kind == "chains":
         N = args.particles or 1000
-        sweeps = args.sweeps or 10
-        M = args.chains
-        name = f"KA LJ 80:20 N={N} rho=1.2 T={args.temperature} x {M} independent chains per GPU, Displacement sigma=0.05"
-    else:
-        N = args.particles or (1 << 20)
-        sweeps = args.sweeps or 8
-        M = 1
-        name = f"single KA LJ 80:20 box N={N} rho=1.2 T={args.temperature}, checkerboard cell sweeps, Displacement sigma=0.05"
-    pos, sp, box = ka_lattice(N, 1.2, seed=0)
-    return N, M, sweeps, name, pos, sp, box
+        return f"KA LJ 80:20 N={N} rho=1.2 T={args.temperature} x {args.chains} independent chains per GPU, Displacement sigma=0.05"
+    return f"single KA LJ 80:20 box N={args.box_particles} rho=1.2 T={args.temperature}, checkerboard cell sweeps, Displacement sigma=0.05"
+
+
+def config_dict(args):
+    """The SAME dictionary for both arms (--impl ours / reference): it names the workload, nothing arm-specific."""
+    kinds = ["chains", "box"] if args.workload == "all" else [args.workload]
+    cfg = {"workload": workload_name(args, kinds[0]), "particles_per_chain": args.particles or 1000,
+           "chains_per_gpu": args.chains, "sweeps_per_step": args.sweeps or 10, "temperature": args.temperature,
+           "equilibration_sweeps": args.equil, "seed": 42, "precision": args.precision,
+           "l2": "256 MiB buffer zeroed between steps (L2 flush)"}
+    if "box" in kinds and len(kinds) > 1:
+        cfg["also"] = workload_name(args, "box")
+    return cfg
+
+
+def ncu_figures(kind):
+    """Figures of ONE launch of the dominant kernel from the committed `ncu --set full` summary (profiles/ncu_index.json
+    names the CSV, the kernel it must hold and the moves of that launch).  None if the record is missing or stale."""
+    try:
+        ent = json.load(open(NCU_INDEX))[kind]
+        rows = list(csv.DictReader(open(os.path.join(ROOT, ent["csv"]))))
+        val = {r["metric"]: r["value"] for r in rows if r["launch"] == "0"}
+        if ent["kernel"] not in val["Kernel Name"]:
+            return None
+        f = lambda k: float(val[k].replace(",", ""))
+        return {"source": ent["csv"], "kernel": val["Kernel Name"], "moves_per_launch": ent["moves_per_launch"],
+                "warp_instructions_per_move": f("smsp__inst_executed.sum") / ent["moves_per_launch"],
+                "dram_read_bytes": f("dram__bytes_read.sum") * 1e6, "dram_write_bytes": f("dram__bytes_write.sum") * 1e6,
+                "issue_active_pct": f("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                "fp64_pipe_pct": f("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"),
+                "alu_pipe_pct": f("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
+                "registers": int(f("launch__registers_per_thread")), "duration_ms": f("gpu__time_duration.sum")}
+    except Exception:
+        return None
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_arm(args, N, sweeps, pos, sp, box, cores=None):
+def cpu_reference_arm(args, N, pos, sp, box, cores=None, one_chain=False):
     """The oracle on the host cores: one independent chain per thread (the reference's `parallel=true`)."""
     from oracle import oracle as O
     from particlesmc_b200 import models as M
     cores = cores or os.cpu_count() or 1
     par = M.flatten_model_matrix(M.KobAndersen())
     pool = O.make_pool([dict(kind="displacement", prob=1.0, sigma=0.05)])
-    if args.workload == "chains":
-        systems = [O.OracleSystem(pos, sp, box, args.temperature, M.MODEL_LJ, par, O.LINKEDLIST) for _ in range(cores)]
-        sample = f"{cores} chains (one per host thread) x {sweeps} sweeps of N={N}"
-    else:
-        systems = [O.OracleSystem(pos, sp, box, args.temperature, M.MODEL_LJ, par, O.LINKEDLIST)]
-        sample = f"1 chain (the box is one sequential chain on the CPU) x {sweeps} sweeps of N={N}"
-    return O, systems, pool, sample
+    n = 1 if one_chain else cores
+    systems = [O.OracleSystem(pos, sp, box, args.temperature, M.MODEL_LJ, par, O.LINKEDLIST) for _ in range(n)]
+    return O, systems, pool
 
 
 def time_cpu(O, systems, pool, n_trials, t0):
@@ -161,18 +189,17 @@ def time_cpu(O, systems, pool, n_trials, t0):
 
 
 def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (its C restatement: Julia is not available on this
+    box) on all host cores, on the chains workload of the `ours` arm; each step is a bounded sample of it."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    N, M, sweeps, name, pos, sp, box = workload_config(args)
-    ref_sweeps = max(1, min(sweeps, 4)) if args.workload == "chains" else 1
-    if args.workload == "box":
-        # bounded sample: a 65536-particle box has the same 27-cell stencil occupancy as the 2^20 one
-        from particlesmc_b200.synthetic import ka_lattice
-        if N > 65536:
-            N = 65536
-            pos, sp, box = ka_lattice(N, 1.2, seed=0)
-    O, systems, pool, sample = cpu_reference_arm(args, N, ref_sweeps, pos, sp, box)
+    from particlesmc_b200.synthetic import ka_lattice
+    N = args.particles or 1000
+    sweeps = args.sweeps or 10
+    pos, sp, box = ka_lattice(N, 1.2, seed=0)
+    ref_sweeps = max(1, min(sweeps, 4))
+    O, systems, pool = cpu_reference_arm(args, N, pos, sp, box)
     t0 = 0
     for _ in range(args.warmup):
         time_cpu(O, systems, pool, max(1, N // 10), t0)
@@ -184,11 +211,12 @@ def run_reference(args):
         tot_t += dt
         tot_moves += len(systems) * ref_sweeps * N
     value = tot_moves / tot_t
+    sample = (f"{len(systems)} chains (one per host thread) x {ref_sweeps} sweeps of N={N} per step: a bounded sample of the "
+              f"{args.chains} x {sweeps}-sweep step of the GPU arm (chains are independent, throughput does not depend on their number)")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": name, "note": "C restatement of the reference CPU algorithm (oracle/), not Julia: "
-                       "Julia and Arianna.jl are not available on this box"},
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(args),
+            "note": "C restatement of the reference CPU algorithm (oracle/), not Julia: Julia and Arianna.jl are not available on this box",
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -196,30 +224,32 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
-def run_ours(args):
+class Env:
+    pass
+
+
+def measure(env, args, kind, Mc, strong_chains=False):
+    """One workload on this rank's GPU: device-resident throughput, e2e through host buffers, work counters.
+    kind = 'chains' (Mc chains on this rank) or 'box' (one box over all ranks)."""
     import torch
     import torch.distributed as dist
     from particlesmc_b200 import _lib as L
     from particlesmc_b200 import models as M
-    from particlesmc_b200.device import DeviceContext, measure_fma_peak
+    from particlesmc_b200.device import DeviceContext
+    from particlesmc_b200.synthetic import ka_lattice
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-
-    N, Mc, sweeps, name, pos, sp, box = workload_config(args)
+    rank, world, local, dev = env.rank, env.world, env.local, env.dev
+    box_mode = kind == "box"
+    N = args.box_particles if box_mode else (args.particles or 1000)
+    sweeps = args.sweeps or (8 if box_mode else 10)
+    pos, sp, box = ka_lattice(N, 1.2, seed=0)
     par = M.flatten_model_matrix(M.KobAndersen())
-    mode = L.MODE_CHAINS if args.workload == "chains" else L.MODE_BOX
+    mode = L.MODE_BOX if box_mode else L.MODE_CHAINS
+    prec = L.MIXED if (args.precision == "mixed" and not box_mode) else L.FP64
     # chains are keyed by their GLOBAL index: rank r holds chains [r*Mc, (r+1)*Mc)
     ctx = DeviceContext(Mc, N, 3, 2, M.MODEL_LJ, mode=mode, device=local, chain_offset=rank * Mc, threads=args.threads,
-                        prefilter=args.prefilter, precision=L.MIXED if args.precision == "mixed" else L.FP64)
-    stream = torch.cuda.Stream(device=dev)  # a non-default stream shared by torch events and the library
-    torch.cuda.set_stream(stream)
-    ctx.set_stream(stream.cuda_stream)
+                        prefilter=args.prefilter, precision=prec)
+    ctx.set_stream(env.stream.cuda_stream)
     ctx.set_model(par)
 
     # pinned host buffers in the caller's (reference) layout
@@ -241,8 +271,8 @@ def run_ours(args):
         ctx.download_raw(h_pos.data_ptr(), h_sp.data_ptr(), 0, Mc)
 
     upload()
-    strong = args.workload == "box" and world > 1
-    if strong:  # one box replicated on every GPU: colour phases split over ranks, moves pushed over NVLink peer memory
+    split = box_mode and world > 1
+    if split:  # one box, its cell grid cut into one slab per rank; moves pushed over NVLink peer memory
         from particlesmc_b200.sharding import attach_box_peers
         attach_box_peers(ctx)
     ctx.set_moves([dict(kind="displacement", prob=1.0, sigma=0.05)])
@@ -250,7 +280,6 @@ def run_ours(args):
     trials_per_step = sweeps * N
     if args.equil > 0:
         ctx.run(args.equil * N)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def barrier():
         if world > 1:
@@ -262,84 +291,77 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     for _ in range(max(args.warmup, 3)):
-        flush.zero_()
+        env.flush.zero_()
         ctx.run(trials_per_step, sync=False)
     barrier()
     # nvidia-smi needs ~0.2 s to deliver its first sample: keep the GPU under the same load (untimed steps, all
-    # ranks alike) until it is up, so that the clock record covers the timed region even when a step is short
-    extra = 0
-    t_wait = time.perf_counter()
-    while world == 1 and rank == 0 and sampler.proc and not sampler.rows and time.perf_counter() - t_wait < 1.0:
-        ctx.run(trials_per_step, sync=True)
-        extra += 1
-    n_load = 0
+    # ranks alike) until it is up, so that the clock record covers the timed region even when a step is short.
+    # Every rank must run the same number of sweeps of the split box, so the count comes from an all-reduced step time.
+    t_s = time.perf_counter()
+    ctx.run(trials_per_step, sync=True)
+    tt = torch.tensor([time.perf_counter() - t_s], dtype=torch.float64, device=dev)
     if world > 1:
-        # several ranks (and, for the box, the device barriers between them) must issue identical launch sequences: the
-        # number of untimed load steps is derived from an all-reduced step time, the same on every rank
-        t_s = time.perf_counter()
-        ctx.run(trials_per_step, sync=True)
-        tt = torch.tensor([time.perf_counter() - t_s], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        n_load = int(min(400, np.ceil(0.35 / max(float(tt.item()), 1e-4))))
-        for _ in range(n_load):
-            ctx.run(trials_per_step, sync=False)
-        ctx.sync()
-    n_pre = len(sampler.rows)
+    n_load = int(min(400, np.ceil(0.35 / max(float(tt.item()), 1e-4))))
+    for _ in range(n_load):
+        ctx.run(trials_per_step, sync=False)
+    ctx.sync()
     launches0 = ctx.launch_count()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    kernel_ms = []
     barrier()
     ev[0].record()
     for _ in range(args.steps):
-        flush.zero_()
+        env.flush.zero_()
         ctx.run(trials_per_step, sync=False)
     ev[1].record()
     barrier()
     ms_total = ev[0].elapsed_time(ev[1])
     launches = ctx.launch_count() - launches0
-    if rank == 0 and world == 1 and sampler.proc and len(sampler.rows) == n_pre:  # very short timed region:
-        t_wait = time.perf_counter()                                                # extend the load until one more sample
-        while len(sampler.rows) == n_pre and time.perf_counter() - t_wait < 0.5:
-            ctx.run(trials_per_step, sync=True)
-    if world > 1:  # keep the same load up until the sampler has seen it (same count on every rank)
-        for _ in range(max(1, n_load // 2)):
-            ctx.run(trials_per_step, sync=False)
-        ctx.sync()
+    for _ in range(max(1, n_load // 2)):  # keep the same load up until the sampler has seen it (same count on every rank)
+        ctx.run(trials_per_step, sync=False)
+    ctx.sync()
     clocks = sampler.stop() if rank == 0 else None
     if clocks is not None:
         clocks["note"] = "sampled every 50 ms from the last warm-up step through the timed region (same load)"
     # per-launch duration of the sweep kernel(s), CUDA events recorded inside the library on the same stream
+    kernel_ms = []
     for _ in range(args.steps):
         ctx.run(trials_per_step, sync=True)
         kernel_ms.append(ctx.last_run_ms())
+    # work really done, counted on the device during one more (untimed) step
+    ctx.work_counters(1)
+    ctx.run(trials_per_step, sync=True)
+    survivors, evaluations = ctx.work_counters(0)
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
-    moves_per_step = (1 if strong else world) * Mc * trials_per_step
+    moves_local = Mc * trials_per_step // (world if split else 1)   # moves this rank's GPU processes per step
+    moves_per_step = Mc * trials_per_step * (1 if split else world)  # whole job
     value = moves_per_step * args.steps / (ms_total * 1e-3)
 
     # ---- end to end through the C ABI with host buffers -------------------------------------------------
     e2e = None
     if not args.no_e2e:
-        K = args.e2e_contexts if (args.workload == "chains" and args.e2e_contexts > 1 and Mc % args.e2e_contexts == 0) else 1
+        K = args.e2e_contexts if (not box_mode and args.e2e_contexts > 1 and Mc % args.e2e_contexts == 0) else 1
+        parts = []
         if K > 1:
             # the same chains (same global indices, same seed) split over K contexts with their own streams: while one
             # context sweeps, the next one's upload and the previous one's download use the copy engines
             Mk = Mc // K
-            parts = []
             for k in range(K):
                 c = DeviceContext(Mk, N, 3, 2, M.MODEL_LJ, mode=mode, device=local, chain_offset=rank * Mc + k * Mk,
-                                  threads=args.threads, prefilter=args.prefilter,
-                                  precision=L.MIXED if args.precision == "mixed" else L.FP64)
+                                  threads=args.threads, prefilter=args.prefilter, precision=prec)
                 st = torch.cuda.Stream(device=dev)
                 c.set_stream(st.cuda_stream)
                 c.set_model(par)
                 parts.append((c, st, k * Mk))
+
             def up(c, o):
                 c.upload_raw(h_pos.data_ptr() + o * N * 3 * 8, h_sp.data_ptr() + o * N * 8, h_box.data_ptr() + o * 3 * 8,
                              h_T.data_ptr() + o * 8, 0, Mk)
                 c.init_energy()
+
             def down(c, o):
                 c.energy_into(h_E.data_ptr() + o * 8)
                 c.download_raw(h_pos.data_ptr() + o * N * 3 * 8, h_sp.data_ptr() + o * N * 8, 0, Mk)
@@ -347,6 +369,7 @@ def run_ours(args):
                 up(c, o)
                 c.set_moves([dict(kind="displacement", prob=1.0, sigma=0.05)])
                 c.seed(42)
+
             def e2e_step():
                 for c, st, o in parts:
                     up(c, o)
@@ -374,9 +397,8 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         h2d = h_pos.numel() * 8 + h_sp.numel() * 8 + h_box.numel() * 8 + h_T.numel() * 8
         d2h = h_pos.numel() * 8 + h_sp.numel() * 8 + h_E.numel() * 8
-        if K > 1:
-            for c, st, o in parts:
-                c.close()
+        for c, st, o in parts:
+            c.close()
         e2e = {"value": moves_per_step * args.steps / (float(t.item()) * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "contexts": K,
                "energy_per_particle_mean": float(h_E.numpy().mean() / N)}
@@ -385,68 +407,119 @@ def run_ours(args):
     e_run, e_tot = ctx.energy(), ctx.total_energy()
     drift = float(np.max(np.abs(e_run - e_tot) / np.abs(e_tot)))
     calls, acc = ctx.counters()
+    ctx.close()
+    return dict(kind=kind, N=N, Mc=Mc, sweeps=sweeps, value=value, ms_total=ms_total, launches=int(launches), clocks=clocks,
+                kernel_ms=float(np.mean(kernel_ms)), e2e=e2e, survivors_per_move=survivors / max(moves_local, 1),
+                evaluations_per_move=evaluations / max(moves_local, 1), moves_local=moves_local, split=split,
+                checks={"energy_bookkeeping_rel_drift": drift, "acceptance": float(acc.sum() / max(calls.sum(), 1)),
+                        "energy_per_particle": float(e_tot.mean() / N)})
+
+
+def roofline(env, args, m, peak64, peak32):
+    kind = m["kind"]
+    work = WORK[kind]
+    mixed = args.precision == "mixed" and kind == "chains"
+    peak = peak32 if mixed else peak64
+    per_gpu = m["moves_local"] / (m["kernel_ms"] * 1e-3)  # moves/s of this GPU while the kernel runs
+    achieved = per_gpu * work["P"] * work["F"] / 1e12
+    actual = per_gpu * m["survivors_per_move"] * FLOP_PER_SURVIVOR[kind] / 1e12
+    ncu = ncu_figures(kind) if (args.precision == "fp64" and args.prefilter == 0) else None
+    clk = (m["clocks"] or {}).get("sm_mhz") or 1965.0
+    issue_frac = None
+    if ncu:
+        issue_frac = per_gpu * ncu["warp_instructions_per_move"] / (env.sms * 4 * clk * 1e6)
+    if kind == "chains":
+        kernel = ("k_chain_sweep_spec<MIXED>" if mixed else "k_chain_sweep_spec") if args.prefilter == 0 else \
+            ("k_chain_sweep_fast" if args.prefilter == 1 else "k_chain_sweep")
+    else:
+        kernel = "k_box_sweep_all (8 colours in one launch) + 4 cell-rebuild kernels + reduction"
+    peaks = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    return {"bound": "fp32_pipe" if mixed else "fp64_pipe", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+            "frac": achieved / peak, "frac_actual": actual / peak, "issue_frac": issue_frac,
+            "traffic": (ncu["dram_read_bytes"] + ncu["dram_write_bytes"]) if ncu else None, "kernel": kernel,
+            "kernel_ms_per_launch": m["kernel_ms"], "launches_per_step": m["launches"] / args.steps,
+            "survivors_per_move": m["survivors_per_move"], "evaluations_per_move": m["evaluations_per_move"],
+            "fp64_flop_per_survivor": FLOP_PER_SURVIVOR[kind],
+            "work_model": f"frac: reference-equivalent, P={work['P']:.0f} candidate pairs/move x F={work['F']:.2f} flop/pair "
+                          "(SURVEY.md 8d); frac_actual: candidates that passed the integer prefilter (counted on the device in "
+                          "this run) x fp64 flops per survivor of the kernel's SASS; issue_frac: warp-instructions per move of "
+                          "the committed ncu capture x moves/s over SMs x 4 schedulers x sampled clock",
+            "note": "the kernel rejects ~91 % of the reference's candidates with a 3-instruction integer test and evaluates only the "
+                    "survivors in fp64, so `frac` is not a pipe utilisation -- `frac_actual` and `issue_frac` are",
+            "ncu": ncu,
+            "peak_source": "FMA burst micro-benchmark run in this process (pmc_measure_fma_peak); MEASURED_PEAKS.json holds no "
+                           "FP64/FP32 CUDA-core figure",
+            "fp64_fma_peak_tflops": peak64, "fp32_fma_peak_tflops": peak32,
+            "hbm_algorithmic_gbs": 2.0 * m["Mc"] * m["N"] * 28 / (m["kernel_ms"] * 1e-3) / 1e9 / (env.world if m["split"] else 1),
+            "hbm_peak_gbs": json.load(open(peaks))["hbm_gbs"] if os.path.exists(peaks) else 6650.0}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from particlesmc_b200.device import measure_fma_peak
+
+    env = Env()
+    env.rank = int(os.environ.get("RANK", "0"))
+    env.world = int(os.environ.get("WORLD_SIZE", "1"))
+    env.local = int(os.environ.get("LOCAL_RANK", "0"))
+    if env.world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", env.local))
+    torch.cuda.set_device(env.local)
+    env.dev = torch.device("cuda", env.local)
+    env.sms = torch.cuda.get_device_properties(env.local).multi_processor_count
+    env.stream = torch.cuda.Stream(device=env.dev)  # a non-default stream shared by torch events and the library
+    torch.cuda.set_stream(env.stream)
+    env.flush = torch.empty(256 << 20, dtype=torch.uint8, device=env.dev)  # > 126 MB L2
+    rank, world = env.rank, env.world
+
+    kinds = ["chains", "box"] if args.workload == "all" else [args.workload]
+    res = {}
+    if "chains" in kinds:
+        res["chains"] = measure(env, args, "chains", args.chains)
+        if world > 1 and not args.no_strong and args.chains % world == 0:
+            res["strong"] = measure(env, args, "chains", args.chains // world, strong_chains=True)
+    if "box" in kinds:
+        res["box"] = measure(env, args, "box", 1)
 
     if rank == 0:
-        work = WORK[args.workload]
-        kms = float(np.mean(kernel_ms))
-        peak64 = measure_fma_peak(True, local)
-        peak32 = measure_fma_peak(False, local)
-        achieved = Mc * trials_per_step * work["P"] * work["F"] / (kms * 1e-3) / 1e12
-        # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch, and the issue-slot figures of that launch, from the
-        # committed ncu --set full captures (profiles/r01_final_*_ncu_full_summary.csv: 4096 chains x N=1000 x 1 sweep;
-        # one colour of N=2^20); null for any other shape
-        traffic, ncu = None, None
-        if args.workload == "chains" and Mc == 4096 and N == 1000 and args.precision == "fp64" and args.prefilter == 0:
-            traffic = NCU_CHAINS["dram_read_bytes"] + NCU_CHAINS["dram_write_bytes"]
-            ncu = NCU_CHAINS
-        elif args.workload == "box" and N == (1 << 20) and args.prefilter >= 0:
-            traffic = NCU_BOX["dram_read_bytes"] + NCU_BOX["dram_write_bytes"]
-            ncu = NCU_BOX
-        mixed = args.precision == "mixed"
-        peak = peak32 if mixed else peak64
-        kernel = (("k_chain_sweep_spec<MIXED>" if args.prefilter == 0 else "k_chain_sweep_mixed") if mixed else
-                  "k_chain_sweep_spec" if args.prefilter == 0 else
-                  "k_chain_sweep_fast" if args.prefilter == 1 else "k_chain_sweep") if args.workload == "chains" \
-            else "k_box_sweep_fast (8 colours + cell rebuild)"
-        roofline = {"bound": "fp32_pipe" if mixed else "fp64_pipe", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                    "frac": achieved / peak, "traffic": traffic,
-                    "kernel": kernel,
-                    "kernel_ms_per_launch": kms, "launches_per_step": launches / args.steps,
-                    "work_model": f"reference-equivalent: P={work['P']:.0f} candidate pairs/move x F={work['F']:.2f} flop/pair (SURVEY.md 8d)",
-                    "note": "achieved counts the REFERENCE's pair evaluations per move; the kernel rejects ~91 % of the candidates "
-                            "with a 3-instruction integer test and evaluates only the survivors in fp64, so frac can exceed the "
-                            "pipe utilisation (ncu: see `ncu`) -- the kernel is bound by instruction issue, not by the FMA pipe",
-                    "ncu": ncu,
-                    "peak_source": "FMA burst micro-benchmark run in this process (pmc_measure_fma_peak); "
-                                   "MEASURED_PEAKS.json holds no FP64/FP32 CUDA-core figure",
-                    "fp64_fma_peak_tflops": peak64, "fp32_fma_peak_tflops": peak32,
-                    "hbm_algorithmic_gbs": 2.0 * Mc * N * 28 / (kms * 1e-3) / 1e9,
-                    "hbm_peak_gbs": json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
-                    if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0}
+        peak64 = measure_fma_peak(True, env.local)
+        peak32 = measure_fma_peak(False, env.local)
+        head = res[kinds[0]]
         cpu = None
-        if not args.no_cpu_baseline:
-            N_c, pos_c, sp_c, box_c = N, pos, sp, box
-            if args.workload == "box" and N > 65536:
-                from particlesmc_b200.synthetic import ka_lattice
-                N_c = 65536
-                pos_c, sp_c, box_c = ka_lattice(N_c, 1.2, seed=0)
-            cs = args.cpu_sweeps if args.workload == "chains" else 2
-            O, systems, pool, sample = cpu_reference_arm(args, N_c, cs, pos_c, sp_c, box_c)
-            time_cpu(O, systems, pool, N_c // 4, 0)
-            v, dt, cores = time_cpu(O, systems, pool, cs * N_c, N_c)
-            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "seconds": dt}
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-                "scaling": "strong" if strong else "weak", "vs_baseline": None,
+        if not args.no_cpu_baseline and world == 1 and "chains" in res:
+            from particlesmc_b200.synthetic import ka_lattice
+            N = res["chains"]["N"]
+            pos, sp, box = ka_lattice(N, 1.2, seed=0)
+            O, systems, pool = cpu_reference_arm(args, N, pos, sp, box)
+            time_cpu(O, systems, pool, N // 4, 0)
+            v, dt, cores = time_cpu(O, systems, pool, args.cpu_sweeps * N, N)
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "seconds": dt,
+                   "sample": f"{len(systems)} chains (one per host thread) x {args.cpu_sweeps} sweeps of N={N}"}
+
+        def sub(m, scaling):
+            return {"value": m["value"], "unit": UNIT, "scaling": scaling, "ms_per_step": m["ms_total"] / args.steps,
+                    "sweeps_per_step": m["sweeps"], "ms_per_sweep": m["ms_total"] / args.steps / m["sweeps"],
+                    "systems_per_gpu": m["Mc"], "particles": m["N"], "e2e": m["e2e"], "gpu_launches": m["launches"],
+                    "clocks": m["clocks"], "roofline": roofline(env, args, m, peak64, peak32), "checks": m["checks"]}
+
+        line = {"metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": head["ms_total"] / args.steps, "higher_is_better": True,
+                "scaling": "strong" if head["split"] else "weak", "vs_baseline": None,
                 "dtype": "f64" if args.precision == "fp64" else "f32 pair terms / f64 accumulate", "data": "synthetic",
-                "config": {"workload": name, "sweeps_per_step": sweeps, "trials_per_step_per_gpu": Mc * trials_per_step // (world if strong else 1),
-                           "equilibration_sweeps": args.equil, "cta_threads": args.threads or "default",
-                           "l2": "256 MiB buffer zeroed between steps (L2 flush)", "seed": 42},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-                "checks": {"energy_bookkeeping_rel_drift": drift, "acceptance": float(acc.sum() / max(calls.sum(), 1)),
-                           "energy_per_particle": float(e_tot.mean() / N)}}
+                "config": config_dict(args), "clocks": head["clocks"], "e2e": head["e2e"],
+                "gpu_launches": sum(m["launches"] for m in res.values()),
+                "roofline": roofline(env, args, head, peak64, peak32), "cpu_baseline": cpu, "checks": head["checks"]}
+        if "strong" in res:
+            line["strong"] = sub(res["strong"], "strong")
+            line["strong"]["note"] = f"the same {args.chains} chains in total, {args.chains // world} per GPU"
+        elif "chains" in res and world == 1:
+            line["strong"] = {"value": res["chains"]["value"], "unit": UNIT, "scaling": "strong",
+                              "note": "N = 1: identical to the headline run"}
+        if "box" in res and kinds[0] != "box":
+            line["box"] = sub(res["box"], "strong")
+            line["box"]["workload"] = workload_name(args, "box")
         print(json.dumps(line))
-    ctx.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -1,11 +1,16 @@
-nvidia-smi -L
-timeout 300 python -m pytest tests/test_gpu_multirank.py -x -q > gpurun_out/ab5_tests.log 2>&1; tail -5 gpurun_out/ab5_tests.log
-timeout 300 python bench.py --workload box --no-cpu-baseline --no-e2e --steps 5 --warmup 3 > gpurun_out/ab5_box1.json 2>gpurun_out/ab5_box1.err
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --workload box --no-cpu-baseline --no-e2e --steps 5 --warmup 3 > gpurun_out/ab5_box2.json 2>gpurun_out/ab5_box2.err; tail -5 gpurun_out/ab5_box2.err
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/ab6_tests.log 2>&1; tail -5 gpurun_out/ab6_tests.log
+( time timeout 900 python bench.py > gpurun_out/ab6_bench.json 2>gpurun_out/ab6_bench.err ) 2>&1 | grep real; tail -3 gpurun_out/ab6_bench.err
+( time timeout 600 python bench.py --impl reference --steps 5 --warmup 3 > gpurun_out/ab6_ref.json 2>gpurun_out/ab6_ref.err ) 2>&1 | grep real
 python - <<'PY'
 import json
-for f in ['gpurun_out/ab5_box1.json','gpurun_out/ab5_box2.json']:
+for f in ['gpurun_out/ab6_bench.json','gpurun_out/ab6_ref.json']:
   try:
-    d=json.loads(open(f).read().strip().split('\n')[-1]); print(f, '%.4g'%d['value'], 'e2e', d['e2e'] and '%.4g'%d['e2e']['value'], d['ms_per_step'], d['gpu_launches'], d['checks'])
+    d=json.loads(open(f).read().strip().split('\n')[-1])
+    print(f, '%.4g'%d['value'], 'e2e %.4g'%d['e2e']['value'], d['ms_per_step'], d['gpu_launches'])
+    if 'roofline' in d:
+        r=d['roofline']; print('  roofline', r['frac'], r['frac_actual'], r['issue_frac'], r['survivors_per_move'], r['evaluations_per_move'])
+    if 'box' in d:
+        b=d['box']; r=b['roofline']; print('  box %.4g'%b['value'], 'e2e %.4g'%b['e2e']['value'], b['ms_per_sweep'], r['frac'], r['frac_actual'], r['issue_frac'], r['survivors_per_move'], r['evaluations_per_move'])
+    print('  cpu', d.get('cpu_baseline'))
   except Exception as e: print(f, 'FAILED', e)
 PY

@@ -187,14 +187,23 @@ int pmc_counters(pmc_ctx *ctx, int64_t *calls, int64_t *accepted);
 int64_t pmc_launch_count(const pmc_ctx *ctx);
 /* Device time of the most recent pmc_run, measured with CUDA events on the launch stream (ms). */
 int pmc_last_run_ms(pmc_ctx *ctx, float *ms);
+/* Work actually done by the sweep kernels, counted on the device (bench.py's roofline.frac_actual): enable = 1 resets
+ * and starts counting in the following pmc_run calls, 0 stops and reads, 2 reads.  out[0] = candidate particles that
+ * passed the integer prefilter and were evaluated in fp64 (each against the old and the new position), out[1] = trial
+ * evaluations including those a speculative round had to repeat, out[2..3] = 0.  Counting costs a few instructions per
+ * trial, so it is off by default; implemented by the default kernels of both modes (speculative chains, box sweep). */
+int pmc_work_counters(pmc_ctx *ctx, int32_t enable, uint64_t *out /*[4]*/);
 
 /* ---- multi-GPU, single large box (PMC_MODE_BOX) ---------------------------------------------------------- */
-/* Every rank (one process per GPU) holds a replica of the box, uploads the SAME state and uses the same seed.
- * Each colour phase of a sweep is split evenly over the ranks; a rank pushes its accepted moves into all
- * peers' replicas with peer stores over NVLink from inside the sweep kernel, and a device-side flag barrier
- * separates the phases -- no host round trip and no collective library on the data path.  The result is
- * bit-identical to the single-GPU run.  Call order: pmc_upload on every rank, exchange the 64-byte handles
- * (any host channel, e.g. an all-gather), pmc_box_peer_attach, then pmc_init_energy / pmc_run as usual. */
+/* The cell grid is cut into slabs along x, one per rank (one process per GPU).  Every rank uploads the SAME state
+ * and uses the same seed; it keeps the particle-order positions of the whole box, but cell lists only for its slab
+ * plus the halo planes its stencils reach, and sweeps only its slab's cells.  Accepted moves are stored from inside
+ * the sweep kernel straight into the peers' memory over NVLink (positions: every peer; cell-list entries and the
+ * per-cell completion stamps: the peers whose halo holds the cell); a cell waits only for the stamps of its own
+ * neighbour cells, and sweeps are chained by per-rank flags -- no host round trip, no barrier kernel and no
+ * collective library on the data path.  The result is bit-identical to the single-GPU run.  Call order: pmc_upload
+ * on every rank, exchange the 64-byte handles (any host channel, e.g. an all-gather), pmc_box_peer_attach (before
+ * the first pmc_run), then pmc_init_energy / pmc_run as usual; every rank must issue the same pmc_run calls. */
 #define PMC_IPC_HANDLE_BYTES 64
 #define PMC_MAX_RANKS 8
 int pmc_box_peer_export(pmc_ctx *ctx, uint8_t *handle /*[PMC_IPC_HANDLE_BYTES]*/);

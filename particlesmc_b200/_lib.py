@@ -49,7 +49,7 @@ EXPORTS = [
     "pmc_abi_version", "pmc_last_error", "pmc_create", "pmc_destroy", "pmc_set_stream", "pmc_set_model",
     "pmc_set_bonds", "pmc_set_molecules", "pmc_upload", "pmc_init_energy", "pmc_set_moves", "pmc_seed", "pmc_run", "pmc_sync",
     "pmc_run_traced", "pmc_replay", "pmc_energy", "pmc_total_energy", "pmc_local_energy", "pmc_download",
-    "pmc_pair_histogram", "pmc_chain_correlation", "pmc_energy_histogram", "pmc_counters", "pmc_launch_count", "pmc_last_run_ms", "pmc_measure_fma_peak", "pmc_box_peer_export",
+    "pmc_pair_histogram", "pmc_chain_correlation", "pmc_energy_histogram", "pmc_counters", "pmc_launch_count", "pmc_last_run_ms", "pmc_work_counters", "pmc_measure_fma_peak", "pmc_box_peer_export",
     "pmc_box_peer_attach",
 ]
 
@@ -96,6 +96,7 @@ def load():
     L.pmc_launch_count.restype = C.c_int64
     L.pmc_last_run_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.pmc_measure_fma_peak.argtypes = [C.c_int32, C.c_int32, dp]
+    L.pmc_work_counters.argtypes = [vp, C.c_int32, C.POINTER(C.c_uint64)]
     L.pmc_box_peer_export.argtypes = [vp, u8p]
     L.pmc_box_peer_attach.argtypes = [vp, C.c_int32, C.c_int32, u8p]
     for name in EXPORTS:

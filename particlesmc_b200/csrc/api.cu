@@ -195,6 +195,8 @@ struct pmc_ctx {
     int mol_uniform_len = 0;  // > 0: every molecule has this many sites (pmc_chain_correlation)
     int *bad = nullptr;
     int32_t *queue = nullptr;  // [1 + n_chains] work queue of the speculative kernel (chains_spec.cuh)
+    unsigned long long *stats = nullptr;  // [4] pmc_work_counters
+    bool stats_on = false;
     // staging
     double *raw_pos = nullptr;
     long long *raw_sp = nullptr;
@@ -290,6 +292,7 @@ void fill_chain_args(pmc_ctx *c, pmc::ChainArgs &a, int64_t n_trials, bool any_s
     a.Npad = c->Npad;
     a.ns = c->cfg.n_species;
     a.n_trials = n_trials;
+    a.stats = c->stats_on ? c->stats : nullptr;
 }
 
 int check_ready(pmc_ctx *c, bool need_moves) {
@@ -446,6 +449,7 @@ int pmc_create(const pmc_config *cfg, pmc_ctx **out) {
     if (a == cudaSuccess) a = dalloc(&c->accepted, M * PMC_MAX_MOVES);
     if (a == cudaSuccess) a = dalloc(&c->par, (size_t)PMC_MAX_SPECIES * PMC_MAX_SPECIES * PMC_NPAR);
     if (a == cudaSuccess) a = dalloc(&c->bad, 1);
+    if (a == cudaSuccess) a = dalloc(&c->stats, 4);
     if (a == cudaSuccess && cfg->mode == PMC_MODE_CHAINS) a = dalloc(&c->queue, M + 1);
     // the zero-fills above ran on the legacy default stream, which the context's non-blocking stream does not
     // wait for: drain them before any kernel of this context can touch the buffers
@@ -472,7 +476,7 @@ void pmc_destroy(pmc_ctx *c) {
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
     if (c->boxst) pmc::box_destroy(c->boxst);
     void *bufs[] = {c->x, c->img, c->sp, c->spids, c->heads, c->spoff, c->box, c->temp, c->energy, c->etot, c->eloc,
-                    c->par, c->calls, c->accepted, c->bonds, c->bad, c->queue, c->raw_pos, c->raw_sp, c->mol_start, c->mol_len};
+                    c->par, c->calls, c->accepted, c->bonds, c->bad, c->queue, c->stats, c->raw_pos, c->raw_sp, c->mol_start, c->mol_len};
     for (void *p : bufs)
         if (p) cudaFree(p);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -958,6 +962,24 @@ int pmc_last_run_ms(pmc_ctx *c, float *ms) {
     CU(cudaSetDevice(c->cfg.device));
     CU(cudaEventSynchronize(c->ev1));
     CU(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+    return PMC_OK;
+}
+
+int pmc_work_counters(pmc_ctx *c, int32_t enable, uint64_t *out) {
+    if (!c) return fail(PMC_ERR_INVALID, "null context");
+    CU(cudaSetDevice(c->cfg.device));
+    if (enable == 1) {
+        CU(cudaMemsetAsync(c->stats, 0, 4 * sizeof(unsigned long long), c->stream));
+        c->stats_on = true;
+    } else if (enable == 0 || enable == 2) {
+        if (!out) return fail(PMC_ERR_INVALID, "null argument");
+        CU(cudaMemcpyAsync(out, c->stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        if (enable == 0) c->stats_on = false;
+    } else {
+        return fail(PMC_ERR_INVALID, "enable must be 0, 1 or 2");
+    }
+    if (c->boxst) pmc::box_set_stats(c->boxst, c->stats_on ? c->stats : nullptr);
     return PMC_OK;
 }
 

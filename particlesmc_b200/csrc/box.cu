@@ -91,6 +91,7 @@ struct BoxArgs {
     double *eloc;             // [N] (energy kernel)
     int *overflow;  // 1: a stencil exceeds `cap`, 2: a plane exceeds plane_cap
     int *error;     // 3: a wait on another GPU timed out
+    unsigned long long *stats;  // pmc_work_counters (nullptr: off)
     // dataflow of one sweep: persistent CTAs pull (phase, cell) units from work[0]; a cell starts when the neighbour
     // cells of EARLIER phases carry this sweep's stamp in done[] -- no barrier between the colour phases
     uint32_t stamp;
@@ -569,6 +570,7 @@ __global__ void __launch_bounds__(kBfThreads, 8) k_box_sweep_all(const __grid_co
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ Stencil<DIM> st;
     __shared__ int s_unit;
+    __shared__ unsigned int s_stat[2];  // pmc_work_counters: fp64-evaluated candidates, trials evaluated
     constexpr bool FAST = KC > 0;
     constexpr int NST = Stencil<DIM>::NST;
     const int CAP = FAST ? kBfThreads * KC : A.cap;
@@ -600,6 +602,7 @@ __global__ void __launch_bounds__(kBfThreads, 8) k_box_sweep_all(const __grid_co
     const uint32_t qa = sb + F.q + (uint32_t)warp * (2u * (FAST ? KC : 1) * 32);
     const size_t ns_ = (size_t)A.g.nc[0] * A.plane_cap;
     const int n_units = (1 << DIM) * A.cell_n;
+    if (threadIdx.x < 2) s_stat[threadIdx.x] = 0u;
     uint32_t rebuilt_ok = 0;  // bit p: peer p has finished this sweep's rebuild (its arrays may be written into)
 
     for (;;) {
@@ -755,6 +758,8 @@ __global__ void __launch_bounds__(kBfThreads, 8) k_box_sweep_all(const __grid_co
                             incl += (lane >= o) ? v : 0;
                         }
                         const int total = __shfl_sync(0xffffffffu, incl, 31);
+                        if (A.stats && lane == 0) atomicAdd(&s_stat[0], (unsigned int)total);
+                        if (A.stats && tid == 0) atomicAdd(&s_stat[1], 1u);
                         uint32_t wp = qa + 2u * (uint32_t)(incl - mine);
 #pragma unroll
                         for (int kk = 0; kk < KC; kk++) {
@@ -770,6 +775,10 @@ __global__ void __launch_bounds__(kBfThreads, 8) k_box_sweep_all(const __grid_co
                         }
                         __syncwarp();
                     } else {
+                        if (A.stats && tid == 0) {
+                            atomicAdd(&s_stat[0], (unsigned int)(ncand - 1));
+                            atomicAdd(&s_stat[1], 1u);
+                        }
                         for (int j = tid; j < ncand; j += kBfThreads)
                             if (j != k) pair_terms((uint32_t)j);
                     }
@@ -857,6 +866,10 @@ __global__ void __launch_bounds__(kBfThreads, 8) k_box_sweep_all(const __grid_co
             *(volatile uint32_t *)(A.done + cell) = A.stamp;  // overflow: reported by the host, nobody may hang on this cell
             for (int p = 0; p < A.n_peers; p++) *(volatile uint32_t *)(A.peer_done[p] + cell) = A.stamp;
         }
+    }
+    if (A.stats) {
+        __syncthreads();
+        if (tid < 2) atomicAdd(A.stats + tid, (unsigned long long)s_stat[tid]);
     }
     // the CTA that leaves last tells every peer that this rank's sweep (all its pushes) is complete
     if (A.n_peers) {
@@ -1004,6 +1017,7 @@ struct BoxState {
     long long *rsp = nullptr;
     int64_t calls = 0;
     int64_t launches = 0;
+    unsigned long long *stats = nullptr;  // device work counters (owned by the context), nullptr: off
     size_t smem = 0;        // energy / histogram kernels
     int fast_kc = 0;        // > 0: k_box_sweep_all<.., KC> with the prefilter
     size_t sweep_smem = 0;
@@ -1117,6 +1131,7 @@ void fill_args(BoxState *b, BoxArgs &a) {
     a.cell_acc = b->cell_acc;
     a.eloc = b->eloc;
     a.error = b->flags;
+    a.stats = b->stats;
     a.overflow = b->flags + 1;
     a.stamp = b->stamp;
     a.done = b->done;
@@ -1432,6 +1447,7 @@ void box_destroy(BoxState *b) {
 
 void box_set_stream(BoxState *b, cudaStream_t st) { b->stream = st; }
 void box_set_sigma(BoxState *b, double sigma) { b->sigma = sigma; }
+void box_set_stats(BoxState *b, unsigned long long *stats) { b->stats = stats; }
 void box_seed(BoxState *b, uint64_t seed) {
     b->seed = seed;
     b->sweep = 0;

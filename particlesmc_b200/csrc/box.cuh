@@ -17,6 +17,7 @@ void box_destroy(BoxState *b);
 void box_set_stream(BoxState *b, cudaStream_t st);
 int box_set_model(BoxState *b, const double *params);
 void box_set_sigma(BoxState *b, double sigma);
+void box_set_stats(BoxState *b, unsigned long long *stats);
 void box_seed(BoxState *b, uint64_t seed);
 int box_upload(BoxState *b, const double *pos_aos, const int64_t *species, const double *box3, double temperature);
 int box_init_energy(BoxState *b, double *e_out);

@@ -53,6 +53,7 @@ struct ChainArgs {
     // n_seg segments of seg_len trials per chain and persistent CTAs pull (chain, segment) units from queue[0];
     // queue[1 + chain] counts the finished segments of a chain (a unit waits for its predecessor).  nullptr: one CTA per chain.
     int32_t *queue;
+    unsigned long long *stats;  // pmc_work_counters: [0] fp64-evaluated candidates, [1] trial evaluations (nullptr: off)
     int32_t n_chains, n_seg;
     long long seg_len;
 };

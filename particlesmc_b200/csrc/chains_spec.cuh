@@ -80,7 +80,7 @@ __host__ __device__ inline SpecLayout spec_layout(int dim, int Npad, bool full_p
     f.rec = take((uint32_t)kRecBytes * kSpecBatch);
     f.pub = take(2u * kPubBytes * nw + 16u);  // two alternating sets + the retired count of the round
     f.cnt = take(8u * 2 * PMC_MAX_MOVES);
-    f.cnt32 = take(4u * 2 * PMC_MAX_MOVES);  // per-batch counters (native 32-bit shared atomics), folded into cnt
+    f.cnt32 = take(4u * (2 * PMC_MAX_MOVES + 4));  // per-batch counters (native 32-bit shared atomics), folded into cnt; + work counters
     f.par = take(full_par ? 8u * PMC_MAX_SPECIES * PMC_MAX_SPECIES * PMC_NPAR : 0u);
     f.rcs = take(8u * PMC_MAX_SPECIES);
     f.spids = take(swaps ? 2u * (uint32_t)Npad : 0u);  // SpeciesList (src/utils.jl:31-49), DiscreteSwap pools only
@@ -214,6 +214,7 @@ __global__ void __launch_bounds__(32 * NW, NPAD <= 1024 ? (NW == 8 ? 3 : (MIXED 
             scnt[tid] = 0ull;
             ((uint32_t *)(smem_raw + F.cnt32))[tid] = 0u;
         }
+        if (tid < 4) ((uint32_t *)(smem_raw + F.cnt32))[2 * PMC_MAX_MOVES + tid] = 0u;
         if constexpr (SWAPS) {
             uint16_t *si_ = (uint16_t *)(smem_raw + F.spids);
             const uint16_t *gi = A.spids + (size_t)c * gNpad;
@@ -257,6 +258,10 @@ __global__ void __launch_bounds__(32 * NW, NPAD <= 1024 ? (NW == 8 ? 3 : (MIXED 
             uint32_t *c32 = (uint32_t *)(smem_raw + F.cnt32);
             ((unsigned long long *)(smem_raw + F.cnt))[k] += c32[k];
             c32[k] = 0u;
+            if (A.stats && k < 2) {  // work counters of the previous batch
+                atomicAdd(A.stats + k, (unsigned long long)c32[2 * PMC_MAX_MOVES + k]);
+                c32[2 * PMC_MAX_MOVES + k] = 0u;
+            }
         }
         // ---- proposals of trials tb .. tb+nb-1, parked in shared memory (same stream as every other kernel) ----
         // generated by two warps (ceil(batch / 32)); which two alternates from batch to batch (PMC_SPEC_ROTATE)
@@ -545,6 +550,11 @@ __global__ void __launch_bounds__(32 * NW, NPAD <= 1024 ? (NW == 8 ? 3 : (MIXED 
                         incl += (lane >= o) ? t : 0;
                     }
                     const int total = __shfl_sync(0xffffffffu, incl, 31);
+                    if (A.stats && lane == 0) {
+                        uint32_t *c32 = (uint32_t *)(smem_raw + F.cnt32);
+                        atomicAdd(&c32[2 * PMC_MAX_MOVES], (uint32_t)total);
+                        atomicAdd(&c32[2 * PMC_MAX_MOVES + 1], 1u);
+                    }
                     const uint32_t prow = si * (uint32_t)ns;
                     double part = 0.0;
                     uint32_t bi[PMC_MAX_BONDS];  // MOL: bonded partners of i (0xFFFF = none)
@@ -847,6 +857,7 @@ __global__ void __launch_bounds__(32 * NW, NPAD <= 1024 ? (NW == 8 ? 3 : (MIXED 
         const unsigned long long *scnt = (const unsigned long long *)(smem_raw + F.cnt);
         const uint32_t *c32 = (const uint32_t *)(smem_raw + F.cnt32);
         if (tid == 0) A.energy[c] = lds_f64(tail + 8);
+        if (A.stats && tid < 2) atomicAdd(A.stats + tid, (unsigned long long)c32[2 * PMC_MAX_MOVES + tid]);
         if (tid < A.n_moves) {
             atomicAdd(A.calls + (size_t)c * PMC_MAX_MOVES + tid, scnt[tid] + c32[tid]);
             atomicAdd(A.accepted + (size_t)c * PMC_MAX_MOVES + tid, scnt[PMC_MAX_MOVES + tid] + c32[PMC_MAX_MOVES + tid]);

@@ -223,6 +223,13 @@ class DeviceContext:
     def launch_count(self) -> int:
         return int(self.lib.pmc_launch_count(self._h))
 
+    def work_counters(self, enable: int):
+        """pmc_work_counters: 1 = reset and start counting, 0 = stop and read, 2 = read.  Returns
+        (fp64-evaluated candidates, trial evaluations) for 0 / 2."""
+        out = np.zeros(4, dtype=np.uint64)
+        L.check(self.lib.pmc_work_counters(self._h, int(enable), out.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return int(out[0]), int(out[1])
+
     def last_run_ms(self) -> float:
         ms = C.c_float()
         L.check(self.lib.pmc_last_run_ms(self._h, C.byref(ms)))
