@@ -198,6 +198,15 @@ class OracleSystem:
         acc = lib().orc_step_swap(self._h, A, B, int(i), int(j), float(u), revert_mode, C.byref(e1), C.byref(e2))
         return bool(acc), e1.value, e2.value
 
+    def step_swap_draw(self, A, B, ka, kb, u, revert_mode=0):
+        """DoubleUniform draw resolved through the oracle's OWN species lists (src/moves.jl:238-241, utils.jl:31-49):
+        slots (ka, kb) -> particles (i, j), then the swap.  Returns (accepted, i, j, e1, e2)."""
+        e1, e2 = C.c_double(), C.c_double()
+        i, j = C.c_int(), C.c_int()
+        acc = lib().orc_step_swap_draw(self._h, A, B, int(ka), int(kb), float(u), revert_mode, C.byref(i), C.byref(j),
+                                       C.byref(e1), C.byref(e2))
+        return bool(acc), i.value, j.value, e1.value, e2.value
+
     def step_flip(self, i, j, u, revert_mode=0):
         e1, e2 = C.c_double(), C.c_double()
         acc = lib().orc_step_flip(self._h, int(i), int(j), float(u), revert_mode, C.byref(e1), C.byref(e2))

@@ -19,6 +19,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <type_traits>
@@ -855,9 +856,11 @@ __global__ void __launch_bounds__(kBfThreads, 8) k_box_sweep_all(const __grid_co
             }
             // ---- publish: this cell is done for this sweep (system-wide only if a peer keeps its plane; the pushes into the
             // canonical state of the other peers are fenced once, when the CTA leaves) ----
-            if (keeps) __threadfence_system(); else __threadfence();
+            // (the barrier orders every thread's stores before thread 0's fence, which makes them visible -- system-wide if
+            // a peer keeps the plane -- before the stamp: one fence per cell instead of one per thread)
             __syncthreads();
             if (tid == 0) {
+                if (keeps) __threadfence_system(); else __threadfence();
                 *(volatile uint32_t *)(A.done + cell) = A.stamp;
                 for (int p = 0; p < A.n_peers; p++)
                     if (keeps & (1u << p)) *(volatile uint32_t *)(A.peer_done[p] + cell) = A.stamp;
@@ -873,8 +876,8 @@ __global__ void __launch_bounds__(kBfThreads, 8) k_box_sweep_all(const __grid_co
     }
     // the CTA that leaves last tells every peer that this rank's sweep (all its pushes) is complete
     if (A.n_peers) {
-        __threadfence_system();
         __syncthreads();
+        if (tid == 0) __threadfence_system();  // this CTA's pushes (ordered before by the barrier) are performed system-wide
         if (tid == 0 && atomicAdd(A.work + 1, 1) == (int)gridDim.x - 1) {
             __threadfence_system();
             for (int p = 0; p < A.n_peers; p++) *(volatile uint32_t *)(A.peer_flags[p] + kFlagSwept + A.rank) = A.stamp;
@@ -1026,6 +1029,9 @@ struct BoxState {
     // multi-GPU
     int rank = 0, world = 1;
     unsigned char *peer_block[PMC_MAX_PEERS + 1] = {};  // opened IPC mapping of every rank's block (self = local)
+    // PMC_BOX_TIMING=1 in the environment: device time of the three parts of every sweep (CUDA events), printed at destroy
+    bool timing = false;
+    std::vector<cudaEvent_t> tev;
 };
 
 namespace {
@@ -1410,6 +1416,7 @@ int box_create(BoxState **out, const pmc_config &cfg) {
     if (cfg.molecules) return bfail(PMC_ERR_UNSUPPORTED, "Molecules are not supported in PMC_MODE_BOX");
     BoxState *b = new BoxState();
     b->cfg = cfg;
+    b->timing = std::getenv("PMC_BOX_TIMING") != nullptr;
     b->N = cfg.n_particles;
     b->dim = cfg.dim;
     b->ns = cfg.n_species;
@@ -1436,6 +1443,20 @@ int box_create(BoxState **out, const pmc_config &cfg) {
 
 void box_destroy(BoxState *b) {
     if (!b) return;
+    if (b->timing && b->tev.size() >= 4) {
+        cudaDeviceSynchronize();
+        double t[3] = {0, 0, 0};
+        const size_t n = b->tev.size() / 4, skip = n / 2;  // second half of the run
+        for (size_t s = skip; s < n; s++)
+            for (int k = 0; k < 3; k++) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, b->tev[4 * s + k], b->tev[4 * s + k + 1]);
+                t[k] += ms;
+            }
+        fprintf(stderr, "[pmc box timing] rank %d/%d: %zu sweeps, per sweep: rebuild %.1f us, sweep kernel %.1f us, reduce (+ wait for peers) %.1f us\n",
+                b->rank, b->world, n - skip, 1e3 * t[0] / (n - skip), 1e3 * t[1] / (n - skip), 1e3 * t[2] / (n - skip));
+        for (auto e : b->tev) cudaEventDestroy(e);
+    }
     for (int r = 0; r < b->world; r++)
         if (r != b->rank && b->peer_block[r]) cudaIpcCloseMemHandle(b->peer_block[r]);
     void *bufs[] = {b->shared_block, b->ids, b->cid, b->sp, b->sps, b->eloc, b->par, b->energy, b->etmp, b->acc_total,
@@ -1544,6 +1565,14 @@ int box_run(BoxState *b, int64_t n_trials) {
         }
         const uint32_t prev = b->stamp;
         b->stamp++;
+        auto mark = [&]() {
+            if (!b->timing) return;
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            cudaEventRecord(e, b->stream);
+            b->tev.push_back(e);
+        };
+        mark();
         int rc = build_cells(b, false, prev, b->stamp);
         if (rc) return rc;
         BoxArgs A;
@@ -1553,6 +1582,7 @@ int box_run(BoxState *b, int64_t n_trials) {
             A.phase_of[order[k]] = k;
         }
         BCU(cudaMemsetAsync(b->work, 0, 2 * sizeof(int), b->stream));
+        mark();
         const int grid = std::min(b->sweep_grid, ncol * A.cell_n);
         if (grid > 0) {
             rc = bdispatch(b->dim, b->cfg.model_kind, [&](auto D, auto MDL) {
@@ -1572,8 +1602,10 @@ int box_run(BoxState *b, int64_t n_trials) {
             });
             if (rc) return rc;
         }
+        mark();
         rc = reduce_cells(b, A, b->stamp, true);
         if (rc) return rc;
+        mark();
         b->launches += 1;
         b->sweep++;
         b->calls += b->N;

@@ -175,3 +175,75 @@ def test_checkerboard_samples_same_energy_as_sequential_chain():
     assert gc[:15].max() < 1e-3 and abs(gc[-5:].mean() - 1.0) < 0.1  # excluded core, plateau ~ 1
     # acceptance: the checkerboard additionally rejects cell-crossing proposals (~ 3*sigma*sqrt(2/pi)/cell side)
     assert abs(series["box_acc"] - series["chain_acc"]) < 0.06
+
+
+def test_checkerboard_energy_distribution_matches_sequential_chains():
+    """test/gerhard_energy_distribution.jl compares energy DISTRIBUTIONS, not only means.  Here: the histogram of the
+    energy per particle (pmc_energy_histogram, on the device) sampled by the checkerboard sweeps of one box against the
+    one sampled by 256 independent sequential chains of the same system (KA N = 2048, T = 2: a liquid that relaxes
+    within a few hundred sweeps), both started from one equilibrated configuration.  Mean, width (the heat capacity)
+    and the cumulative distributions agree within the sampling error, which is estimated from blocks because successive
+    samples of the single box are correlated."""
+    N, T = 2048, 2.0
+    pos, sp, box = ka_lattice(N, 1.2, seed=21)
+    par = M.flatten_model_matrix(M.KobAndersen())
+    moves = [dict(kind="displacement", prob=1.0, sigma=0.05)]
+    with box_ctx(pos, sp, box, T, M.KobAndersen()) as b:  # common equilibrated start
+        b.init_energy()
+        b.set_moves(moves)
+        b.seed(1)
+        b.run(3000 * N)
+        p0, _ = b.download()
+        e0 = b.energy()[0] / N
+    pos = p0[0] - np.floor(p0[0] / box) * box
+    emin, emax, nbins = e0 - 0.6, e0 + 0.6, 240
+    centers = emin + (np.arange(nbins) + 0.5) * (emax - emin) / nbins
+    # sequential chains: 256 chains x 40 samples, 25 sweeps apart, after 1500 sweeps that make the chains independent of
+    # the common start (sigma = 0.05: a particle needs a few hundred sweeps to diffuse over its own diameter)
+    nch, nsamp = 256, 40
+    with DeviceContext(nch, N, 3, 2, M.MODEL_LJ) as c:
+        c.set_model(par)
+        c.upload(np.broadcast_to(pos, (nch,) + pos.shape).copy(), np.broadcast_to(sp, (nch,) + sp.shape).copy(), box, T)
+        c.init_energy()
+        c.set_moves(moves)
+        c.seed(8)
+        c.run(1500 * N)
+        h_chain = np.zeros(nbins, dtype=np.uint64)
+        means = []
+        for _ in range(nsamp):
+            c.run(25 * N)
+            h_chain += c.energy_histogram(emin, emax, nbins)
+            means.append(c.energy() / N)
+    means = np.array(means)  # [nsamp][nch]
+    # the box: one system, a sample every 2 sweeps
+    nbox, nblk = 8192, 16
+    with box_ctx(pos, sp, box, T, M.KobAndersen()) as b:
+        b.init_energy()
+        b.set_moves(moves)
+        b.seed(9)
+        b.run(200 * N)
+        e_box = np.zeros(nbox)
+        h_box = np.zeros(nbins, dtype=np.uint64)
+        for k in range(nbox):
+            b.run(2 * N)
+            h_box += b.energy_histogram(emin, emax, nbins)
+            e_box[k] = b.energy()[0] / N
+    assert h_chain.sum() == nch * nsamp and h_box.sum() == nbox  # nothing fell outside the window
+    assert np.array_equal(np.histogram(e_box, bins=nbins, range=(emin, emax))[0], h_box.astype(np.int64))  # device binning
+    pc, pb = h_chain / h_chain.sum(), h_box / h_box.sum()
+    mc, mb = (pc * centers).sum(), (pb * centers).sum()
+    vc, vb = (pc * (centers - mc) ** 2).sum(), (pb * (centers - mb) ** 2).sum()
+    blocks = e_box.reshape(nblk, -1)
+    err_b = blocks.mean(axis=1).std(ddof=1) / np.sqrt(nblk)          # correlated series: block means
+    err_c = means.mean(axis=0).std(ddof=1) / np.sqrt(nch)              # independent chains
+    assert abs(mb - mc) < 4.0 * np.hypot(err_b, err_c) + 2e-4, (mb, mc, err_b, err_c)
+    verr_b = blocks.var(axis=1).std(ddof=1) / np.sqrt(nblk)
+    assert abs(vb - vc) < 4.0 * verr_b + 0.08 * vc, (vb, vc, verr_b)
+    # shape of the distribution: cumulative distributions of the CENTRED energies (the means were compared above with
+    # their own error bars; the single box delivers only ~150 independent samples of the mean)
+    grid = np.linspace(-0.2, 0.2, 161)
+    cdf = lambda p, m: np.interp(grid, centers - m + 0.5 * (emax - emin) / nbins, np.cumsum(p))
+    ks_shape = np.max(np.abs(cdf(pc, mc) - cdf(pb, mb)))
+    assert ks_shape < 0.03, (ks_shape, mb, mc, vb, vc)
+    ks = np.max(np.abs(np.cumsum(pc) - np.cumsum(pb)))
+    assert ks < 0.03 + 0.4 * 4.0 * np.hypot(err_b, err_c) / np.sqrt(vc), (ks, mb, mc, vb, vc)

@@ -5,6 +5,7 @@ conserved, the same seed gives the same trajectory."""
 import numpy as np
 import pytest
 
+from oracle import oracle as O
 from particlesmc_b200 import _lib as L
 from particlesmc_b200 import models as M
 from particlesmc_b200.device import DeviceContext
@@ -68,4 +69,37 @@ def test_config3_box_of_2_to_the_20():
             p, s = ctx.download()
             assert np.array_equal(np.bincount(s[0]), np.bincount(sp))
             finals.append(p[0])
+            e_final = e_run
     assert np.array_equal(finals[0], finals[1])
+    # the oracle (reference arithmetic: LinkedList cells, division minimum image) on the final configuration of the
+    # full-size box: total energy within 1e-12 of the device's running energy and of its recomputation
+    orc = O.OracleSystem(finals[0] - np.floor(finals[0] / box) * box, sp, box, 1.0, M.MODEL_LJ, par, O.LINKEDLIST)
+    assert abs(orc.energy - e_final) / abs(orc.energy) < 1e-12, (orc.energy, e_final)
+
+
+def test_config2_block_of_chains_replayed_by_the_oracle():
+    """32 consecutive chains picked at random out of the 4096 of BASELINE config 2: (a) the production run (persistent
+    work queue, no tracing) and a traced run of just those chains (same global chain ids) end in bit-identical
+    configurations; (b) the oracle replays the traced proposals of every one of them: same decisions, same energies."""
+    N, nch, n_trials, nsub = 1000, 4096, 1500, 32
+    pos, sp, box = ka_lattice(N, 1.2, seed=0)
+    par = M.flatten_model_matrix(M.KobAndersen())
+    first = int(np.random.default_rng(20261017).integers(0, nch - nsub))
+    with DeviceContext(nch, N, 3, 2, M.MODEL_LJ) as ctx:
+        ka_chains(ctx, pos, sp, box, nch)
+        ctx.run(n_trials)
+        p_full, _ = ctx.download(first, nsub)
+        e_full = ctx.energy()[first:first + nsub]
+    with DeviceContext(nsub, N, 3, 2, M.MODEL_LJ, chain_offset=first) as sub:
+        ka_chains(sub, pos, sp, box, nsub)
+        tr, acc, dE = sub.run_traced(n_trials)
+        p_sub, _ = sub.download()
+        assert np.array_equal(p_sub, p_full)
+        assert np.array_equal(sub.energy(), e_full)
+    z = np.zeros(n_trials, dtype=np.int32)
+    for c in range(nsub):
+        orc = O.OracleSystem(pos, sp, box, 1.0, M.MODEL_LJ, par, O.LINKEDLIST)
+        o_acc, o_dE, _ = orc.replay(tr["kind"][c], tr["i"][c], z, z, z, tr["delta"][c], tr["u"][c], 1)
+        assert np.array_equal(o_acc, acc[c]), f"chain {first + c}"
+        assert np.max(np.abs(o_dE - dE[c])) < 1e-10
+        assert abs(orc.energy - e_full[c]) < 1e-10 * abs(orc.energy)

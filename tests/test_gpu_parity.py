@@ -467,3 +467,98 @@ def test_energy_bookkeeping_after_long_run():
         assert np.all(calls.sum(axis=1) == 50 * 216)
         rate = acc[:, 0] / calls[:, 0]
         assert np.all((rate > 0.05) & (rate < 0.95))
+
+
+# ---------------------------------------------------------------------------------------------------
+# round 2: the holes the round-1 review named
+# ---------------------------------------------------------------------------------------------------
+def test_swap_slots_resolve_through_the_species_lists_like_the_reference(config0):
+    """DoubleUniform draws SLOTS of the per-species id lists (src/moves.jl:238-241); which particle a slot names depends on
+    how update_species_list! (src/moves.jl:175-179) rearranged the lists after every accepted swap.  Here the oracle
+    draws the particles itself: it receives the slots the GPU's Philox stream produced (recomputed on the host from
+    seed, chain and trial number) and resolves them through its OWN lists; the GPU must have picked the same particles
+    and taken the same decisions for thousands of trials with hundreds of accepted swaps in between."""
+    par = M.flatten_model_matrix(M.JBB())
+    pool = [dict(kind="displacement", prob=0.2, sigma=0.05), dict(kind="swap", prob=0.4, species=(1, 3)),
+            dict(kind="swap", prob=0.4, species=(2, 3))]
+    species_of = {1: (1, 3), 2: (2, 3)}
+    seed, n_trials, T = 1234, 4000, 1.0
+    counts = np.bincount(config0["species"], minlength=4)
+    with DeviceContext(2, 1290, 2, 3, M.MODEL_SMOOTHLJ, chain_offset=5) as ctx:
+        ctx.set_model(par)
+        ctx.upload(np.stack([config0["position"]] * 2), np.stack([config0["species"]] * 2), config0["box"], T)
+        ctx.init_energy()
+        ctx.set_moves(pool)
+        ctx.seed(seed)
+        tr, acc, dE = ctx.run_traced(n_trials)
+        gpos, gsp = ctx.download()
+    key = (seed & 0xFFFFFFFF, seed >> 32)
+    for c in range(2):
+        orc = O.OracleSystem(config0["position"], config0["species"], config0["box"], T, M.MODEL_SMOOTHLJ, par, O.LINKEDLIST)
+        n_acc_swaps = 0
+        for t in range(n_trials):
+            r = tr[c, t]
+            if r["kind"] == 0:
+                a, _, _ = orc.step_displacement(r["i"], r["delta"][:2], r["u"], 0)
+            else:
+                A, B = species_of[int(r["move"])]
+                blkA = O.philox4x32_10((t, 0, 5 + c, 0), key)
+                blkB = O.philox4x32_10((t, 0, 5 + c, 1), key)
+                ka = (int(blkA[1]) * int(counts[A])) >> 32
+                kb = (int(blkB[0]) * int(counts[B])) >> 32
+                a, i, j, _, _ = orc.step_swap_draw(A, B, ka, kb, r["u"], 0)
+                assert (i, j) == (int(r["i"]), int(r["j"])), f"chain {c} trial {t}: slots ({ka}, {kb}) name other particles"
+                n_acc_swaps += int(a)
+            assert a == bool(acc[c, t]), f"chain {c} trial {t}"
+        assert n_acc_swaps > 100
+        opos, osp = orc.state()
+        assert np.array_equal(osp, gsp[c])
+        d = opos - gpos[c]
+        assert np.max(np.abs(d - np.round(d / config0["box"]) * config0["box"])) < 1e-11  # same point, any periodic image
+
+
+def test_stretched_bonds_consecutive_trials_on_bonded_sites():
+    """Bonded partners interact through FENE up to r0 (1.425 .. 1.575 for Trimer), beyond the WCA cutoff that sizes the
+    filter sphere of a trial.  Trials on the two ends of a stretched bond land in the same speculative round; the second
+    must not keep an energy computed from the partner's old position (src/molecules.jl:160-176).  Injected proposals,
+    hot system (nearly every move accepted), decisions and energy changes against the oracle."""
+    par = M.flatten_model_matrix(M.Trimer())
+    nmol, spacing, blen = 64, 3.2, 1.33
+    grid = np.array([(x, y, z) for x in range(4) for y in range(4) for z in range(4)], dtype=float) * spacing + 0.7
+    pos = np.zeros((3 * nmol, 3))
+    pos[0::3] = grid
+    pos[1::3] = grid + [blen, 0.0, 0.0]
+    pos[2::3] = grid + [blen, blen, 0.0]
+    sp = np.tile([1, 2, 3], nmol)
+    bonds = []
+    for m in range(nmol):
+        bonds += [[3 * m + 1], [3 * m, 3 * m + 2], [3 * m + 1]]
+    box = np.full(3, 4 * spacing)
+    n = 3 * nmol
+    rng = np.random.default_rng(3)
+    nt = 3000
+    tr = np.zeros((1, nt), dtype=TRIAL_DTYPE)
+    # runs of trials that walk along one molecule: 0-1-2-1-0 ... bonded sites back to back
+    mol = rng.integers(0, nmol, nt // 5 + 1)
+    walk = np.array([0, 1, 2, 1, 0])
+    tr["i"][0] = (3 * np.repeat(mol, 5)[:nt] + np.tile(walk, nt // 5 + 1)[:nt])
+    tr["j"] = -1
+    tr["delta"][0] = rng.normal(0, 0.004, (nt, 3))
+    tr["u"][0] = rng.random(nt)
+    T = 50.0
+    orc = O.OracleSystem(pos, sp, box, T, M.MODEL_KG, par, O.LINKEDLIST, bonds=bonds)
+    assert np.isfinite(orc.energy)
+    with DeviceContext(1, n, 3, 3, M.MODEL_KG, molecules=True) as ctx:
+        ctx.set_model(par)
+        ctx.set_bonds(bonds)
+        ctx.upload(pos, sp, box, T)
+        ctx.init_energy()
+        assert rel(ctx.energy()[0], orc.energy) < RTOL_E
+        g_acc, g_dE = ctx.replay(tr)
+        z = np.zeros(nt, dtype=np.int32)
+        o_acc, o_dE, _ = orc.replay(tr["kind"][0], tr["i"][0], z, z, z, tr["delta"][0], tr["u"][0], 0)
+        assert o_acc.mean() > 0.5  # hot: the earlier trial of a round usually moved the partner
+        assert np.array_equal(o_acc, g_acc[0])
+        fin = np.isfinite(o_dE)
+        assert np.max(np.abs(o_dE[fin] - g_dE[0][fin]) / np.maximum(1.0, np.abs(o_dE[fin]))) < 1e-10
+        assert rel(ctx.energy()[0], orc.energy) < 1e-10
