@@ -8,7 +8,7 @@
 # Everything else (TOML/CLI schema, Atoms/Molecules, Move/Action/Policy objects, Store*/Print* output
 # algorithms) stays the reference's.  One Arianna step advances every chain by `sweepstep` trials in a
 # single kernel launch; `system.position`, `system.species`, `system.energy[1]` and the Move counters are
-# refreshed from the device whenever Arianna is about to run an output algorithm.
+# refreshed from the device whenever Arianna is about to run an output algorithm at the same step (`output_due`).
 #
 # NOT EXECUTED in the build container (no Julia there; see DESIGN.md).  The same call sequence is exercised
 # from Python/ctypes in particlesmc_b200/device.py and tests/.  Arianna's algorithm hook names
@@ -110,10 +110,29 @@ function MetropolisB200(chains; pool, seed = 1, parallel = false, sweepstep = le
     return alg
 end
 
-# One Arianna step: `sweepstep` trials per chain, asynchronous on the device.
+# Does any OTHER algorithm of the simulation (StoreCallbacks, StoreTrajectories, StoreLastFrames, StoreAcceptance,
+# PrintTimeSteps: src/ParticlesMC.jl:249-291) run at the current step?  Arianna's `run!` calls, at every step t, the
+# `make_step!` of each algorithm whose scheduler contains t, in list order -- Metropolis first (it is pushed first,
+# src/ParticlesMC.jl:246), the outputs after it.  The field names `t`, `algorithms`, `schedulers` are those of Arianna
+# 0.2.x's `Simulation`; if this installation names them differently the answer is a conservative `true` (the host
+# copies are then refreshed after every step: correct, only slower).
+function output_due(simulation, alg)
+    all(p -> hasproperty(simulation, p), (:t, :algorithms, :schedulers)) || return true
+    t = simulation.t
+    for (a, sched) in zip(simulation.algorithms, simulation.schedulers)
+        a === alg && continue
+        t in sched && return true
+    end
+    return false
+end
+
+# One Arianna step: `sweepstep` trials per chain in one launch.  The launch is asynchronous; the host copies
+# (`position`, `species`, `energy[1]`, the Move counters) are refreshed only when an output algorithm is about to read
+# them at this very step, so a run that stores every 1000 sweeps pays one download per 1000 launches.
 function Arianna.make_step!(simulation::Arianna.Simulation, alg::MetropolisB200)
     check(ccall((:pmc_run, LIB), Cint, (Ptr{Cvoid}, Int64), alg.ctx, alg.sweepstep))
     alg.dirty = true
+    output_due(simulation, alg) && sync_host!(simulation, alg)
     return nothing
 end
 

@@ -210,6 +210,7 @@ struct pmc_ctx {
     bool spec_swaps = false;
     bool sweep_swap_cfg = false;
     bool cubic = true;  // every uploaded chain has a cubic box (enables the fixed-point prefilter)
+    double min_box = 1e300;  // shortest box length uploaded so far (proposal widths are checked against it)
     pmc::BoxState *boxst = nullptr;
 };
 
@@ -571,6 +572,7 @@ int pmc_upload(pmc_ctx *c, int32_t first, int32_t count, const double *position,
             if (!(L > 0.0) || !std::isfinite(L)) return fail(PMC_ERR_INVALID, "chain %d: box length must be positive", first + k);
             b3[(size_t)k * 3 + a] = L;
             if (L != box[(size_t)k * d]) c->cubic = false;
+            if (L < c->min_box) c->min_box = L;
         }
         if (!(temperature[k] > 0.0)) return fail(PMC_ERR_INVALID, "chain %d: temperature must be positive", first + k);
     }
@@ -649,6 +651,8 @@ int pmc_set_moves(pmc_ctx *c, const pmc_move *pool, int32_t n) {
         tot += m.probability;
     }
     if (!(tot > 0.0)) return fail(PMC_ERR_INVALID, "move probabilities sum to zero");
+    if (c->cfg.mode == PMC_MODE_BOX && n != 1)
+        return fail(PMC_ERR_UNSUPPORTED, "PMC_MODE_BOX sweeps with ONE Displacement move (got a pool of %d)", n);
     c->pool.assign(pool, pool + n);
     if (c->boxst) pmc::box_set_sigma(c->boxst, pool[0].sigma);
     return PMC_OK;
@@ -665,6 +669,10 @@ int pmc_seed(pmc_ctx *c, uint64_t seed) {
 int pmc_run(pmc_ctx *c, int64_t n_trials) {
     int rc = check_ready(c, true);
     if (rc) return rc;
+    // a displaced particle is folded back with ONE box length (fp32 Box-Muller proposals end at 6.7 sigma)
+    for (auto &m : c->pool)
+        if (m.kind == PMC_MOVE_DISPLACEMENT && !(7.0 * m.sigma < c->min_box))
+            return fail(PMC_ERR_INVALID, "Displacement sigma %g is too wide for a box of length %g (need 7 sigma < L)", m.sigma, c->min_box);
     if (n_trials < 0) return fail(PMC_ERR_INVALID, "n_trials must be >= 0");
     if (n_trials == 0) return PMC_OK;
     CU(cudaSetDevice(c->cfg.device));

@@ -239,7 +239,10 @@ def get_model(table: dict) -> Model:
     """TOML ``[model."i-j"]`` table -> model (IO.jl:129-156)."""
     name = table["name"]
     if name == "GeneralKG":
-        kw = {k: table[k] for k in ("rcut", "epsbond", "sigmabond", "rcutbond") if k in table}
+        # TOML keys of the reference schema (IO.jl:136-141): epsilonbond / sigmabond / rcutbond
+        kw = {k: table[k] for k in ("rcut", "sigmabond", "rcutbond") if k in table}
+        if "epsilonbond" in table:
+            kw["epsbond"] = table["epsilonbond"]
         return GeneralKG(table["epsilon"], table["sigma"], table["k"], table["r0"], **kw)
     if name == "SmoothLennardJones":
         return SmoothLennardJones(table["epsilon"], table["sigma"], rcut=table.get("rcut"))

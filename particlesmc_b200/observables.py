@@ -46,7 +46,9 @@ class EnergyHistogram:
 
     def add(self, ctx, allreduce=None):
         h = ctx.energy_histogram(self.emin, self.emax, self.nbins, self.per_particle)
-        self.counts += allreduce(h) if allreduce is not None else h
+        if allreduce is not None:  # sums come back as float64 (exact for counts < 2^53)
+            h = np.rint(np.asarray(allreduce(h))).astype(np.uint64)
+        self.counts += h
 
     @property
     def edges(self):

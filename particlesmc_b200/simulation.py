@@ -48,6 +48,16 @@ def build_schedule(steps: int, burn: int, block) -> List[int]:
     """``build_schedule(steps, burn, interval::Int)`` -> burn:interval:steps;
     ``build_schedule(steps, burn, block::Vector)`` -> the block pattern repeated every ``block[end]`` steps
     (src/ParticlesMC.jl:255-261; the function itself is Arianna's)."""
+    if isinstance(block, float):
+        # build_schedule(interval, 0, base::Float64): logarithmic block 0, base^0, base^1, ... <= interval
+        # (src/ParticlesMC.jl:254-256 calls it with base 2.0 for `log_base` schedulers)
+        base, out, n = float(block), [burn], 0
+        if base <= 1.0:
+            raise NotImplementedError("logarithmic schedules need a base > 1")
+        while burn + int(np.floor(base ** n)) <= steps:
+            out.append(burn + int(np.floor(base ** n)))
+            n += 1
+        return sorted(set(out))
     if np.isscalar(block):
         return list(range(burn, steps + 1, int(block)))
     block = [int(b) for b in block]

@@ -142,10 +142,16 @@ def make_context(systems: Sequence[Particles], *, device: int = 0, chain_offset:
     """Device context holding ``systems`` (all of one shape and model), uploaded but energy not initialised."""
     s0 = systems[0]
     mol = isinstance(s0, Molecules)
+    params = flatten_model_matrix(s0.model_matrix)
     for s in systems:
         if (s.N, s.d) != (s0.N, s0.d) or isinstance(s, Molecules) != mol:
             raise ValueError("all chains must have the same N, d and system type")
-    params = flatten_model_matrix(s0.model_matrix)
+        # the device holds ONE model table and ONE bond topology for all chains of a context
+        if s is not s0 and not np.array_equal(flatten_model_matrix(s.model_matrix), params):
+            raise ValueError("all chains of one context must share the model matrix")
+        if mol and s is not s0 and (list(map(list, s.bonds)) != list(map(list, s0.bonds)) or
+                                    list(s.start_mol) != list(s0.start_mol) or list(s.length_mol) != list(s0.length_mol)):
+            raise ValueError("all chains of one context must share the bond topology and molecule layout")
     ns = params.shape[0]
     if mode is None:
         mode = choose_mode(s0.N, s0.d, mol)
