@@ -555,6 +555,27 @@ __global__ void __launch_bounds__(32 * NW, NPAD <= 1024 ? (NW == 8 ? 3 : (MIXED 
                         atomicAdd(&c32[2 * PMC_MAX_MOVES], (uint32_t)total);
                         atomicAdd(&c32[2 * PMC_MAX_MOVES + 1], 1u);
                     }
+                    // Everything about this trial except its energy change is known here.  fp64: published now, off the
+                    // critical path between the reduction and the barrier (dE and the decision follow after the pass; +1 %);
+                    // PMC_MIXED (64 registers) publishes after the pass (early: -2.6 %).
+                    // +0: dE, new position | +32: what the conflict test of LATER trials needs | +48: what retiring THIS trial needs
+                    auto publish = [&]() {
+                        const uint32_t pw = pa + (uint32_t)kPubBytes * (uint32_t)warp;
+                        uint32_t qn;
+                        if constexpr (MIXED) {
+                            sts_u32x4(pw + 16, un0, un1, un2, 0u);
+                            qn = pack8(un0, un1, un2);
+                        } else {
+                            sts_f64(pw + 8, xn[0]);
+                            sts_f64x2(pw + 16, xn[1], xn[2]);
+                            qn = pack8(to_fixed32(xn[0], fscale), to_fixed32(xn[1], fscale), (DIM == 3) ? to_fixed32(xn[2], fscale) : 0u);
+                        }
+                        sts_u32x4(pw + 32, umq, (uint32_t)fthr, pack8(uo0, uo1, uo2), qn);
+                        sts_u32x4(pw + 48, (uint32_t)i, 0u, (uint32_t)((wr0 + 1) | ((wr1 + 1) << 2) | ((wr2 + 1) << 4)), lds_u32(ra + 48));
+                    };
+                    if constexpr (!MIXED) {
+                        if (lane == 0) publish();
+                    }
                     const uint32_t prow = si * (uint32_t)ns;
                     double part = 0.0;
                     uint32_t bi[PMC_MAX_BONDS];  // MOL: bonded partners of i (0xFFFF = none)
@@ -670,21 +691,10 @@ __global__ void __launch_bounds__(32 * NW, NPAD <= 1024 ? (NW == 8 ? 3 : (MIXED 
                     const double dE = warp_sum(part);
                     const bool acc = A.exact_exp ? accept_exact(dE, Tk, thr) : (dE < thr);
                     if (lane == 0) {
+                        if constexpr (MIXED) publish();
                         const uint32_t pw = pa + (uint32_t)kPubBytes * (uint32_t)warp;
-                        uint32_t qn;
-                        if constexpr (MIXED) {
-                            sts_f64(pw, dE);
-                            sts_u32x4(pw + 16, un0, un1, un2, 0u);
-                            qn = pack8(un0, un1, un2);
-                        } else {
-                            sts_f64x2(pw, dE, xn[0]);
-                            sts_f64x2(pw + 16, xn[1], xn[2]);
-                            qn = pack8(to_fixed32(xn[0], fscale), to_fixed32(xn[1], fscale), (DIM == 3) ? to_fixed32(xn[2], fscale) : 0u);
-                        }
-                        // +32: what the conflict test of LATER trials needs | +48: what retiring THIS trial needs
-                        sts_u32x4(pw + 32, umq, (uint32_t)fthr, pack8(uo0, uo1, uo2), qn);
-                        sts_u32x4(pw + 48, (uint32_t)i, acc ? 1u : 0u, (uint32_t)((wr0 + 1) | ((wr1 + 1) << 2) | ((wr2 + 1) << 4)),
-                                  lds_u32(ra + 48));
+                        sts_f64(pw, dE);
+                        sts_u32(pw + 52, acc ? 1u : 0u);
                     }
                 }  // !is_swap
             }
@@ -735,41 +745,36 @@ __global__ void __launch_bounds__(32 * NW, NPAD <= 1024 ? (NW == 8 ? 3 : (MIXED 
                         }
                     }
                 }
+                // what the commit may need is fetched BEFORE the ballots (independent loads, in flight together): lane
+                // `sub` < DIM of a group holds coordinate `sub` of its trial's new position, lane 0 the energy changes
+                double cval = 0.0;
+                uint32_t cval32 = 0u;
+                if constexpr (MIXED) {
+                    if (sub < DIM) cval32 = lds_u32(pw + 16u + 4u * (uint32_t)sub);
+                } else {
+                    if (sub < DIM) cval = lds_f64(pw + 8u + 8u * (uint32_t)sub);
+                }
+                double dEs[NW];
+#pragma unroll
+                for (int v = 0; v < NW; v++) dEs[v] = lane == 0 ? lds_f64(pa + (uint32_t)kPubBytes * (uint32_t)v) : 0.0;
+                const double E0 = lane == 0 ? lds_f64(tail + 8) : 0.0;
                 const unsigned cb = __ballot_sync(0xffffffffu, live && conflict < 0);
                 const int ndone = cb ? min(nspec, (__ffs((int)cb) - 1) / G) : nspec;
                 const bool mine = live && w < ndone;
                 const bool acc = mine && (fl & 1u) != 0u;
                 const unsigned accb = __ballot_sync(0xffffffffu, acc && sub == 0);
-                if (acc && !wswap) {
-                    if constexpr (MIXED) {
-                        if (sub == 0) {
-                            uint32_t n0, n1, n2, pad_;
-                            lds_u32x4(pw + 16, n0, n1, n2, pad_);
-                            const uint32_t ua = sb + F.x + 4u * iw;
-                            sts_u32(ua, n0);
-                            sts_u32(ua + nb4, n1);
-                            if constexpr (DIM == 3) sts_u32(ua + 2 * nb4, n2);
+                if (acc && !wswap) {  // one store per lane: coordinates, packed word; rarely an image counter
+                    if (sub < DIM) {
+                        if constexpr (MIXED) sts_u32(sb + F.x + 4u * iw + (uint32_t)sub * nb4, cval32);
+                        else sts_f64(sb + F.x + 8u * iw + (uint32_t)sub * nb8, cval);
+                    } else if (sub == 3) {
+                        sts_u32(sb + F.pk + 4u * pk_pos(iw), qn);
+                        if (wr != 0x15u) {  // some coordinate wrapped around the box
+                            const int w0 = (int)(wr & 3u) - 1, w1 = (int)((wr >> 2) & 3u) - 1, w2 = (int)((wr >> 4) & 3u) - 1;
+                            if (w0) atomicAdd(&gimg[iw], w0);
+                            if (w1) atomicAdd(&gimg[gNpad + iw], w1);
+                            if (DIM == 3 && w2) atomicAdd(&gimg[2 * gNpad + iw], w2);
                         }
-                    } else {
-                        const uint32_t xa = sb + F.x + 8u * iw;
-                        if (sub == 0) {
-                            double dE, x0;
-                            lds_f64x2(pw, dE, x0);
-                            sts_f64(xa, x0);
-                        }
-                        if (sub == 1) {
-                            double x1, x2;
-                            lds_f64x2(pw + 16, x1, x2);
-                            sts_f64(xa + nb8, x1);
-                            if constexpr (DIM == 3) sts_f64(xa + 2 * nb8, x2);
-                        }
-                    }
-                    if (sub == 2) sts_u32(sb + F.pk + 4u * pk_pos(iw), qn);
-                    if (sub == 3 && wr != 0x15u) {  // some coordinate wrapped around the box
-                        const int w0 = (int)(wr & 3u) - 1, w1 = (int)((wr >> 2) & 3u) - 1, w2 = (int)((wr >> 4) & 3u) - 1;
-                        if (w0) atomicAdd(&gimg[iw], w0);
-                        if (w1) atomicAdd(&gimg[gNpad + iw], w1);
-                        if (DIM == 3 && w2) atomicAdd(&gimg[2 * gNpad + iw], w2);
                     }
                 }
                 if (mine && sub == (4 % G)) {
@@ -782,10 +787,10 @@ __global__ void __launch_bounds__(32 * NW, NPAD <= 1024 ? (NW == 8 ? 3 : (MIXED 
                     }
                 }
                 if (lane == 0) {  // energy[1] += dE in trial order (src/moves.jl:11-20)
-                    double E = lds_f64(tail + 8);
+                    double E = E0;
 #pragma unroll
                     for (int v = 0; v < NW; v++)
-                        if (accb & (1u << (G * v))) E += lds_f64(pa + (uint32_t)kPubBytes * (uint32_t)v);
+                        if (accb & (1u << (G * v))) E += dEs[v];
                     sts_f64(tail + 8, E);
                     sts_u32(tail, (uint32_t)ndone);
                 }
