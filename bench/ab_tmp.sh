@@ -1,14 +1,7 @@
-timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_mixed.py tests/test_gpu_stat.py -x -q 2>&1 | tail -3
-B="python bench.py --workload chains --no-cpu-baseline --no-e2e --steps 5 --warmup 3"
-for rep in 1 2; do for v in prev default; do
-  lib=libpmc_b200_$v.so; [ $v = default ] && lib=libpmc_b200.so
-  PMC_B200_LIB=$lib $B > gpurun_out/ab12_${v}_$rep.json 2>/dev/null
-  PMC_B200_LIB=$lib $B --precision mixed > gpurun_out/ab12_${v}_mixed_$rep.json 2>/dev/null
-done; done
-for f in gpurun_out/ab12_*.json; do python - "$f" <<'PY'
-import json,sys
-try:
-    d=json.loads(open(sys.argv[1]).read().strip().split('\n')[-1]); print(sys.argv[1], '%.4g'%d['value'])
-except Exception as e: print(sys.argv[1], 'FAILED', e)
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_simulation.py tests/test_gpu_edge.py tests/test_gpu_observables.py -x -q 2>&1 | tail -15
+python bench/other_configs.py > gpurun_out/ab13_other.json 2>gpurun_out/ab13_other.err; tail -3 gpurun_out/ab13_other.err
+python - <<'PY'
+import json
+for line in open('gpurun_out/ab13_other.json'):
+    d=json.loads(line); print('%.4g'%d['value'], d['config'][:90], d['acceptance_per_move'], d['energy_bookkeeping_rel_drift'])
 PY
-done

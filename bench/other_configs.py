@@ -2,7 +2,8 @@
 """Throughput of the BASELINE configs that are parity cases rather than the headline bench line:
   config 4: 2-D ternary mixture (the reference's own test/config_0 fixture, JBB) with Displacement 0.8 +
             DiscreteSwap (1,3) 0.1 + (2,3) 0.1 (test/gerhard_energy_distribution.jl:63-72), batched chains;
-  config 5: 1000 trimers (test/molecule fixture, Trimer/GeneralKG, bonded FENE + non-bonded WCA), Displacement.
+  config 5: 1000 trimers (test/molecule fixture, Trimer/GeneralKG, bonded FENE + non-bonded WCA), Displacement, and
+            Displacement 0.8 + MoleculeFlip 0.2 (the pool of examples/ortho-terphenyl).
 Device-resident, CUDA events inside the library (pmc_last_run_ms).  One JSON line per config.
     python bench/other_configs.py [--chains 1184] [--sweeps 20]
 """
@@ -64,6 +65,14 @@ def main():
         ctx.upload(np.stack([m["position"]] * nch), np.stack([m["species"]] * nch), m["box"], m["temperature"])
         run("1000 trimers N=3000 (test/molecule), Trimer/GeneralKG, Displacement", ctx, m["N"], nch, max(1, a.sweeps // 4),
             [dict(kind="displacement", prob=1.0, sigma=0.05)])
+    # the pool examples/ortho-terphenyl actually runs (params-template.toml:59-68): Displacement 0.8 + MoleculeFlip 0.2
+    with DeviceContext(nch, m["N"], 3, 3, M.MODEL_KG, molecules=True) as ctx:
+        ctx.set_model(M.flatten_model_matrix(M.Trimer()))
+        ctx.set_bonds([[j - 1 for j in b] for b in m["bonds"]])
+        ctx.set_molecules(np.arange(0, m["N"], 3), np.full(m["N"] // 3, 3))
+        ctx.upload(np.stack([m["position"]] * nch), np.stack([m["species"]] * nch), m["box"], m["temperature"])
+        run("1000 trimers N=3000 (test/molecule), Trimer/GeneralKG, Displacement 0.8 + MoleculeFlip 0.2", ctx, m["N"], nch,
+            max(1, a.sweeps // 4), [dict(kind="displacement", prob=0.8, sigma=0.05), dict(kind="flip", prob=0.2)])
 
 
 if __name__ == "__main__":

@@ -346,11 +346,11 @@ int sweep(pmc_ctx *c, int64_t n_trials, const pmc_trial *d_replay, pmc_trial *d_
     a.exact_exp = exact_exp ? 1 : 0;
     CU(cudaEventRecord(c->ev0, c->stream));
     const bool filter = c->cubic && c->cfg.prefilter >= 0 && c->sweep_smem_filter > c->sweep_smem;
-    bool flips = false;  // MoleculeFlip stays in the general kernel (molecules are excluded here anyway)
+    bool flips = false;  // MoleculeFlip: the speculative kernel (Molecules) or the general one, never the one-trial-at-a-time kernel
     for (auto &m : c->pool) flips = flips || m.kind == PMC_MOVE_FLIP;
     const bool fastk = filter && !flips && !c->cfg.molecules && pmc::chain_fast_supported(c->cfg.dim, c->Npad, c->threads);
     const bool mol = c->cfg.molecules != 0, mixed = c->cfg.precision == PMC_MIXED;
-    const bool speck = c->cubic && !flips && c->cfg.prefilter == 0 &&
+    const bool speck = c->cubic && (!flips || mol) && c->cfg.prefilter == 0 &&
                        pmc::chain_spec_supported(c->cfg.dim, c->cfg.model_kind, c->Npad, c->threads, mol, mixed, any_swap);
     if (speck) {
         const size_t ss = pmc::chain_spec_smem_bytes(c->cfg.dim, c->Npad, c->cfg.model_kind, mixed, mol, any_swap);

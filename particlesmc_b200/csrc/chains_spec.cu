@@ -22,18 +22,18 @@ template <bool MIXED, bool SWAPS, typename F>
 cudaError_t spec_dispatch(int dim, int model, int Npad, bool mol, int threads, F &&f) {
     const int np = spec_npad(Npad);
     constexpr int kNwS = (MIXED || SWAPS) ? 4 : PMC_SPEC_NW_SMALL;  // trials in flight for the small shapes
-    if (SWAPS && (mol || MIXED || model == PMC_MODEL_KG)) return cudaErrorInvalidValue;
-    if (mol) {
+    if (SWAPS && !mol && (MIXED || model == PMC_MODEL_KG)) return cudaErrorInvalidValue;
+    if (mol) {  // Molecules: GeneralKG, 3-D; Displacement pools, and pools with MoleculeFlip / DiscreteSwap (SWAPS)
         if (MIXED || dim != 3 || model != PMC_MODEL_KG) return cudaErrorInvalidValue;
-        if constexpr (!MIXED && !SWAPS) {
+        if constexpr (!MIXED) {
             if (threads == 128) {
-                if (np == 256) return f(spec::k_chain_sweep_spec<3, PMC_MODEL_KG, 256, false, true, 4>);
-                if (np == 512) return f(spec::k_chain_sweep_spec<3, PMC_MODEL_KG, 512, false, true, 4>);
-                if (np == 1024) return f(spec::k_chain_sweep_spec<3, PMC_MODEL_KG, 1024, false, true, 4>);
+                if (np == 256) return f(spec::k_chain_sweep_spec<3, PMC_MODEL_KG, 256, false, true, 4, SWAPS>);
+                if (np == 512) return f(spec::k_chain_sweep_spec<3, PMC_MODEL_KG, 512, false, true, 4, SWAPS>);
+                if (np == 1024) return f(spec::k_chain_sweep_spec<3, PMC_MODEL_KG, 1024, false, true, 4, SWAPS>);
             } else {
-                if (np == 2048) return f(spec::k_chain_sweep_spec<3, PMC_MODEL_KG, 2048, false, true, 8>);
-                if (np == 3072) return f(spec::k_chain_sweep_spec<3, PMC_MODEL_KG, 3072, false, true, 8>);
-                if (np == 4096) return f(spec::k_chain_sweep_spec<3, PMC_MODEL_KG, 4096, false, true, 8>);
+                if (np == 2048) return f(spec::k_chain_sweep_spec<3, PMC_MODEL_KG, 2048, false, true, 8, SWAPS>);
+                if (np == 3072) return f(spec::k_chain_sweep_spec<3, PMC_MODEL_KG, 3072, false, true, 8, SWAPS>);
+                if (np == 4096) return f(spec::k_chain_sweep_spec<3, PMC_MODEL_KG, 4096, false, true, 8, SWAPS>);
             }
         }
         return cudaErrorInvalidValue;
@@ -72,7 +72,7 @@ int spec_warps(int dim, int Npad, bool mol, bool mixed, bool swaps) {
 bool chain_spec_supported(int dim, int model, int Npad, int threads, bool mol, bool mixed, bool swaps) {
     const int np = spec_npad(Npad);
     if (Npad > np || threads != 32 * spec_warps(dim, Npad, mol, mixed, swaps)) return false;
-    if (swaps && (mol || mixed || model == PMC_MODEL_KG)) return false;
+    if (swaps && (mixed || (!mol && model == PMC_MODEL_KG))) return false;
     if (mixed) return !mol && np <= 1024;
     if (mol) return dim == 3 && model == PMC_MODEL_KG;
     return np <= 2048;

@@ -111,13 +111,14 @@ __device__ __forceinline__ uint32_t pk_pos(uint32_t j) { return (j & ~127u) | ((
 // MOL = true: Molecules -- bonded partners (A.bonds, <= PMC_MAX_BONDS per site) are excluded from the pair pass and
 // contribute bond_potential (FENE + bonded LJ, src/models.jl:202-226) in a separate pass of the first lanes.
 // NPAD up to 4096: the survivor mask of a lane is NPAD / 1024 words.
-// SWAPS = true adds DiscreteSwap trials (src/moves.jl:137-214): positions fixed, four local energies in one pass over
+// SWAPS = true adds DiscreteSwap trials (src/moves.jl:137-214) and, with MOL, MoleculeFlip trials (src/moves.jl:291-352:
+// the species of two sites of one molecule exchanged): positions fixed, four local energies in one pass over
 // the survivors of two spheres; an accepted swap ends the round for later swaps (the species lists changed).
 template <int DIM, int MODEL, int NPAD, bool MIXED = false, bool MOL = false, int NW = 4, bool SWAPS = false>
 __global__ void __launch_bounds__(32 * NW, NPAD <= 1024 ? (NW == 8 ? 3 : (MIXED ? 8 : (MOL ? 5 : 6))) : (NW == 4 ? 4 : 2)) k_chain_sweep_spec(const __grid_constant__ ChainArgs A) {
     constexpr int NT = 32 * NW;
     static_assert(!(MIXED && MOL) && !(MIXED && NW != 4), "PMC_MIXED is implemented for Atoms, N <= 1024");
-    static_assert(!(SWAPS && (MIXED || MOL)), "DiscreteSwap pools: Atoms, fp64");
+    static_assert(!(SWAPS && MIXED), "DiscreteSwap / MoleculeFlip pools: fp64");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int KC = NPAD / 32;  // candidates per lane: k = 4 * c + e  <->  particle j = 128 * c + 4 * lane + e
     constexpr int NM = (KC + 31) / 32, KCW = KC < 32 ? KC : 32;  // mask words per lane, candidates per word
@@ -273,6 +274,7 @@ __global__ void __launch_bounds__(32 * NW, NPAD <= 1024 ? (NW == 8 ? 3 : (MIXED 
         if (pidx < nb) {
             const long long q = tb + pidx;
             pmc_trial tr;
+            unsigned long long flip_pairs = 0ull;  // MoleculeFlip: four parked candidate pairs (site offsets in the molecule)
             if (A.replay) {
                 tr = A.replay[(size_t)c * A.n_trials + q];
             } else {
@@ -297,6 +299,29 @@ __global__ void __launch_bounds__(32 * NW, NPAD <= 1024 ? (NW == 8 ? 3 : (MIXED 
                     tr.delta[0] = (double)(sg * z0);
                     tr.delta[1] = (double)(sg * z1);
                     tr.delta[2] = (DIM == 3) ? (double)(sg * z2) : 0.0;
+                } else if (MOL && tr.kind == PMC_MOVE_FLIP) {
+                    // MoleculeFlip (src/moves.jl:344-352): a molecule uniformly, then ordered pairs of distinct sites until
+                    // their species differ.  Species are only known when the trial is evaluated, so four candidate pairs
+                    // are parked (same draws as the general kernel, chains.cu); the first unlike one is taken.
+                    const int mol = A.n_mol > 0 ? (int)bounded(a.v[1], (uint32_t)A.n_mol) : 0;
+                    const int len = A.n_mol > 0 ? __ldg(A.mol_len + mol) : 0;
+                    tr.i = A.n_mol > 0 ? __ldg(A.mol_start + mol) : -1;
+                    tr.j = -1;
+                    const Philox4 c4 = philox4x32_10((uint32_t)t, (uint32_t)(t >> 32), gchain, 2u, k0, k1);
+                    const uint32_t w8[8] = {b.v[0], b.v[1], b.v[2], b.v[3], c4.v[0], c4.v[1], c4.v[2], c4.v[3]};
+                    unsigned long long packed = 0;
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; q4++) {
+                        uint32_t pa_ = 0, pb_ = 0;
+                        if (len >= 2) {
+                            pa_ = bounded(w8[2 * q4], (uint32_t)len);
+                            pb_ = bounded(w8[2 * q4 + 1], (uint32_t)(len - 1));
+                            pb_ += (pb_ >= pa_) ? 1u : 0u;
+                        }
+                        packed |= (unsigned long long)((pa_ & 0xFFu) | ((pb_ & 0xFFu) << 8)) << (16 * q4);
+                    }
+                    flip_pairs = len >= 2 && len <= 255 ? packed : 0ull;
+                    tr.delta[0] = tr.delta[1] = tr.delta[2] = 0.0;
                 } else {  // slots in the species lists; resolved to particles when the trial is evaluated
                     const int *sso = (const int *)(smem_raw + F.spoff);
                     const int nA = sso[A.mv_a[m] + 1] - sso[A.mv_a[m]], nB = sso[A.mv_b[m] + 1] - sso[A.mv_b[m]];
@@ -311,11 +336,11 @@ __global__ void __launch_bounds__(32 * NW, NPAD <= 1024 ? (NW == 8 ? 3 : (MIXED 
             double *rd = (double *)rec;
             int *ri = (int *)(rec + 32);
             uint32_t *rt = (uint32_t *)(rec + 64);
-            rd[0] = tr.delta[0];
+            rd[0] = (MOL && SWAPS && tr.kind == PMC_MOVE_FLIP && !A.replay) ? __longlong_as_double((long long)flip_pairs) : tr.delta[0];
             rd[1] = tr.delta[1];
             rd[2] = tr.delta[2];
             rd[3] = A.exact_exp ? tr.u : -Tk * log(tr.u);
-            ri[0] = (int)__double2ll_rn(tr.delta[0] * fscale);
+            ri[0] = (int)__double2ll_rn(tr.delta[0] * fscale);  // (delta is 0 for swaps and flips)
             ri[1] = (int)__double2ll_rn(tr.delta[1] * fscale);
             ri[2] = (int)__double2ll_rn(tr.delta[2] * fscale);
             ri[3] = tr.i;
@@ -346,11 +371,28 @@ __global__ void __launch_bounds__(32 * NW, NPAD <= 1024 ? (NW == 8 ? 3 : (MIXED 
                 if constexpr (SWAPS) {
                     int mv, kind, j, sab;
                     lds_s32x4(ra + 48, mv, kind, j, sab);
-                    if (kind == PMC_MOVE_SWAP) {
+                    if (kind == PMC_MOVE_SWAP || (MOL && kind == PMC_MOVE_FLIP)) {
                         is_swap = true;
-                        // ---- DiscreteSwap: positions fixed, four local energies in one pass (src/moves.jl:159-167) ----
+                        // ---- DiscreteSwap / MoleculeFlip: positions fixed, four local energies in one pass
+                        // (swap_particle_species!, src/moves.jl:159-167) ----
                         const uint32_t soa = sb + F.spoff;
-                        if (!A.replay && i >= 0) {  // slots -> particles through the species lists (current state)
+                        if (MOL && kind == PMC_MOVE_FLIP && !A.replay) {
+                            // the first parked pair whose sites carry different species NOW (src/moves.jl:347-350)
+                            const unsigned long long packed = (unsigned long long)__double_as_longlong(d0);
+                            const int base = i;
+                            i = -1;
+                            j = -1;
+                            if (packed != 0ull && base >= 0) {
+#pragma unroll
+                                for (int q4 = 3; q4 >= 0; q4--) {
+                                    const int sa_ = base + (int)((packed >> (16 * q4)) & 0xFFull), sb2 = base + (int)((packed >> (16 * q4 + 8)) & 0xFFull);
+                                    if (lds_u8(sb + F.sp + (uint32_t)sa_) != lds_u8(sb + F.sp + (uint32_t)sb2)) {
+                                        i = sa_;
+                                        j = sb2;
+                                    }
+                                }
+                            }
+                        } else if (!A.replay && i >= 0) {  // slots -> particles through the species lists (current state)
                             const uint32_t oa = lds_u32(soa + 4u * (uint32_t)(sab & 0xFF)), ob = lds_u32(soa + 4u * (uint32_t)(sab >> 8));
                             i = (int)lds_u16(sb + F.spids + 2u * (oa + (uint32_t)i));
                             j = (int)lds_u16(sb + F.spids + 2u * (ob + (uint32_t)j));
@@ -410,6 +452,14 @@ __global__ void __launch_bounds__(32 * NW, NPAD <= 1024 ? (NW == 8 ? 3 : (MIXED 
                                 return r2 <= p[PMC_P_RCUT2] ? pair_potential<MODEL>(p, r2) : 0.0;
                             }
                         };
+                        uint32_t bsi[PMC_MAX_BONDS], bsj[PMC_MAX_BONDS];  // MOL: bonded partners of i and of j (0xFFFF = none)
+                        if constexpr (MOL) {
+#pragma unroll
+                            for (int k = 0; k < PMC_MAX_BONDS; k++) {
+                                bsi[k] = (uint32_t)__ldg(A.bonds + (size_t)iu * PMC_MAX_BONDS + k);
+                                bsj[k] = (uint32_t)__ldg(A.bonds + (size_t)ju * PMC_MAX_BONDS + k);
+                            }
+                        }
                         auto sterm = [&](uint32_t k) -> double {
                             double t = 0.0;
                             if (k < (uint32_t)N) {
@@ -417,13 +467,21 @@ __global__ void __launch_bounds__(32 * NW, NPAD <= 1024 ? (NW == 8 ? 3 : (MIXED 
                                 const double xk0 = lds_f64(ka), xk1 = lds_f64(ka + nb8), xk2 = DIM == 3 ? lds_f64(ka + 2 * nb8) : 0.0;
                                 const uint32_t sk = lds_u8(sb + F.sp + k);
                                 const uint32_t skn = k == iu ? sj : (k == ju ? si : sk);  // species of k after the exchange
-                                if (k != iu) {  // k-term of particle i's local energy: (si, sk) -> (sj, sk')
+                                bool pair_i = k != iu, pair_j = k != ju;
+                                if constexpr (MOL) {  // bonded partners: bond pass below (they may lie outside both spheres)
+#pragma unroll
+                                    for (int b = 0; b < PMC_MAX_BONDS; b++) {
+                                        pair_i = pair_i && k != bsi[b];
+                                        pair_j = pair_j && k != bsj[b];
+                                    }
+                                }
+                                if (pair_i) {  // k-term of particle i's local energy: (si, sk) -> (sj, sk')
                                     double r2 = mi_acc(xi0, xk0, L, hL, 0.0);
                                     r2 = mi_acc(xi1, xk1, L, hL, r2);
                                     if constexpr (DIM == 3) r2 = mi_acc(xi2, xk2, L, hL, r2);
                                     t += pair_e(sj, skn, r2) - pair_e(si, sk, r2);
                                 }
-                                if (k != ju) {  // k-term of particle j's local energy: (sj, sk) -> (si, sk')
+                                if (pair_j) {  // k-term of particle j's local energy: (sj, sk) -> (si, sk')
                                     double r2 = mi_acc(xj0, xk0, L, hL, 0.0);
                                     r2 = mi_acc(xj1, xk1, L, hL, r2);
                                     if constexpr (DIM == 3) r2 = mi_acc(xj2, xk2, L, hL, r2);
@@ -457,6 +515,30 @@ __global__ void __launch_bounds__(32 * NW, NPAD <= 1024 ? (NW == 8 ? 3 : (MIXED 
                                     mm ^= 1u << b;
                                     part += sterm(cand_index<KCW>(b, lane) + 1024u * (uint32_t)mw);
                                 }
+                            }
+                        }
+                        if constexpr (MOL) {
+                            // bond pass: lanes 0..5 own the bonded partners of i, lanes 6..11 those of j (FENE + bonded LJ,
+                            // src/models.jl:219-226, with the species pair before and after the exchange)
+                            const bool of_j = lane >= PMC_MAX_BONDS;
+                            uint32_t b = 0xFFFFu;
+#pragma unroll
+                            for (int k = 0; k < PMC_MAX_BONDS; k++) {
+                                if (lane == k) b = bsi[k];
+                                if (lane == PMC_MAX_BONDS + k) b = bsj[k];
+                            }
+                            if (valid && lane < 2 * PMC_MAX_BONDS && b != 0xFFFFu) {
+                                const uint32_t ka = sb + F.x + 8u * b;
+                                const double xk0 = lds_f64(ka), xk1 = lds_f64(ka + nb8), xk2 = DIM == 3 ? lds_f64(ka + 2 * nb8) : 0.0;
+                                const uint32_t sk = lds_u8(sb + F.sp + b);
+                                const uint32_t skn = b == iu ? sj : (b == ju ? si : sk);
+                                double r2 = mi_acc(of_j ? xj0 : xi0, xk0, L, hL, 0.0);
+                                r2 = mi_acc(of_j ? xj1 : xi1, xk1, L, hL, r2);
+                                if constexpr (DIM == 3) r2 = mi_acc(of_j ? xj2 : xi2, xk2, L, hL, r2);
+                                const double *spar = (const double *)(smem_raw + F.par);
+                                const double *po = spar + ((of_j ? sj : si) * (uint32_t)ns + sk) * PMC_NPAR;
+                                const double *pn = spar + ((of_j ? si : sj) * (uint32_t)ns + skn) * PMC_NPAR;
+                                part += bond_potential(pn, r2) - bond_potential(po, r2);
                             }
                         }
                         const double dE = warp_sum(part);
@@ -737,11 +819,19 @@ __global__ void __launch_bounds__(32 * NW, NPAD <= 1024 ? (NW == 8 ? 3 : (MIXED 
                             if (flv & 2u) conflict = -1;
                         }
                         if constexpr (MOL) {
-                            // a bonded partner that moved changes the bond term even from outside the pair cutoff sphere
-                            // (FENE bonds reach r0 > rc): src/molecules.jl:160-176
+                            // a bonded partner that moved (or changed species) changes the bond term even from outside the
+                            // pair cutoff sphere (FENE bonds reach r0 > rc): src/molecules.jl:160-176.  A flip has two
+                            // particles on either side: iw / wr (= j of w) against iv / c_ (= j of v).
+                            const bool vswap = SWAPS && (flv & 2u) != 0u;
 #pragma unroll
-                            for (int k = 0; k < PMC_MAX_BONDS; k++)
-                                if ((uint32_t)__ldg(A.bonds + (size_t)iw * PMC_MAX_BONDS + k) == iv) conflict = -1;
+                            for (int k = 0; k < PMC_MAX_BONDS; k++) {
+                                const uint32_t bw = (uint32_t)__ldg(A.bonds + (size_t)iw * PMC_MAX_BONDS + k);
+                                if (bw == iv || (vswap && bw == c_)) conflict = -1;
+                                if (wswap) {
+                                    const uint32_t bw2 = (uint32_t)__ldg(A.bonds + (size_t)wr * PMC_MAX_BONDS + k);
+                                    if (bw2 == iv || (vswap && bw2 == c_)) conflict = -1;
+                                }
+                            }
                         }
                     }
                 }
