@@ -1,7 +1,13 @@
-python bench.py > gpurun_out/r02_bench_1gpu.json 2> gpurun_out/r02_bench_1gpu.err
-python bench.py --impl reference --steps 5 --warmup 3 > gpurun_out/r02_bench_reference.json 2>/dev/null
-python bench.py --workload chains --precision mixed --no-cpu-baseline > gpurun_out/r02_bench_mixed.json 2>/dev/null
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02_bench_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --equil 10 > gpurun_out/r02_launches.log 2>&1
-PMC_SPEC_QUEUE=0 ncu --set full --clock-control none --import-source on -k regex:k_chain_sweep_spec -s 3 -c 1 -o gpurun_out/r02_final_spec python bench.py --workload chains --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --sweeps 1 --equil 20 > gpurun_out/r02_final_spec.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_box_sweep_all -s 6 -c 1 -o gpurun_out/r02_final_box python bench.py --workload box --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --sweeps 1 --equil 5 > gpurun_out/r02_final_box.log 2>&1
-ls -la gpurun_out/*.ncu-rep | tail -3
+export PMC_BOX_TIMING=1
+timeout 900 python -m pytest tests/test_gpu_box.py tests/test_gpu_multirank.py tests/test_gpu_fullsize.py tests/test_gpu_edge.py tests/test_gpu_observables.py -x -q 2>&1 | grep -v "pmc box timing" | tail -12
+for v in prev default; do
+  lib=libpmc_b200_$v.so; [ $v = default ] && lib=libpmc_b200.so
+  for n in 1048576 131072; do
+  PMC_B200_LIB=$lib timeout 300 python bench.py --workload box --box-particles $n --no-cpu-baseline --no-e2e --steps 10 --warmup 3 > gpurun_out/ab14_${v}_$n.json 2>gpurun_out/ab14_${v}_$n.err; grep "pmc box timing" gpurun_out/ab14_${v}_$n.err
+  python - gpurun_out/ab14_${v}_$n.json <<'PY'
+import json,sys
+d=json.loads(open(sys.argv[1]).read().strip().split('\n')[-1])
+print(sys.argv[1], 'box %.4g ms/step %.4f'%(d['value'], d['ms_per_step']), d['checks'], d['roofline']['survivors_per_move'], d['roofline']['evaluations_per_move'])
+PY
+  done
+done
