@@ -562,3 +562,60 @@ def test_stretched_bonds_consecutive_trials_on_bonded_sites():
         fin = np.isfinite(o_dE)
         assert np.max(np.abs(o_dE[fin] - g_dE[0][fin]) / np.maximum(1.0, np.abs(o_dE[fin]))) < 1e-10
         assert rel(ctx.energy()[0], orc.energy) < 1e-10
+
+
+def test_trace_parity_small_molecules_flip_and_swap(molecule):
+    """The four-warp speculative kernel for Molecules with a pool that holds all three move kinds: Displacement,
+    MoleculeFlip (src/moves.jl:291-352) and DiscreteSwap (src/moves.jl:137-214) on 300 trimers -- every decision against
+    the oracle, species lists and per-molecule composition consistent afterwards."""
+    par = M.flatten_model_matrix(M.Trimer())
+    n = 900
+    pos = molecule["position"][:n].copy()
+    sp = molecule["species"][:n]
+    bonds = [[j for j in b if j <= n] for b in molecule["bonds"][:n]]
+    box = molecule["box"]
+    pool = [dict(kind="displacement", prob=0.5, sigma=0.06), dict(kind="flip", prob=0.3), dict(kind="swap", prob=0.2, species=(1, 3))]
+    with DeviceContext(2, n, 3, 3, M.MODEL_KG, molecules=True) as ctx:
+        ctx.set_model(par)
+        ctx.set_bonds(zero_based(bonds))
+        ctx.set_molecules(np.arange(0, n, 3), np.full(n // 3, 3))
+        ctx.upload(np.stack([pos, pos]), np.stack([sp, sp]), box, [2.0, 6.0])
+        ctx.init_energy()
+        ctx.set_moves(pool)
+        ctx.seed(123)
+        orcs = [O.OracleSystem(pos - np.floor(pos / box) * box, sp, box, T, M.MODEL_KG, par, O.LINKEDLIST,
+                               bonds=zero_based(bonds)) for T in (2.0, 6.0)]
+        tr, acc = check_trace(ctx, orcs, {0: (0, 0), 1: (0, 0), 2: (1, 3)}, 4000)
+        # every kind was drawn; flips are accepted now and then, swaps between molecules (they re-label bonds whose rest
+        # lengths differ by 10 %) practically never -- their energy changes are what check_trace compared
+        assert (tr["kind"] == 1).sum() > 500 and (tr["kind"] == 2).sum() > 800 and acc[tr["kind"] == 2].sum() > 0
+        fl = tr["kind"] == 2
+        assert np.all(tr["i"][fl] // 3 == tr["j"][fl] // 3) and np.all(tr["i"][fl] != tr["j"][fl])
+        _, spf = ctx.download()
+        assert np.array_equal(np.bincount(spf[0], minlength=4), np.bincount(sp, minlength=4))  # composition conserved
+        ctx.run(2000)  # the species lists written back by the traced launch feed the next one
+        e_run, e_tot = ctx.energy(), ctx.total_energy()
+        assert np.max(np.abs(e_run - e_tot) / np.abs(e_tot)) < 1e-10
+
+
+def test_work_counters_count_what_the_sweep_kernel_evaluates():
+    """pmc_work_counters (bench.py's roofline.frac_actual): candidates that reached the fp64 pass and trial evaluations,
+    counted on the device.  Evaluations >= trials (speculative rounds repeat a few), survivors per evaluation close to
+    the density x filter-sphere volume, nothing counted while switched off."""
+    N, n_chains, n_trials = 1000, 8, 4000
+    pos, sp, box = ka_config(N, 5)
+    with DeviceContext(n_chains, N, 3, 2, M.MODEL_LJ) as ctx:
+        ctx.set_model(M.flatten_model_matrix(M.KobAndersen()))
+        ctx.upload(np.stack([pos] * n_chains), np.stack([sp] * n_chains), box, 1.0)
+        ctx.init_energy()
+        ctx.set_moves([dict(kind="displacement", prob=1.0, sigma=0.05)])
+        ctx.seed(4)
+        ctx.run(n_trials)
+        assert ctx.work_counters(2) == (0, 0)
+        ctx.work_counters(1)
+        ctx.run(n_trials)
+        surv, evals = ctx.work_counters(0)
+        assert n_chains * n_trials <= evals < 1.25 * n_chains * n_trials
+        assert 60 < surv / evals < 120  # ~ 1.2 x 4/3 pi 2.6^3 = 88 for the A particles, fewer for B
+        ctx.run(n_trials)
+        assert ctx.work_counters(2) == (surv, evals)  # off again
