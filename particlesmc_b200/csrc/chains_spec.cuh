@@ -42,7 +42,8 @@ constexpr int kPubBytes = 64;                  // published result of one trial
 //   PMC_SPEC_ROTATE  the retiring warp and the proposal-generating warps rotate from round to round (warp w of every CTA
 //                    sits on SM sub-partition w % 4; measured +0.5 %).
 // Measured and dropped in round 2: minimum image / cutoff as predicated PTX (ptxas turns them back into selects, -1.4 %);
-// eight trials in flight at N = 1000 (6.6e8 vs 9.5e8 moves/s: longer rounds, more re-evaluated trials).
+// eight trials in flight at N = 1000 (6.6e8 vs 9.5e8 moves/s: longer rounds, more re-evaluated trials; equal at 512 chains per
+// GPU, +8 % only at 256); proposal generation spread over all four warps instead of two (-1.2 %: twice the instructions).
 #ifndef PMC_SPEC_ROTATE
 #define PMC_SPEC_ROTATE 1
 #endif
