@@ -43,7 +43,11 @@ constexpr int kPubBytes = 64;                  // published result of one trial
 //                    sits on SM sub-partition w % 4; measured +0.5 %).
 // Measured and dropped in round 2: minimum image / cutoff as predicated PTX (ptxas turns them back into selects, -1.4 %);
 // eight trials in flight at N = 1000 (6.6e8 vs 9.5e8 moves/s: longer rounds, more re-evaluated trials; equal at 512 chains per
-// GPU, +8 % only at 256); proposal generation spread over all four warps instead of two (-1.2 %: twice the instructions).
+// GPU, +8 % only at 256); proposal generation spread over all four warps instead of two (-1.2 %: twice the instructions);
+// keeping a conflicting trial by ADDING the four pair terms with the earlier accepted particle at retirement instead of
+// evaluating it again (exact, the pair energy is additive: evaluations per move 1.079 -> 1.001, but the in-order
+// decide / correct pass lengthens the serial section of every round: -5.6 %, and the bit-for-bit equality of split and
+// unsplit launches is lost to the rounding of the corrections).
 #ifndef PMC_SPEC_ROTATE
 #define PMC_SPEC_ROTATE 1
 #endif
