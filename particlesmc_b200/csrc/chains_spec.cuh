@@ -61,6 +61,11 @@ __device__ __forceinline__ void lds_u32x4(uint32_t a, uint32_t &v0, uint32_t &v1
 __device__ __forceinline__ void sts_u32x4(uint32_t a, uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3) {
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v0), "r"(v1), "r"(v2), "r"(v3) : "memory");
 }
+// shared-memory add without a generic pointer (a generic shared pointer makes the compiler re-derive the shared window,
+// S2R SR_CgaCtaId + LEA, in front of every use)
+__device__ __forceinline__ void reds_add_u32(uint32_t a, uint32_t v) {
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
 __device__ __forceinline__ void sts_f64x2(uint32_t a, double v0, double v1) {
     asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(v0), "d"(v1) : "memory");
 }
@@ -133,7 +138,16 @@ __global__ void __launch_bounds__(32 * NW, NPAD <= 1024 ? (NW == 8 ? 3 : (MIXED 
     const int N = A.N, gNpad = A.Npad, ns = A.ns;
     constexpr bool kFullPar = !MIXED && (MOL || !(MODEL == PMC_MODEL_LJ || MODEL == PMC_MODEL_KG));
     const SpecLayout F = spec_layout(DIM, Npad, kFullPar, MIXED, NW, SWAPS);
-    const uint32_t sb = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    uint32_t sb = (uint32_t)__cvta_generic_to_shared(smem_raw);
+#ifndef PMC_SPEC_PIN_BASE
+#define PMC_SPEC_PIN_BASE 1
+#endif
+#if PMC_SPEC_PIN_BASE
+    // keep the shared-window base in a register: left alone, the compiler re-derives it (S2R SR_CgaCtaId + LEA, tens of
+    // cycles of latency) in front of dependent stores on the serial path of every round (+2 %; PMC_MIXED, at its 64
+    // registers, measured 0.8 % slower with it)
+    if constexpr (!MIXED) asm volatile("" : "+r"(sb));
+#endif
     const uint32_t nb8 = 8u * (uint32_t)Npad;  // byte stride between coordinate planes (fp64)
     constexpr uint32_t nb4 = 4u * (uint32_t)NPAD;  // ... of the fixed-point planes (MIXED)
     const uint32_t tail = sb + F.pub + 2u * kPubBytes * NW;  // [0] retired count of the round, [4] work unit, [8] running energy
@@ -638,9 +652,8 @@ __global__ void __launch_bounds__(32 * NW, NPAD <= 1024 ? (NW == 8 ? 3 : (MIXED 
                     }
                     const int total = __shfl_sync(0xffffffffu, incl, 31);
                     if (A.stats && lane == 0) {
-                        uint32_t *c32 = (uint32_t *)(smem_raw + F.cnt32);
-                        atomicAdd(&c32[2 * PMC_MAX_MOVES], (uint32_t)total);
-                        atomicAdd(&c32[2 * PMC_MAX_MOVES + 1], 1u);
+                        reds_add_u32(sb + F.cnt32 + 4u * (2 * PMC_MAX_MOVES), (uint32_t)total);
+                        reds_add_u32(sb + F.cnt32 + 4u * (2 * PMC_MAX_MOVES + 1), 1u);
                     }
                     // Everything about this trial except its energy change is known here.  fp64: published now, off the
                     // critical path between the reduction and the barrier (dE and the decision follow after the pass; +1 %);
@@ -873,9 +886,8 @@ __global__ void __launch_bounds__(32 * NW, NPAD <= 1024 ? (NW == 8 ? 3 : (MIXED 
                     }
                 }
                 if (mine && sub == (4 % G)) {
-                    uint32_t *c32 = (uint32_t *)(smem_raw + F.cnt32);
-                    atomicAdd(&c32[mv], 1u);
-                    if (acc) atomicAdd(&c32[PMC_MAX_MOVES + mv], 1u);
+                    reds_add_u32(sb + F.cnt32 + 4u * mv, 1u);
+                    if (acc) reds_add_u32(sb + F.cnt32 + 4u * (PMC_MAX_MOVES + mv), 1u);
                     if (dbg_out) {
                         if (A.acc_out) A.acc_out[(size_t)c * A.n_trials + tb + cur + w] = acc ? 1 : 0;
                         if (A.dE_out) A.dE_out[(size_t)c * A.n_trials + tb + cur + w] = lds_f64(pw);
