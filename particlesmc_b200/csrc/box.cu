@@ -576,7 +576,10 @@ __global__ void __launch_bounds__(kBfThreads, 8) k_box_sweep_all(const __grid_co
     constexpr int NST = Stencil<DIM>::NST;
     const int CAP = FAST ? kBfThreads * KC : A.cap;
     const BfLayout F = bf_layout(DIM, CAP);
-    const uint32_t sb = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    uint32_t sb = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    // keep the shared-window base in a register: left alone, the compiler re-derives it (S2R SR_CgaCtaId + LEA, tens of
+    // cycles of latency) three times per trial, once right in front of the survivor loads
+    asm volatile("" : "+r"(sb));
     const uint32_t cap8 = 8u * (uint32_t)CAP;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double *sr = (double *)(smem_raw + F.r);
