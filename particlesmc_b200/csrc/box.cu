@@ -557,7 +557,11 @@ __device__ __forceinline__ void bf_sts_u8(uint32_t a, uint32_t v) { asm volatile
 // frame coordinate r in [-cs, 2cs) -> fixed point in [0, 3 * 2^30); its top byte (pack8) counts units of cs / 64
 // in [0, 192).  The moved particle and its trial position lie in the centre cell [64, 128), so no byte difference
 // reaches 128 and the signed-byte reading of VABSDIFF4 (common.cuh) never aliases in the frame.
-__device__ __forceinline__ uint32_t bf_fixed(double r, double cs, double scale) { return (uint32_t)__double2ull_rd((r + cs) * scale); }
+// (floor of the exact product in one DFMA.RM against 2^52, low mantissa word -- DMUL + F2I.U64.FLOOR costs more issue
+// slots and sits on the dependent path of every trial)
+__device__ __forceinline__ uint32_t bf_fixed(double r, double cs, double scale) {
+    return (uint32_t)__double2loint(__fma_rd(r + cs, scale, 4503599627370496.0));
+}
 
 // KC > 0: the trials are issued the way chains_fast.cuh does it -- 128 threads per active cell, every thread keeps the
 // packed 8-bit frame coordinates of its KC candidates in registers, one sphere test (midpoint of old/new, radius rc +
@@ -754,14 +758,19 @@ __global__ void __launch_bounds__(kBfThreads, 8) k_box_sweep_all(const __grid_co
                             const uint32_t v = __vabsdiffu4(umq, myq[kk]);
                             m = __funnelshift_l((uint32_t)__dp4a((int)v, (int)v, fthr), m, 1);
                         }
+                        // exclusive prefix of the per-lane survivor counts (<= KC each) from one ballot per count bit: the
+                        // ballots are independent, where a shuffle scan is five dependent steps on the path of every trial
                         const int mine = __popc(m);
-                        int incl = mine;
+                        constexpr int CB = KC < 4 ? 2 : (KC < 8 ? 3 : 4);  // bits of a count <= KC
+                        const uint32_t lt = (1u << lane) - 1u;
+                        int before = 0, total = 0;
 #pragma unroll
-                        for (int o = 1; o < 32; o <<= 1) {
-                            const int v = __shfl_up_sync(0xffffffffu, incl, o);
-                            incl += (lane >= o) ? v : 0;
+                        for (int b = 0; b < CB; b++) {
+                            const uint32_t bal = __ballot_sync(0xffffffffu, (mine >> b) & 1);
+                            before += __popc(bal & lt) << b;
+                            total += __popc(bal) << b;
                         }
-                        const int total = __shfl_sync(0xffffffffu, incl, 31);
+                        const int incl = before + mine;
                         if (A.stats && lane == 0) atomicAdd(&s_stat[0], (unsigned int)total);
                         if (A.stats && tid == 0) atomicAdd(&s_stat[1], 1u);
                         uint32_t wp = qa + 2u * (uint32_t)(incl - mine);
