@@ -649,7 +649,7 @@ __global__ void __launch_bounds__(kBfThreads, 8) k_box_sweep_all(const __grid_co
         }
         uint32_t myq[FAST ? KC : 1];  // packed 8-bit prefilter coordinates of this thread's candidates
 #pragma unroll
-        for (int k = 0; k < (FAST ? KC : 1); k++) myq[k] = 0u;
+        for (int k = 0; k < (FAST ? KC : 1); k++) myq[k] = 0x80000000u;  // empty slot: fourth byte 128 never passes the sphere test
         const int ncand = load_stencil<DIM, kBfThreads>(A, cc, &st, sr, ssp, CAP, [&](int t, uint32_t q) {
             if constexpr (FAST) {
 #pragma unroll
@@ -760,6 +760,7 @@ __global__ void __launch_bounds__(kBfThreads, 8) k_box_sweep_all(const __grid_co
                         }
                         // exclusive prefix of the per-lane survivor counts (<= KC each) from one ballot per count bit: the
                         // ballots are independent, where a shuffle scan is five dependent steps on the path of every trial
+                        if (tid == (k & (kBfThreads - 1))) m &= ~(1u << (KC - 1 - k / kBfThreads));  // the moved particle itself
                         const int mine = __popc(m);
                         constexpr int CB = KC < 4 ? 2 : (KC < 8 ? 3 : 4);  // bits of a count <= KC
                         const uint32_t lt = (1u << lane) - 1u;
@@ -782,10 +783,8 @@ __global__ void __launch_bounds__(kBfThreads, 8) k_box_sweep_all(const __grid_co
                             }
                         }
                         __syncwarp();
-                        for (int q = lane; q < total; q += 32) {
-                            const uint32_t j = bf_lds_u16(qa + 2u * (uint32_t)q);
-                            if (j < (uint32_t)ncand && j != (uint32_t)k) pair_terms(j);
-                        }
+                        // (empty slots and the moved particle left at the mask level: no test per survivor)
+                        for (int q = lane; q < total; q += 32) pair_terms(bf_lds_u16(qa + 2u * (uint32_t)q));
                         __syncwarp();
                     } else {
                         if (A.stats && tid == 0) {
