@@ -1,4 +1,4 @@
-timeout 900 python -m pytest tests/test_gpu_box.py tests/test_gpu_multirank.py -x -q 2>&1 | tail -3
+timeout 900 python -m pytest tests/test_gpu_box.py tests/test_gpu_multirank.py tests/test_gpu_observables.py tests/test_gpu_edge.py -x -q 2>&1 | tail -3
 for v in prev default; do
   lib=libpmc_b200_$v.so; [ $v = default ] && lib=libpmc_b200.so
   for n in 1048576 131072; do

@@ -372,7 +372,8 @@ struct Stencil {
 // byte coordinates of candidate t in the stencil frame (fast kernel: into the thread's registers).  Loads bypass L1:
 // inside a persistent kernel the sorted arrays change between the cells a CTA visits (own CTAs, other SMs, peer GPUs).
 template <int DIM, int NT, typename Sink>
-__device__ int load_stencil(const BoxArgs &A, const int (&cc)[3], Stencil<DIM> *st, double *sr, uint8_t *ssp, int cap, Sink &&sink) {
+__device__ int load_stencil(const BoxArgs &A, const int (&cc)[3], Stencil<DIM> *st, double *sr, uint8_t *ssp, uint8_t *cellof, int cap,
+                            Sink &&sink) {
     constexpr int NST = Stencil<DIM>::NST;
     const int tid = threadIdx.x;
     if (tid < NST) {
@@ -408,13 +409,14 @@ __device__ int load_stencil(const BoxArgs &A, const int (&cc)[3], Stencil<DIM> *
         if (tid == 0) atomicExch(A.overflow, 1);
         return -1;
     }
+    // stencil cell of every flat index, written once per cell (`cellof`: `cap` bytes of scratch) -- a binary search
+    // over the 3^d offsets per candidate is five dependent shared-memory loads in front of every global load
+    for (int s_ = tid >> 5; s_ < NST; s_ += NT >> 5)
+        for (int p_ = tid & 31; p_ < st->cnt[s_]; p_ += 32) cellof[st->off[s_] + p_] = (uint8_t)s_;
+    __syncthreads();
     const size_t ns_ = (size_t)A.g.nc[0] * A.plane_cap;
     for (int t = tid; t < nall; t += NT) {
-        int lo = 0, hi = NST;  // stencil cell of flat index t: binary search over the 3^d offsets
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (t >= st->off[mid]) lo = mid; else hi = mid;
-        }
+        const int lo = cellof[t];
         const int slot = st->base[lo] + (t - st->off[lo]);
 #pragma unroll
         for (int a = 0; a < DIM; a++) sr[a * cap + t] = __ldcg(A.rs + (size_t)a * ns_ + slot) + st->sh[lo][a];
@@ -459,7 +461,7 @@ __global__ void __launch_bounds__(kBoxThreads) k_box_energy(const __grid_constan
         cc[1] = l % A.g.nc[1];
         cc[0] = l / A.g.nc[1];
     }
-    const int ncand = load_stencil<DIM, kBoxThreads>(A, cc, &st, sr, ssp, A.cap, [](int, uint32_t) {});
+    const int ncand = load_stencil<DIM, kBoxThreads>(A, cc, &st, sr, ssp, ssp + A.cap, A.cap, [](int, uint32_t) {});
     if (ncand < 0) return;
     const int ncen = st.off[1], b = st.base[0];
     double wsum = 0.0;
@@ -650,7 +652,7 @@ __global__ void __launch_bounds__(kBfThreads, 8) k_box_sweep_all(const __grid_co
         uint32_t myq[FAST ? KC : 1];  // packed 8-bit prefilter coordinates of this thread's candidates
 #pragma unroll
         for (int k = 0; k < (FAST ? KC : 1); k++) myq[k] = 0x80000000u;  // empty slot: fourth byte 128 never passes the sphere test
-        const int ncand = load_stencil<DIM, kBfThreads>(A, cc, &st, sr, ssp, CAP, [&](int t, uint32_t q) {
+        const int ncand = load_stencil<DIM, kBfThreads>(A, cc, &st, sr, ssp, smem_raw + F.mv, CAP, [&](int t, uint32_t q) {
             if constexpr (FAST) {
 #pragma unroll
                 for (int k = 0; k < KC; k++)
@@ -915,7 +917,7 @@ __global__ void __launch_bounds__(kBoxThreads) k_box_pair_histogram(const __grid
         cc[1] = l % A.g.nc[1];
         cc[0] = l / A.g.nc[1];
     }
-    const int ncand = load_stencil<DIM, kBoxThreads>(A, cc, &st, sr, ssp, A.cap, [](int, uint32_t) {});
+    const int ncand = load_stencil<DIM, kBoxThreads>(A, cc, &st, sr, ssp, (uint8_t *)sid, A.cap, [](int, uint32_t) {});
     if (ncand < 0) return;
     // particle ids of the candidates (to count every unordered pair once: only id_i < id_j)
     for (int s = 0; s < Stencil<DIM>::NST; s++) {
