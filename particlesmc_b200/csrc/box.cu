@@ -415,7 +415,15 @@ __device__ int load_stencil(const BoxArgs &A, const int (&cc)[3], Stencil<DIM> *
         for (int p_ = tid & 31; p_ < st->cnt[s_]; p_ += 32) cellof[st->off[s_] + p_] = (uint8_t)s_;
     __syncthreads();
     const size_t ns_ = (size_t)A.g.nc[0] * A.plane_cap;
-    for (int t = tid; t < nall; t += NT) {
+    // thread (warp, lane) owns the candidates t = 32 * (lane / 8) + 8 * warp + lane % 8 (mod NT): runs of eight neighbouring
+    // candidates go to different warps, so the particles of one stencil cell -- inside a trial's filter sphere together or
+    // not at all; the centre cell always -- are shared out (with whole 32-runs per warp, warp 0 holds the centre cell alone
+    // and often needs a second pass over its survivors while the others wait at the block barrier).  Measured: +2.7 % where
+    // the sweep is bound by one cell's latency (N = 131072, a GPU's share of the box at 8 GPUs), -0.6 % at N = 2^20 (a
+    // warp's survivors sit on half of the banks); runs of 16: no effect either way; a stride-4 interleave: 13 % slower (a
+    // quarter of the banks).
+    for (int t = 32 * ((tid & 31) >> 3) + 8 * (tid >> 5) + (tid & 7); t < nall; t += NT) {
+        static_assert(NT == 128, "candidate interleave assumes four warps");
         const int lo = cellof[t];
         const int slot = st->base[lo] + (t - st->off[lo]);
 #pragma unroll
@@ -588,6 +596,7 @@ __global__ void __launch_bounds__(kBfThreads, 8) k_box_sweep_all(const __grid_co
     asm volatile("" : "+r"(sb));
     const uint32_t cap8 = 8u * (uint32_t)CAP;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ptid = 32 * (lane >> 3) + 8 * warp + (lane & 7);  // this thread owns candidates ptid, ptid + 128, ... (load_stencil)
     double *sr = (double *)(smem_raw + F.r);
     uint8_t *ssp = smem_raw + F.sp;
     const double *spar = (const double *)(smem_raw + F.par);
@@ -762,7 +771,7 @@ __global__ void __launch_bounds__(kBfThreads, 8) k_box_sweep_all(const __grid_co
                         }
                         // exclusive prefix of the per-lane survivor counts (<= KC each) from one ballot per count bit: the
                         // ballots are independent, where a shuffle scan is five dependent steps on the path of every trial
-                        if (tid == (k & (kBfThreads - 1))) m &= ~(1u << (KC - 1 - k / kBfThreads));  // the moved particle itself
+                        if (ptid == (k & (kBfThreads - 1))) m &= ~(1u << (KC - 1 - k / kBfThreads));  // the moved particle itself
                         const int mine = __popc(m);
                         constexpr int CB = KC < 4 ? 2 : (KC < 8 ? 3 : 4);  // bits of a count <= KC
                         const uint32_t lt = (1u << lane) - 1u;
@@ -780,7 +789,7 @@ __global__ void __launch_bounds__(kBfThreads, 8) k_box_sweep_all(const __grid_co
 #pragma unroll
                         for (int kk = 0; kk < KC; kk++) {
                             if (m & (1u << (KC - 1 - kk))) {
-                                bf_sts_u16(wp, (uint32_t)(kk * kBfThreads + tid));
+                                bf_sts_u16(wp, (uint32_t)(kk * kBfThreads + ptid));
                                 wp += 2;
                             }
                         }
@@ -813,7 +822,7 @@ __global__ void __launch_bounds__(kBfThreads, 8) k_box_sweep_all(const __grid_co
                         Esum += dE;
                         nacc++;
                         if constexpr (FAST) {
-                            if (tid == (k & (kBfThreads - 1))) {  // owner refreshes its register copy
+                            if (ptid == (k & (kBfThreads - 1))) {  // owner refreshes its register copy
                                 const int ki = k / kBfThreads;
                                 const uint32_t f = pack8(bf_fixed(xn[0], cs0, fscale), bf_fixed(xn[1], cs0, fscale), DIM == 3 ? bf_fixed(xn[2], cs0, fscale) : 0u);
 #pragma unroll
