@@ -123,7 +123,10 @@ struct BoxArgs {
 __device__ __forceinline__ bool wait_for(const volatile uint32_t *p, uint32_t want, int *error, bool at_least) {
     unsigned long long t0 = 0;
     for (unsigned spins = 0;; spins++) {
-        const uint32_t v = *p;
+        // acquire load at system scope: pairs with the fence + flag store of the CTA (or GPU) that produced the data, so
+        // that this thread's later loads -- and, through the barrier that follows every wait, its CTA's -- see that data
+        uint32_t v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
         if (at_least ? (int32_t)(v - want) >= 0 : v == want) return true;
         if (*(volatile int *)error == 3) return false;
         if ((spins & 1023u) == 1023u) {
