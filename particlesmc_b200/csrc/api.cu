@@ -946,7 +946,7 @@ int pmc_counters(pmc_ctx *c, int64_t *calls, int64_t *accepted) {
 
 int pmc_box_peer_export(pmc_ctx *c, uint8_t *handle) {
     if (!c || !handle) return fail(PMC_ERR_INVALID, "null argument");
-    if (c->cfg.mode != PMC_MODE_BOX) return fail(PMC_ERR_INVALID, "peer replicas exist only in PMC_MODE_BOX");
+    if (c->cfg.mode != PMC_MODE_BOX) return fail(PMC_ERR_INVALID, "peer attachment exists only in PMC_MODE_BOX");
     CU(cudaSetDevice(c->cfg.device));
     int rc = pmc::box_peer_export(c->boxst, handle);
     if (rc) return fail(rc, "%s", pmc::box_error());
@@ -955,7 +955,7 @@ int pmc_box_peer_export(pmc_ctx *c, uint8_t *handle) {
 
 int pmc_box_peer_attach(pmc_ctx *c, int32_t rank, int32_t world, const uint8_t *handles) {
     if (!c || !handles) return fail(PMC_ERR_INVALID, "null argument");
-    if (c->cfg.mode != PMC_MODE_BOX) return fail(PMC_ERR_INVALID, "peer replicas exist only in PMC_MODE_BOX");
+    if (c->cfg.mode != PMC_MODE_BOX) return fail(PMC_ERR_INVALID, "peer attachment exists only in PMC_MODE_BOX");
     CU(cudaSetDevice(c->cfg.device));
     int rc = pmc::box_peer_attach(c->boxst, rank, world, handles);
     if (rc) return fail(rc, "%s", pmc::box_error());

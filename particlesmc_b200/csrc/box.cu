@@ -2,8 +2,9 @@
 //
 // Reference counterparts
 //   cell list build      src/neighbours.jl:236-270 (LinkedList ctor + build_neighbour_list!)  -> K1:
-//                        bin -> prefix sum -> scatter -> per-cell canonical order (descending particle
-//                        id, the order head-insertion produces, neighbours.jl:257-268) + gather to SoA
+//                        bin -> prefix sum per x-plane of cells -> scatter -> per-cell canonical order
+//                        (descending particle id, the order head-insertion produces, neighbours.jl:257-268)
+//                        + gather of in-cell coordinates (fp64 and packed bytes) into the sorted arrays
 //   local / total energy src/atoms.jl:40-58, :81-88                                          -> K2
 //   Metropolis trial     src/moves.jl:57-90 + src/utils.jl:8-10                               -> K5
 // K5 has NO reference counterpart as an algorithm: the reference updates one particle at a time over
@@ -13,6 +14,10 @@
 // grid origin is shifted by a fresh random vector every sweep (Anderson et al., J. Comput. Phys. 254
 // (2013) 27), which keeps detailed balance per sub-sweep and restores ergodicity.  Parity with the
 // reference is therefore statistical for trajectories and exact (1e-12) for energies.
+// One sweep = 4 rebuild kernels + ONE persistent sweep kernel (all colours; a cell waits for the completion stamps of
+// its own neighbour cells, no barrier between the phases) + one deterministic reduction.  Over several GPUs the cell
+// grid is cut into x-slabs: a rank keeps cell lists for its slab plus a halo plane, sweeps its own cells and stores
+// accepted moves straight into its peers' memory (NVLink, CUDA IPC); flags chain the sweeps, nothing else does.
 #include "box.cuh"
 
 #include <algorithm>

@@ -1,15 +1,17 @@
-// chains_spec.cuh -- speculative sweep kernel for the dominant PMC_MODE_CHAINS case (Atoms, Displacement-only pool,
-// cubic box, N <= 1024): ONE WARP PER TRIAL, four consecutive trials of a chain in flight per round.
+// chains_spec.cuh -- speculative sweep kernel of PMC_MODE_CHAINS (cubic boxes; Atoms up to N = 2048 with Displacement and
+// DiscreteSwap pools, Molecules up to N = 4096 with Displacement / MoleculeFlip / DiscreteSwap pools, PMC_MIXED up to
+// N = 1024): ONE WARP PER TRIAL, four (N <= 1024) or eight consecutive trials of a chain in flight per round.
 //
 // k_chain_sweep_fast (chains_fast.cuh) spends one CTA on one trial: the four warps each scan a quarter of the
 // candidates, but everything around the scan -- record and position loads, wrapping, the compaction scan, the block
 // reduction, the barrier, the commit -- is replicated in all four warps, and the fp64 pass runs with ~21 of 32 lanes.
 // Here warp w of the CTA evaluates trial t + w of the SAME chain against the current state, alone: it scans all
 // candidates (32 per lane, packed 8-bit coordinates streamed from a shared-memory table), compacts the survivors into its own queue, runs
-// the fp64 pass at ~86 % lane utilisation and reduces with shuffles only.  After a barrier, warp 0 retires the four
-// results in trial order and publishes how many retired; a second barrier starts the next round (retiring in every
-// warp redundantly saves that barrier but costs 165 more instructions per move: measured 3 % slower; letting the warp
-// that arrives last retire the round behind a shared-memory arrival counter instead of the first barrier: 4 % slower):
+// the fp64 pass at ~86 % lane utilisation and reduces with shuffles only.  After a barrier, ONE warp retires the four
+// results and publishes how many retired -- all trials of the round at once, a group of lanes per trial, because this
+// serial section is what bounds the kernel; a second barrier starts the next round (retiring in every warp redundantly
+// saves that barrier but costs 165 more instructions per move: measured 3 % slower; letting the warp that arrives last
+// retire the round behind a shared-memory arrival counter instead of the first barrier: 4 % slower):
 //
 //   trial t+w stands  <=>  no earlier trial of this round was ACCEPTED with its particle inside the filter sphere of
 //                          t+w, tested on the old AND the new position with the very 8-bit test the scan uses.

@@ -210,7 +210,7 @@ class DeviceContext:
         L.check(self.lib.pmc_counters(self._h, _lp(calls), _lp(acc)))
         return calls, acc
 
-    # -- multi-GPU replicas of one large box ---------------------------------------------------------------
+    # -- one large box over several GPUs (slabs of the cell grid, halo pushes over NVLink peer memory) -----------
     def box_peer_handle(self) -> np.ndarray:
         h = np.zeros(64, dtype=np.uint8)
         L.check(self.lib.pmc_box_peer_export(self._h, h.ctypes.data_as(C.POINTER(C.c_uint8))))

@@ -42,7 +42,7 @@ def gather_chain_values(local: np.ndarray, n_chains: int):
 
 
 def attach_box_peers(ctx) -> None:
-    """Multi-GPU single box: all-gather the 64-byte CUDA IPC handles of every rank's replica (host channel:
+    """Multi-GPU single box: all-gather the 64-byte CUDA IPC handles of every rank's shared block (host channel:
     torch.distributed, any backend) and attach them.  Call on every rank after ``ctx.upload``; collective."""
     import torch
     import torch.distributed as dist

@@ -1,5 +1,5 @@
-"""Multi-rank single box: W ranks, each holding a replica and sweeping 1/W of every colour's active
-cells, pushing accepted moves into the peers' replicas through CUDA-IPC peer memory, must reproduce the
+"""Multi-rank single box: W ranks, each sweeping its slab of the cell grid (1/W of every colour's active
+cells) and pushing accepted moves into the peers' memory through CUDA-IPC peer mappings, must reproduce the
 single-rank run BIT FOR BIT (same-colour cells never interact, RNG is keyed by cell).  Runs with 2 processes; on a
 single-GPU box both ranks share cuda:0 (peer memory over IPC works the same, only slower)."""
 import os
