@@ -24,6 +24,8 @@
 // speculation costs is the re-evaluated trials (about 3 % per pair of trials at 35 % acceptance: 3.7 of 4 trials
 // retire per round).
 #pragma once
+#include <type_traits>
+
 #include "chains.cuh"
 #include "chains_fast.cuh"
 #include "common.cuh"
@@ -247,6 +249,7 @@ __global__ void __launch_bounds__(32 * NW, NPAD <= 1024 ? (NW == 8 ? 3 : (MIXED 
                 double rc2 = 0.0;
                 for (int k = 0; k < ns * ns; k++) rc2 = fmax(rc2, A.par[k * PMC_NPAR + PMC_P_RCUT2]);
                 ((uint32_t *)sso)[PMC_MAX_SPECIES + 1] = neg_thr8(sqrt(rc2) * fscale * 0x1p-24);
+                *(double *)(smem_raw + F.spoff + 24) = sqrt(rc2) * fscale * 0x1p-24;  // the same radius in byte units
             }
         }
         if (tid < PMC_MAX_SPECIES) {  // largest cutoff radius per species of the moved particle (filter sphere)
@@ -272,6 +275,11 @@ __global__ void __launch_bounds__(32 * NW, NPAD <= 1024 ? (NW == 8 ? 3 : (MIXED 
     const bool dbg_out = A.acc_out != nullptr || A.dE_out != nullptr;
 
     uint32_t rnd = 0;  // rounds so far: selects the retiring warp
+    // species lists are only read by DiscreteSwap proposals (and by replayed ones); MoleculeFlip pools skip their upkeep
+    bool keep_lists = A.replay != nullptr, lists_dirty = false;
+    if constexpr (SWAPS) {
+        for (int k = 0; k < A.n_moves; k++) keep_lists = keep_lists || A.mv_kind[k] == PMC_MOVE_SWAP;
+    }
     for (long long tb = seg_lo; tb < seg_hi; tb += kSpecBatch) {
         const int nb = (int)min((long long)kSpecBatch, seg_hi - tb);
         __syncthreads();
@@ -429,30 +437,54 @@ __global__ void __launch_bounds__(32 * NW, NPAD <= 1024 ? (NW == 8 ? 3 : (MIXED 
                         constexpr int NCHUNK = KCW / 4, NCH = NCHUNK >= 4 ? 4 : NCHUNK, CG = NCHUNK / NCH;
                         uint32_t m[NM];
                         int mine = 0;
+                        // survivors of either sphere (TWO = true), or of the one sphere qc / cthr that contains both
+                        auto scan = [&](auto two, uint32_t qc, int cthr) {
 #pragma unroll
-                        for (int mw = 0; mw < NM; mw++) {
-                            uint32_t mc[NCH];
+                            for (int mw = 0; mw < NM; mw++) {
+                                uint32_t mc[NCH];
 #pragma unroll
-                            for (int h = 0; h < NCH; h++) mc[h] = 0u;
+                                for (int h = 0; h < NCH; h++) mc[h] = 0u;
 #pragma unroll
-                            for (int cc = 0; cc < CG; cc++) {
+                                for (int cc = 0; cc < CG; cc++) {
 #pragma unroll
-                                for (int h = 0; h < NCH; h++) {
-                                    uint32_t w4[4];
-                                    lds_u32x4(pka + 512u * (uint32_t)(mw * 8 + h * CG + cc), w4[0], w4[1], w4[2], w4[3]);
+                                    for (int h = 0; h < NCH; h++) {
+                                        uint32_t w4[4];
+                                        lds_u32x4(pka + 512u * (uint32_t)(mw * 8 + h * CG + cc), w4[0], w4[1], w4[2], w4[3]);
 #pragma unroll
-                                    for (int e = 0; e < 4; e++) {  // survivor of either sphere
-                                        const uint32_t t1 = __vabsdiffu4(qi, w4[e]), t2 = __vabsdiffu4(qj, w4[e]);
-                                        const int v = __dp4a((int)t1, (int)t1, gthr) | __dp4a((int)t2, (int)t2, gthr);
-                                        mc[h] = __funnelshift_l((uint32_t)v, mc[h], 1);
+                                        for (int e = 0; e < 4; e++) {
+                                            const uint32_t t1 = __vabsdiffu4(qc, w4[e]);
+                                            int v = __dp4a((int)t1, (int)t1, cthr);
+                                            if constexpr (decltype(two)::value) {
+                                                const uint32_t t2 = __vabsdiffu4(qj, w4[e]);
+                                                v |= __dp4a((int)t2, (int)t2, cthr);
+                                            }
+                                            mc[h] = __funnelshift_l((uint32_t)v, mc[h], 1);
+                                        }
                                     }
                                 }
-                            }
-                            uint32_t mm = mc[0];
+                                uint32_t mm = mc[0];
 #pragma unroll
-                            for (int h = 1; h < NCH; h++) mm = (mm << (4 * CG)) | mc[h];
-                            m[mw] = valid ? mm : 0u;
-                            mine += __popc(m[mw]);
+                                for (int h = 1; h < NCH; h++) mm = (mm << (4 * CG)) | mc[h];
+                                m[mw] = valid ? mm : 0u;
+                                mine += __popc(m[mw]);
+                            }
+                        };
+                        bool one_sphere = false;
+                        if constexpr (MOL) one_sphere = kind == PMC_MOVE_FLIP;
+                        if (one_sphere) {
+                            // MoleculeFlip: the two sites sit a bond length apart, so ONE sphere around their midpoint with
+                            // radius rc_max + |x_i - x_j| / 2 holds everything within rc_max of either (triangle inequality)
+                            // at half the scan instructions; the midpoint and the half distance come from the wrapping
+                            // 32-bit fixed-point difference (minimum image for free), like a Displacement's
+                            const uint32_t ui0 = to_fixed32(xi0, fscale), ui1 = to_fixed32(xi1, fscale), ui2 = DIM == 3 ? to_fixed32(xi2, fscale) : 0u;
+                            const int e0 = (int)(to_fixed32(xj0, fscale) - ui0), e1 = (int)(to_fixed32(xj1, fscale) - ui1);
+                            const int e2 = DIM == 3 ? (int)(to_fixed32(xj2, fscale) - ui2) : 0;
+                            const double hd = 0.5 * sqrt((double)e0 * (double)e0 + (double)e1 * (double)e1 + (double)e2 * (double)e2) * 0x1p-24;
+                            const double rcu = lds_f64(soa + 24);
+                            scan(std::false_type{}, pack8(ui0 + (uint32_t)(e0 >> 1), ui1 + (uint32_t)(e1 >> 1), ui2 + (uint32_t)(e2 >> 1)),
+                                 (int)neg_thr8(rcu + hd + 0x1p-20));
+                        } else {
+                            scan(std::true_type{}, qi, gthr);
                         }
                         int incl = mine;
 #pragma unroll
@@ -912,6 +944,14 @@ __global__ void __launch_bounds__(32 * NW, NPAD <= 1024 ? (NW == 8 ? 3 : (MIXED 
                         sw &= sw - 1u;
                         const uint32_t is_ = __shfl_sync(0xffffffffu, iw, src), js_ = __shfl_sync(0xffffffffu, wr, src);
                         const uint32_t si = lds_u8(sb + F.sp + is_), sj = lds_u8(sb + F.sp + js_);
+                        if (!keep_lists) {  // no DiscreteSwap in the pool: nobody reads the lists in this launch
+                            lists_dirty = true;
+                            if (lane == 0) {
+                                asm volatile("st.shared.u8 [%0], %1;" ::"r"(sb + F.sp + is_), "r"(sj) : "memory");
+                                asm volatile("st.shared.u8 [%0], %1;" ::"r"(sb + F.sp + js_), "r"(si) : "memory");
+                            }
+                            continue;
+                        }
                         const uint32_t oi = lds_u32(sb + F.spoff + 4u * si), oj = lds_u32(sb + F.spoff + 4u * sj);
                         const uint32_t ni = lds_u32(sb + F.spoff + 4u * si + 4u) - oi, nj = lds_u32(sb + F.spoff + 4u * sj + 4u) - oj;
                         auto find = [&](uint32_t off, uint32_t n, uint32_t who) -> uint32_t {
@@ -959,6 +999,27 @@ __global__ void __launch_bounds__(32 * NW, NPAD <= 1024 ? (NW == 8 ? 3 : (MIXED 
             uint16_t *gi = A.spids + (size_t)c * gNpad, *gh = A.heads + (size_t)c * gNpad;
             const uint16_t *si_ = (const uint16_t *)(smem_raw + F.spids);
             const int *sso = (const int *)(smem_raw + F.spoff);
+            if constexpr (MOL) {
+                // accepted flips of a pool without DiscreteSwap left the lists alone (the reference's Molecules carry
+                // none, src/molecules.jl:24-41): rebuild them from the species, ids ascending per species as at upload,
+                // so that a later pool with DiscreteSwap finds them consistent.  Counts per species are unchanged.
+                if (__syncthreads_or(lists_dirty ? 1 : 0)) {
+                    if (warp == 0) {
+                        uint16_t *wl = (uint16_t *)(smem_raw + F.spids);
+                        for (int sp_ = 0; sp_ < ns; sp_++) {
+                            int pos = sso[sp_];
+                            for (int b0 = 0; b0 < N; b0 += 32) {
+                                const int k = b0 + lane;
+                                const bool f = k < N && smem_raw[F.sp + k] == (unsigned char)sp_;
+                                const unsigned bal = __ballot_sync(0xffffffffu, f);
+                                if (f) wl[pos + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)k;
+                                pos += __popc(bal);
+                            }
+                        }
+                    }
+                    __syncthreads();
+                }
+            }
             for (int k = tid; k < gNpad; k += NT) {
                 gsp[k] = smem_raw[F.sp + k];
                 gi[k] = si_[k];

@@ -598,6 +598,55 @@ def test_trace_parity_small_molecules_flip_and_swap(molecule):
         assert np.max(np.abs(e_run - e_tot) / np.abs(e_tot)) < 1e-10
 
 
+def test_flip_only_pool_leaves_species_lists_usable_for_later_swaps(molecule):
+    """A pool without DiscreteSwap does not keep the species lists up to date while it runs (the reference's Molecules
+    carry none, src/molecules.jl:24-41); the kernel rebuilds them from the species when it leaves, ids ascending per
+    species as at upload.  Phase 1: Displacement + MoleculeFlip against the oracle.  Phase 2: a pool WITH DiscreteSwap --
+    the slots its Philox stream draws must name the particles that an oracle built from the downloaded phase-1 state
+    (lists in index order) resolves them to."""
+    par = M.flatten_model_matrix(M.Trimer())
+    n = 900
+    pos = molecule["position"][:n].copy()
+    sp = molecule["species"][:n]
+    bonds = [[j for j in b if j <= n] for b in molecule["bonds"][:n]]
+    box = molecule["box"]
+    seed, T, n1, n2 = 77, 4.0, 3000, 1500
+    with DeviceContext(1, n, 3, 3, M.MODEL_KG, molecules=True) as ctx:
+        ctx.set_model(par)
+        ctx.set_bonds(zero_based(bonds))
+        ctx.set_molecules(np.arange(0, n, 3), np.full(n // 3, 3))
+        ctx.upload(pos[None], sp[None], box, T)
+        ctx.init_energy()
+        ctx.set_moves([dict(kind="displacement", prob=0.5, sigma=0.06), dict(kind="flip", prob=0.5)])
+        ctx.seed(seed)
+        orc = O.OracleSystem(pos - np.floor(pos / box) * box, sp, box, T, M.MODEL_KG, par, O.LINKEDLIST, bonds=zero_based(bonds))
+        tr, acc = check_trace(ctx, [orc], {0: (0, 0), 1: (0, 0)}, n1)
+        assert acc[0][tr[0]["kind"] == 2].sum() > 50  # accepted flips: the lists of phase 2 depend on them
+        pos1, sp1 = ctx.download()
+        assert not np.array_equal(sp1[0], sp)
+        ctx.set_moves([dict(kind="displacement", prob=0.5, sigma=0.06), dict(kind="swap", prob=0.5, species=(1, 3))])
+        tr2, acc2, _ = ctx.run_traced(n2)
+    counts = np.bincount(sp1[0], minlength=4)
+    key = (seed & 0xFFFFFFFF, seed >> 32)
+    p1 = pos1[0] - np.floor(pos1[0] / box) * box
+    orc2 = O.OracleSystem(p1, sp1[0], box, T, M.MODEL_KG, par, O.LINKEDLIST, bonds=zero_based(bonds))
+    n_swaps = 0
+    for t in range(n2):
+        r = tr2[0, t]
+        if r["kind"] == 0:
+            a, _, _ = orc2.step_displacement(r["i"], r["delta"], r["u"], 0)
+        else:
+            blkA = O.philox4x32_10((n1 + t, 0, 0, 0), key)
+            blkB = O.philox4x32_10((n1 + t, 0, 0, 1), key)
+            ka = (int(blkA[1]) * int(counts[1])) >> 32
+            kb = (int(blkB[0]) * int(counts[3])) >> 32
+            a, i, j, _, _ = orc2.step_swap_draw(1, 3, ka, kb, r["u"], 0)
+            assert (i, j) == (int(r["i"]), int(r["j"])), f"trial {t}: slots ({ka}, {kb}) name other particles"
+            n_swaps += 1
+        assert a == bool(acc2[0, t]), f"trial {t}"
+    assert n_swaps > 500
+
+
 def test_work_counters_count_what_the_sweep_kernel_evaluates():
     """pmc_work_counters (bench.py's roofline.frac_actual): candidates that reached the fp64 pass and trial evaluations,
     counted on the device.  Evaluations >= trials (speculative rounds repeat a few), survivors per evaluation close to
