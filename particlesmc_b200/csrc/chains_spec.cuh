@@ -946,6 +946,7 @@ __global__ void __launch_bounds__(32 * NW, NPAD <= 1024 ? (NW == 8 ? 3 : (MIXED 
                         const uint32_t si = lds_u8(sb + F.sp + is_), sj = lds_u8(sb + F.sp + js_);
                         if (!keep_lists) {  // no DiscreteSwap in the pool: nobody reads the lists in this launch
                             lists_dirty = true;
+                            __syncwarp();  // every lane has read the two species before lane 0 exchanges them
                             if (lane == 0) {
                                 asm volatile("st.shared.u8 [%0], %1;" ::"r"(sb + F.sp + is_), "r"(sj) : "memory");
                                 asm volatile("st.shared.u8 [%0], %1;" ::"r"(sb + F.sp + js_), "r"(si) : "memory");
