@@ -69,7 +69,12 @@ enum pmc_precision {
 };
 
 /* src/moves.jl: Displacement :34 (+SimpleGaussian :105), DiscreteSwap :137 (+DoubleUniform :226),
- * MoleculeFlip :291 (+DoubleUniform :336-352): species exchange between two unlike sites of one molecule */
+ * MoleculeFlip :291 (+DoubleUniform :336-352): species exchange between two unlike sites of one molecule.
+ * The per-species id lists behind DiscreteSwap (SpeciesList, src/utils.jl:31-49) follow every accepted swap as
+ * update_species_list! does (:175-179).  Molecules carry no such list in the reference; here DiscreteSwap on Molecules
+ * is an extension: a pool with MoleculeFlip and DiscreteSwap exchanges the two list entries of an accepted flip in
+ * place, a pool without DiscreteSwap leaves the lists alone and rebuilds them (ids ascending per species, as at
+ * upload) when pmc_run returns. */
 enum pmc_move_kind { PMC_MOVE_DISPLACEMENT = 0, PMC_MOVE_SWAP = 1, PMC_MOVE_FLIP = 2 };
 
 typedef struct pmc_ctx pmc_ctx;
