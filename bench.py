@@ -19,7 +19,8 @@ One "step" = one pass of the hot path over the whole batch: every chain advanced
   e2e        the same metric through the C ABI with HOST buffers: every step uploads all states from pinned host
              memory (pmc_upload + pmc_init_energy), runs the sweeps and downloads energies and full states
              (pmc_energy + pmc_download).  The chains are held by --e2e-contexts library contexts on separate
-             streams, so one context's copies overlap another's sweeps (same chains, same bytes).
+             streams, staggered so that one context's copies overlap the others' sweeps (same chains, same bytes,
+             every step's upload and download inside the timed region; each download feeds the next upload).
   roofline   pair-evaluation roofline of the sweep kernel (FP64 CUDA-core pipe):
                frac         reference-equivalent: moves/s x P x F with P = candidate pairs the REFERENCE evaluates per
                             move and F flops per pair, over the DFMA burst peak measured in this run
@@ -80,7 +81,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-strong", action="store_true")
     ap.add_argument("--cpu-sweeps", type=int, default=600)
-    ap.add_argument("--e2e-contexts", type=int, default=4,
+    ap.add_argument("--e2e-contexts", type=int, default=8,
                     help="chains workload, e2e leg: the chains are held by this many library contexts on separate streams, so "
                          "that one context's host<->device copies overlap another's sweeps (1 = a single context)")
     return ap.parse_args()
@@ -343,7 +344,11 @@ def measure(env, args, kind, Mc, strong_chains=False):
     # ---- end to end through the C ABI with host buffers -------------------------------------------------
     e2e = None
     if not args.no_e2e:
-        K = args.e2e_contexts if (not box_mode and args.e2e_contexts > 1 and Mc % args.e2e_contexts == 0) else 1
+        K = 1
+        if not box_mode:
+            K = max(1, args.e2e_contexts)
+            while K > 1 and (Mc % K != 0 or Mc // K < 128):  # at least 128 chains per context
+                K //= 2
         parts = []
         if K > 1:
             # the same chains (same global indices, same seed) split over K contexts with their own streams: while one
@@ -370,24 +375,30 @@ def measure(env, args, kind, Mc, strong_chains=False):
                 c.set_moves([dict(kind="displacement", prob=1.0, sigma=0.05)])
                 c.seed(42)
 
-            def e2e_step():
-                for c, st, o in parts:
-                    up(c, o)
-                    c.run(trials_per_step, sync=False)
+            # Every step, every context: upload its chains, sweep, download them (the next step's upload reads what
+            # this step's download wrote: the state round-trips through the host).  The contexts are staggered: while
+            # one is copying, the others sweep -- context k's download of step s is followed at once by its upload and
+            # launch of step s + 1, so the pipeline fills and drains once per e2e_steps() call, not once per step.
+            def e2e_steps(n):
+                for s in range(n):
+                    for c, st, o in parts:
+                        if s > 0:
+                            down(c, o)
+                        up(c, o)
+                        c.run(trials_per_step, sync=False)
                 for c, st, o in parts:
                     down(c, o)
         else:
-            def e2e_step():
-                upload()
-                ctx.run(trials_per_step, sync=False)
-                download()
-        for _ in range(2):
-            e2e_step()
+            def e2e_steps(n):
+                for _ in range(n):
+                    upload()
+                    ctx.run(trials_per_step, sync=False)
+                    download()
+        e2e_steps(2)
         barrier()
         t0 = time.perf_counter()
         ev[0].record()
-        for _ in range(args.steps):
-            e2e_step()
+        e2e_steps(args.steps)
         ev[1].record()
         barrier()
         wall_ms = (time.perf_counter() - t0) * 1e3
